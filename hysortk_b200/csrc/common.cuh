@@ -1,0 +1,153 @@
+// Shared definitions of the hysortk_b200 CUDA engine (sm_100a).
+//
+// Data contract (reference include/kmer.hpp:165-185, src/dnaseq.cpp:9-31):
+//   * reads: 4 bases per byte, first base in bits 7..6, codes A0 C1 G2 T3, each read on a fresh byte
+//   * k-mer: base i in word i/32 at bits 2*(31 - i%32)+1..; word 0 most significant; unused low bits 0
+//   * canonical k-mer = min(forward, reverse complement) under word-0-first comparison
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hsk {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+constexpr int MAX_WORDS = 3;
+
+struct Planes {           // key planes of one k-mer array: p[w][i] = word w of k-mer i
+    u64 *p[MAX_WORDS];
+};
+
+__host__ __device__ __forceinline__ int nwords_for_k(int k) { return k <= 32 ? 1 : (k <= 64 ? 2 : 3); }
+
+// ---- bit helpers -----------------------------------------------------------------------------
+
+// reverse complement of 32 bases held in a u64 (base 0 in the top bits): complement every base and
+// reverse the base order.
+__host__ __device__ __forceinline__ u64 revcomp64(u64 x)
+{
+    x = ~x;
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+    x = ((x >> 8) & 0x00ff00ff00ff00ffull) | ((x & 0x00ff00ff00ff00ffull) << 8);
+    x = ((x >> 16) & 0x0000ffff0000ffffull) | ((x & 0x0000ffff0000ffffull) << 16);
+    x = (x >> 32) | (x << 32);
+#endif
+    // the bit reversal also swapped the two bits of every base; swap them back
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
+// Reverse complement of a K-mer held in NW words (layout above).  Restates the effect of the
+// reference's Kmer::GetTwin (include/kmer.hpp:265-296) with bit reversal instead of its tetramer table.
+template <int NW>
+__host__ __device__ __forceinline__ void kmer_twin(const u64 (&in)[NW], int k, u64 (&out)[NW])
+{
+    u64 t[NW];
+#pragma unroll
+    for (int l = 0; l < NW; ++l) t[NW - 1 - l] = revcomp64(in[l]);
+    const int shift = 2 * (32 * NW - k);   // left-align: 0..62
+    if (shift == 0) {
+#pragma unroll
+        for (int l = 0; l < NW; ++l) out[l] = t[l];
+    } else {
+#pragma unroll
+        for (int l = 0; l < NW; ++l) {
+            u64 v = t[l] << shift;
+            if (l + 1 < NW) v |= t[l + 1] >> (64 - shift);
+            out[l] = v;
+        }
+    }
+}
+
+// canonical representative (reference Kmer::GetRep, include/kmer.hpp:298-303; operator< :216-229)
+template <int NW>
+__host__ __device__ __forceinline__ void kmer_canonical(u64 (&w)[NW], int k)
+{
+    u64 t[NW];
+    kmer_twin<NW>(w, k, t);
+    bool less = false, decided = false;
+#pragma unroll
+    for (int l = 0; l < NW; ++l) {
+        if (!decided && t[l] != w[l]) { less = t[l] < w[l]; decided = true; }
+    }
+    if (less) {
+#pragma unroll
+        for (int l = 0; l < NW; ++l) w[l] = t[l];
+    }
+}
+
+// 32-bit hash of a canonical m-mer value (right-aligned, <= 64 bits).  The choice of hash only
+// decides which bucket counts a k-mer (reference uses MurmurHash3, supermer.hpp:307-313); the
+// result of kmer_count does not depend on it.
+__host__ __device__ __forceinline__ u32 mmer_hash(u64 x)
+{
+    u32 lo = (u32)x, hi = (u32)(x >> 32);
+    u32 h = lo * 0x9E3779B1u;
+    h ^= (hi + 0x7F4A7C15u) * 0x85EBCA77u;
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+
+// bucket of a minimizer hash among nb buckets.  The minimum of a window of hashes is a small number
+// (its top bits are almost always zero), so it is re-scrambled by an odd multiplier before the
+// multiplicative range reduction; the reference takes hash % tot_tasks (kmerops.cpp:1044-1047).
+__host__ __device__ __forceinline__ u32 hash_bucket(u32 h, u32 nb)
+{
+    h *= 0x9E3779B1u;
+    h ^= h >> 15;
+    return (u32)(((u64)h * nb) >> 32);
+}
+
+// ---- extraction geometry ---------------------------------------------------------------------
+// A tile covers EX_TSK k-mer start slots of the flat slot space (slot = 2 bits of the packed
+// buffer, padding slots included) and computes EX_TS m-mer hashes (halo for the minimizer window).
+constexpr int EX_THREADS = 256;
+constexpr int EX_R = 16;                       // consecutive slots per thread
+constexpr int EX_TS = EX_THREADS * EX_R;       // 4096 hash slots per tile
+constexpr int EX_HALO = 128;                   // >= K - M (window - 1), multiple of 64
+constexpr int EX_TSK = EX_TS - EX_HALO;        // 3968 k-mer slots per tile (992 bytes, 16-byte multiple)
+constexpr int EX_TILE_BYTES = EX_TSK / 4;      // 992
+constexpr int EX_WORDS = EX_TS / 16 + 4;       // 260 big-endian 32-bit words of bases staged per tile
+constexpr u32 EX_INVALID = 0xFFFFu;
+constexpr int MAX_BUCKETS = 8192;
+
+// ---- radix geometry --------------------------------------------------------------------------
+constexpr int RS_THREADS = 384;
+constexpr int RS_IPT = 16;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 6144 keys per tile
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_MAX_PASSES = 24;
+
+struct PassDesc { int plane; int shift; };
+struct PassTable { int npasses; PassDesc d[RS_MAX_PASSES]; };
+
+// LSD pass schedule over the significant bits of a k-mer of size k: 8-bit digits, never
+// straddling a word; the last word's unused low bits are skipped.
+inline PassTable make_pass_table(int k)
+{
+    PassTable t;
+    t.npasses = 0;
+    int nw = nwords_for_k(k);
+    for (int pl = nw - 1; pl >= 0; --pl) {
+        int bases = (pl == nw - 1) ? (k - 32 * (nw - 1)) : 32;
+        int low = 64 - 2 * bases;
+        for (int s = low; s < 64; s += 8) {
+            t.d[t.npasses].plane = pl;
+            t.d[t.npasses].shift = s;
+            ++t.npasses;
+        }
+    }
+    return t;
+}
+
+} // namespace hsk

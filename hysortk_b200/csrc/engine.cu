@@ -1,0 +1,750 @@
+// C-ABI engine (include/hsk_capi.h): context, buffers, stage orchestration, supermer exchange.
+//
+// Replaces the body of the reference's hysortk::kmer_count (src/hysortk.cpp:36-95):
+//   prepare_supermer  (kmerops.cpp:23-126)   -> extract.cu   (count pass, bucket scan, scatter pass)
+//   exchange_supermer (kmerops.cpp:130-195)  -> grouped ncclSend/ncclRecv of whole bucket ranges
+//                                               (TaskManager::exchange 80 KB rounds, :814-1007)
+//   filter_kmer       (kmerops.cpp:198-250)  -> per batch of buckets: expand.cu, radix.cu, count.cu
+// The reference's task system (TaskManager, classifier, dispatcher) has no equivalent here: buckets
+// are owned by rank in contiguous ranges and processed in batches sized for HBM.
+#include "../../include/hsk_capi.h"
+#include "kernels.cuh"
+
+#include <nccl.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace hsk;
+
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) return fail("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+// NCCL is bound at run time (dlopen) and only when a context spans more than one rank: a single-GPU
+// caller needs no NCCL at all, and inside a process that already loaded an NCCL (e.g. PyTorch's
+// bundled copy) the same library instance is reused instead of a second, older one being pulled in.
+namespace {
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+}
+
+static int load_nccl()
+{
+    if (g_nccl.ok) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail("cannot load libnccl.so.2: %s", dlerror());
+#define HSK_SYM(field, name)                                                            \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, #name));           \
+    if (!g_nccl.field) return fail("libnccl: missing symbol %s", #name)
+    HSK_SYM(GetUniqueId, ncclGetUniqueId);
+    HSK_SYM(CommInitRank, ncclCommInitRank);
+    HSK_SYM(CommDestroy, ncclCommDestroy);
+    HSK_SYM(AllGather, ncclAllGather);
+    HSK_SYM(AllReduce, ncclAllReduce);
+    HSK_SYM(Send, ncclSend);
+    HSK_SYM(Recv, ncclRecv);
+    HSK_SYM(GroupStart, ncclGroupStart);
+    HSK_SYM(GroupEnd, ncclGroupEnd);
+    HSK_SYM(GetErrorString, ncclGetErrorString);
+#undef HSK_SYM
+    g_nccl.ok = true;
+    return 0;
+}
+
+#define NK(call)                                                                                        \
+    do {                                                                                                \
+        ncclResult_t r_ = (call);                                                                       \
+        if (r_ != ncclSuccess) return fail("%s:%d: %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 16 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {   // page-locked
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 16 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct EvPair { cudaEvent_t a, b; };
+
+} // namespace
+
+struct hsk_ctx {
+    hsk_config cfg;
+    int nwords = 1, m_eff = 0;
+    u32 tg = 0, tt = 0;   // buckets per rank / total
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    ncclComm_t comm = nullptr;
+    int sm_count = 148;
+
+    // input staging (hsk_count)
+    DevBuf d_packed, d_read_off, d_read_len;
+    HostBuf h_read_off, h_read_len;
+    // extraction
+    DevBuf d_cta_totals, d_bucket;   // d_bucket: [kmers T][count T][words T][start T+1][wstart T+1] u64
+    HostBuf h_bucket;
+    DevBuf d_len, d_words, d_ext;
+    // exchange
+    DevBuf d_alltot, d_rlen, d_rwords, d_rext;
+    HostBuf h_alltot;
+    // batch buffers
+    DevBuf d_keys[2][MAX_WORDS], d_val[2], d_rscratch, d_cscratch, d_tsum, d_tbase;
+    // result arena
+    DevBuf d_owords, d_ocnt, d_oocc_off, d_opos, d_orid, d_hist, d_cursor;
+    HostBuf h_cursor, h_owords, h_ocnt, h_oocc_off, h_opos, h_orid, h_hist;
+    u64 n_kept = 0, n_occ = 0;
+    bool have_result = false;
+    hsk_stats stats;
+
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<EvPair> ev_extract, ev_exchange, ev_expand, ev_sort, ev_count;
+
+    cudaEvent_t ev()
+    {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
+    EvPair begin(std::vector<EvPair> &v)
+    {
+        EvPair p{ev(), ev()};
+        cudaEventRecord(p.a, stream);
+        v.push_back(p);
+        return p;
+    }
+    void end(std::vector<EvPair> &v) { cudaEventRecord(v.back().b, stream); }
+    static float sum_ms(const std::vector<EvPair> &v)
+    {
+        float t = 0;
+        for (auto &p : v) { float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b); t += ms; }
+        return t;
+    }
+};
+
+extern "C" {
+
+const char *hsk_last_error(void) { return g_err.c_str(); }
+int hsk_version(void) { return HSK_VERSION; }
+
+int hsk_get_unique_id(void *id_out)
+{
+    static_assert(sizeof(ncclUniqueId) <= HSK_NCCL_ID_BYTES, "nccl id size");
+    ncclUniqueId id;
+    if (load_nccl()) return 1;
+    NK(g_nccl.GetUniqueId(&id));
+    memset(id_out, 0, HSK_NCCL_ID_BYTES);
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+int hsk_create(hsk_ctx **out, const hsk_config *cfg)
+{
+    if (!out || !cfg) return fail("hsk_create: null argument");
+    if (!(cfg->k > 2 && cfg->k < 96)) return fail("hsk_create: KMER_SIZE must satisfy 2 < k < 96 (got %d)", cfg->k);
+    if (!(cfg->m > 0 && cfg->m < cfg->k)) return fail("hsk_create: MINIMIZER_SIZE must satisfy 0 < m < k (got %d)", cfg->m);
+    if (!(cfg->lower > 0 && cfg->lower <= cfg->upper && cfg->upper <= 65535))
+        return fail("hsk_create: need 0 < LOWER <= UPPER <= 65535 (got %d, %d)", cfg->lower, cfg->upper);
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail("hsk_create: bad rank/nranks");
+    if (cfg->nranks > 1 && !cfg->nccl_id) return fail("hsk_create: nccl_id required when nranks > 1");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("hsk_create: device %d not present (%d devices)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail("hsk_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    hsk_ctx *c = new hsk_ctx;
+    c->cfg = *cfg;
+    c->cfg.nccl_id = nullptr;
+    c->nwords = nwords_for_k(cfg->k);
+    c->m_eff = std::min(cfg->m, 32);
+    if (cfg->k - c->m_eff > EX_HALO - 1) c->m_eff = cfg->k - (EX_HALO - 1);
+    c->sm_count = prop.multiProcessorCount;
+    u32 tg = cfg->buckets_per_rank > 0 ? (u32)cfg->buckets_per_rank : 256u;
+    if ((u64)tg * cfg->nranks > MAX_BUCKETS) tg = MAX_BUCKETS / cfg->nranks;
+    if (tg < 1) { delete c; return fail("hsk_create: too many ranks for %d buckets", MAX_BUCKETS); }
+    c->tg = tg;
+    c->tt = tg * (u32)cfg->nranks;
+    if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
+    else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail("cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        c->own_stream = true;
+    }
+    if (cfg->nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, cfg->nccl_id, sizeof(id));
+        if (load_nccl()) { delete c; return 1; }
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, cfg->nranks, id, cfg->rank);
+        if (r != ncclSuccess) { delete c; return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    }
+    memset(&c->stats, 0, sizeof(c->stats));
+    *out = c;
+    return 0;
+}
+
+void hsk_destroy(hsk_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_cta_totals, &c->d_bucket, &c->d_len, &c->d_words,
+                    &c->d_ext, &c->d_alltot, &c->d_rlen, &c->d_rwords, &c->d_rext, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
+                    &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
+                    &c->d_hist, &c->d_cursor};
+    for (auto *b : db) b->release();
+    for (int h = 0; h < 2; ++h) for (int w = 0; w < MAX_WORDS; ++w) c->d_keys[h][w].release();
+    HostBuf *hb[] = {&c->h_read_off, &c->h_read_len, &c->h_bucket, &c->h_alltot, &c->h_cursor, &c->h_owords, &c->h_ocnt,
+                     &c->h_oocc_off, &c->h_opos, &c->h_orid, &c->h_hist};
+    for (auto *b : hb) b->release();
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---- extraction (stages 1+2) -------------------------------------------------------------------------
+// On return h_bucket holds [kmers T][count T][words T][start T+1][wstart T+1] and d_len/d_words/d_ext
+// the bucket-major supermer streams.
+static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
+                       const u32 *d_read_len, u64 nreads, int readid_base)
+{
+    const u32 T = c->tt;
+    cudaStream_t s = c->stream;
+    ExtractParams P;
+    P.packed = d_packed; P.nbytes = nbytes; P.nbytes_padded = nbytes_padded;
+    P.read_off = d_read_off; P.read_len = d_read_len; P.nreads = nreads;
+    P.ntiles = (nbytes + EX_TILE_BYTES - 1) / EX_TILE_BYTES;
+    u32 nctas = (u32)std::min<u64>(std::max<u64>(P.ntiles, 1), (u64)c->sm_count * 4);
+    P.tiles_per_cta = (P.ntiles + nctas - 1) / nctas;
+    P.k = c->cfg.k; P.m = c->m_eff; P.nbuckets = T; P.readid_base = readid_base;
+    if (P.tiles_per_cta * (u64)EX_TSK >= (1ull << 31)) return fail("input too large for one rank (%llu bytes)", (unsigned long long)nbytes);
+
+    const size_t bucket_u64 = 3 * (size_t)T + 2 * ((size_t)T + 1);
+    CK(c->d_cta_totals.ensure((size_t)nctas * T * sizeof(uint2)));
+    CK(c->d_bucket.ensure(bucket_u64 * 8));
+    CK(c->h_bucket.ensure(bucket_u64 * 8));
+    u64 *d_kmers = c->d_bucket.as<u64>();
+    u64 *d_count = d_kmers + T, *d_wordsn = d_count + T, *d_start = d_wordsn + T, *d_wstart = d_start + T + 1;
+    CK(cudaMemsetAsync(d_kmers, 0, bucket_u64 * 8, s));
+
+    c->begin(c->ev_extract);
+    CK(launch_supermer_count(P, nctas, c->d_cta_totals.as<uint2>(), d_kmers, s));
+    CK(launch_bucket_scan(c->d_cta_totals.as<uint2>(), nctas, T, d_count, d_wordsn, d_start, d_wstart, s));
+    CK(cudaMemcpyAsync(c->h_bucket.p, c->d_bucket.p, bucket_u64 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const u64 *h_start = c->h_bucket.as<u64>() + 3 * (size_t)T;
+    const u64 *h_wstart = h_start + T + 1;
+    const u64 S = h_start[T], W = h_wstart[T];
+    CK(c->d_len.ensure((S + 8) * sizeof(u16)));
+    CK(c->d_words.ensure((W + 8) * sizeof(u32)));
+    if (c->cfg.ext) CK(c->d_ext.ensure((S + 8) * sizeof(u64)));
+    CK(launch_supermer_scatter(P, nctas, c->cfg.ext != 0, c->d_cta_totals.as<uint2>(), d_start, d_wstart, c->d_len.as<u16>(),
+                               c->d_words.as<u32>(), c->d_ext.as<u64>(), s));
+    c->end(c->ev_extract);
+    c->stats.n_launches += 3;
+    c->stats.n_supermers = S;
+    c->stats.supermer_bytes = S * (2 + (c->cfg.ext ? 8 : 0)) + W * 4;
+    u64 nk = 0;
+    for (u32 b = 0; b < T; ++b) nk += c->h_bucket.as<u64>()[b];
+    c->stats.n_kmers_local = nk;
+    return 0;
+}
+
+// ---- the whole path on device-resident reads -------------------------------------------------------
+static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
+                        const u32 *d_read_len, u64 nreads, int readid_base)
+{
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    const u32 T = c->tt, TG = c->tg;
+    const int G = c->cfg.nranks, me = c->cfg.rank;
+    const int NW = c->nwords;
+    const bool ext = c->cfg.ext != 0;
+    c->ev_used = 0;
+    c->ev_extract.clear(); c->ev_exchange.clear(); c->ev_expand.clear(); c->ev_sort.clear(); c->ev_count.clear();
+    hsk_stats keep = c->stats;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.ms_h2d = keep.ms_h2d;
+    c->have_result = false;
+    cudaEvent_t ev_t0 = c->ev(), ev_t1 = c->ev();
+    CK(cudaEventRecord(ev_t0, s));
+
+    if (run_extract(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base)) return 1;
+    const u64 *hb = c->h_bucket.as<u64>();
+    const u64 *h_kmers = hb, *h_count = hb + T, *h_wordsn = hb + 2 * (size_t)T, *h_start = hb + 3 * (size_t)T,
+              *h_wstart = h_start + T + 1;
+
+    // ---- totals of every source rank for every bucket: tot[src][3][T] (kmers, count, words)
+    std::vector<u64> tot((size_t)G * 3 * T);
+    if (G == 1) {
+        memcpy(tot.data(), hb, (size_t)3 * T * 8);
+    } else {
+        CK(c->d_alltot.ensure((size_t)G * 3 * T * 8));
+        CK(c->h_alltot.ensure((size_t)G * 3 * T * 8));
+        c->begin(c->ev_exchange);
+        NK(g_nccl.AllGather(c->d_bucket.p, c->d_alltot.p, (size_t)3 * T, ncclUint64, c->comm, s));
+        CK(cudaMemcpyAsync(c->h_alltot.p, c->d_alltot.p, (size_t)G * 3 * T * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        memcpy(tot.data(), c->h_alltot.p, (size_t)G * 3 * T * 8);
+    }
+    auto TK = [&](int src, u32 b) { return tot[((size_t)src * 3 + 0) * T + b]; };
+    auto TC = [&](int src, u32 b) { return tot[((size_t)src * 3 + 1) * T + b]; };
+    auto TW = [&](int src, u32 b) { return tot[((size_t)src * 3 + 2) * T + b]; };
+    const u32 b_lo = (u32)me * TG, b_hi = b_lo + TG;
+
+    // ---- stage 3: supermer all-to-all (whole bucket ranges, one grouped send/recv per peer)
+    std::vector<u64> rbase_idx(G, 0), rbase_w(G, 0);
+    if (G > 1) {
+        u64 ri = 0, rw = 0;
+        for (int src = 0; src < G; ++src) {
+            if (src == me) continue;
+            rbase_idx[src] = ri; rbase_w[src] = rw;
+            for (u32 b = b_lo; b < b_hi; ++b) { ri += TC(src, b); rw += TW(src, b); }
+        }
+        CK(c->d_rlen.ensure((ri + 8) * sizeof(u16)));
+        CK(c->d_rwords.ensure((rw + 8) * sizeof(u32)));
+        if (ext) CK(c->d_rext.ensure((ri + 8) * sizeof(u64)));
+        NK(g_nccl.GroupStart());
+        for (int peer = 0; peer < G; ++peer) {
+            if (peer == me) continue;
+            const u32 p_lo = (u32)peer * TG, p_hi = p_lo + TG;
+            const u64 si = h_start[p_lo], sn = h_start[p_hi] - h_start[p_lo];
+            const u64 sw = h_wstart[p_lo], swn = h_wstart[p_hi] - h_wstart[p_lo];
+            u64 rn = 0, rwn = 0;
+            for (u32 b = b_lo; b < b_hi; ++b) { rn += TC(peer, b); rwn += TW(peer, b); }
+            if (sn) NK(g_nccl.Send(c->d_len.as<u16>() + si, sn * 2, ncclUint8, peer, c->comm, s));
+            if (rn) NK(g_nccl.Recv(c->d_rlen.as<u16>() + rbase_idx[peer], rn * 2, ncclUint8, peer, c->comm, s));
+            if (swn) NK(g_nccl.Send(c->d_words.as<u32>() + sw, swn, ncclUint32, peer, c->comm, s));
+            if (rwn) NK(g_nccl.Recv(c->d_rwords.as<u32>() + rbase_w[peer], rwn, ncclUint32, peer, c->comm, s));
+            if (ext) {
+                if (sn) NK(g_nccl.Send(c->d_ext.as<u64>() + si, sn, ncclUint64, peer, c->comm, s));
+                if (rn) NK(g_nccl.Recv(c->d_rext.as<u64>() + rbase_idx[peer], rn, ncclUint64, peer, c->comm, s));
+            }
+            c->stats.bytes_sent += sn * (2 + (ext ? 8 : 0)) + swn * 4;
+            c->stats.bytes_received += rn * (2 + (ext ? 8 : 0)) + rwn * 4;
+        }
+        NK(g_nccl.GroupEnd());
+        c->end(c->ev_exchange);
+    }
+
+    // ---- batches of owned buckets
+    u64 owned = 0, max_bucket = 0;
+    std::vector<u64> bk(TG, 0);
+    for (u32 b = b_lo; b < b_hi; ++b) {
+        u64 kk = 0;
+        for (int src = 0; src < G; ++src) kk += TK(src, b);
+        bk[b - b_lo] = kk; owned += kk; max_bucket = std::max(max_bucket, kk);
+    }
+    c->stats.n_kmers_owned = owned;
+    u64 cap = c->cfg.batch_kmers ? c->cfg.batch_kmers : (1ull << 28);
+    cap = std::min<u64>(cap, (1ull << 29) - 1);
+    if (max_bucket > (1ull << 29) - 1)
+        return fail("a minimizer bucket holds %llu k-mers (> 2^29-1); raise buckets_per_rank", (unsigned long long)max_bucket);
+    struct Batch { u32 b0, b1; u64 n; };
+    std::vector<Batch> batches;
+    {
+        u32 b0 = b_lo; u64 acc = 0;
+        for (u32 b = b_lo; b < b_hi; ++b) {
+            u64 kk = bk[b - b_lo];
+            if (acc > 0 && acc + kk > cap) { batches.push_back({b0, b, acc}); b0 = b; acc = 0; }
+            acc += kk;
+        }
+        if (acc > 0) batches.push_back({b0, b_hi, acc});
+    }
+    u64 max_batch = 0, max_seg_sup = 0;
+    for (auto &bt : batches) {
+        max_batch = std::max(max_batch, bt.n);
+        for (int src = 0; src < G; ++src) {
+            u64 ns = 0;
+            for (u32 b = bt.b0; b < bt.b1; ++b) ns += TC(src, b);
+            max_seg_sup = std::max(max_seg_sup, ns);
+        }
+    }
+    c->stats.n_batches = batches.size();
+
+    // ---- buffers
+    for (int h = 0; h < 2; ++h) {
+        for (int w = 0; w < NW; ++w) CK(c->d_keys[h][w].ensure((max_batch + 8) * 8));
+        if (ext) CK(c->d_val[h].ensure((max_batch + 8) * 8));
+    }
+    CK(c->d_rscratch.ensure(radix_scratch_bytes(max_batch)));
+    CK(c->d_cscratch.ensure(count_scratch_bytes(max_batch)));
+    const u64 seg_tiles = (max_seg_sup + XP_TILE - 1) / XP_TILE + 1;
+    CK(c->d_tsum.ensure(seg_tiles * sizeof(uint2)));
+    CK(c->d_tbase.ensure(seg_tiles * sizeof(ulonglong2)));
+    const u64 arena = owned / (u64)c->cfg.lower + 8;
+    CK(c->d_owords.ensure(arena * NW * 8));
+    CK(c->d_ocnt.ensure(arena * 4));
+    if (ext) {
+        CK(c->d_oocc_off.ensure((arena + 1) * 8));
+        CK(c->d_opos.ensure((owned + 8) * 4));
+        CK(c->d_orid.ensure((owned + 8) * 4));
+    }
+    const size_t hist_bins = (size_t)c->cfg.upper + 1;
+    CK(c->d_hist.ensure(hist_bins * 8));
+    CK(c->d_cursor.ensure(16));
+    CK(c->h_cursor.ensure(16));
+    CK(cudaMemsetAsync(c->d_hist.p, 0, hist_bins * 8, s));
+    CK(cudaMemsetAsync(c->d_cursor.p, 0, 16, s));
+
+    // ---- per batch: expand -> sort -> count/filter
+    // idx/word start of bucket b inside source src's stream
+    std::vector<u64> seg_i((size_t)G * (TG + 1)), seg_w((size_t)G * (TG + 1));
+    for (int src = 0; src < G; ++src) {
+        u64 ai = (src == me) ? h_start[b_lo] : rbase_idx[src];
+        u64 aw = (src == me) ? h_wstart[b_lo] : rbase_w[src];
+        for (u32 b = b_lo; b <= b_hi; ++b) {
+            seg_i[(size_t)src * (TG + 1) + (b - b_lo)] = ai;
+            seg_w[(size_t)src * (TG + 1) + (b - b_lo)] = aw;
+            if (b < b_hi) { ai += TC(src, b); aw += TW(src, b); }
+        }
+    }
+    (void)h_count; (void)h_wordsn; (void)h_kmers;
+    for (auto &bt : batches) {
+        Planes A, B;
+        for (int w = 0; w < MAX_WORDS; ++w) { A.p[w] = w < NW ? c->d_keys[0][w].as<u64>() : nullptr; B.p[w] = w < NW ? c->d_keys[1][w].as<u64>() : nullptr; }
+        u64 *VA = ext ? c->d_val[0].as<u64>() : nullptr, *VB = ext ? c->d_val[1].as<u64>() : nullptr;
+
+        c->begin(c->ev_expand);
+        u64 out_base = 0;
+        for (int src = 0; src < G; ++src) {
+            const u64 i0 = seg_i[(size_t)src * (TG + 1) + (bt.b0 - b_lo)], i1 = seg_i[(size_t)src * (TG + 1) + (bt.b1 - b_lo)];
+            const u64 w0 = seg_w[(size_t)src * (TG + 1) + (bt.b0 - b_lo)];
+            if (i1 == i0) continue;
+            ExpandSegment seg;
+            const bool local = (src == me);
+            seg.len = (local ? c->d_len.as<u16>() : c->d_rlen.as<u16>()) + i0;
+            seg.words = (local ? c->d_words.as<u32>() : c->d_rwords.as<u32>()) + w0;
+            seg.ext = ext ? ((local ? c->d_ext.as<u64>() : c->d_rext.as<u64>()) + i0) : nullptr;
+            seg.nsup = i1 - i0;
+            seg.out_base = out_base;
+            CK(launch_expand(seg, c->cfg.k, NW, ext, c->d_tsum.as<uint2>(), c->d_tbase.as<ulonglong2>(), A, VA, s));
+            c->stats.n_launches += 3;
+            for (u32 b = bt.b0; b < bt.b1; ++b) out_base += TK(src, b);
+        }
+        c->end(c->ev_expand);
+        if (out_base != bt.n) return fail("internal: batch k-mer count mismatch (%llu vs %llu)", (unsigned long long)out_base, (unsigned long long)bt.n);
+
+        c->begin(c->ev_sort);
+        bool in_b = false; int np = 0, nl = 0;
+        CK(launch_radix_sort(A, B, VA, VB, bt.n, NW, c->cfg.k, c->d_rscratch.p, &in_b, &np, &nl, s));
+        c->end(c->ev_sort);
+        c->stats.n_sort_passes = (u64)np;
+        c->stats.n_launches += (u64)nl;
+
+        c->begin(c->ev_count);
+        CountParams CP;
+        CP.keys = in_b ? B : A;
+        CP.val = ext ? (in_b ? VB : VA) : nullptr;
+        CP.n = bt.n; CP.nwords = NW; CP.lower = (u32)c->cfg.lower; CP.upper = (u32)c->cfg.upper;
+        CP.out_words = c->d_owords.as<u64>(); CP.out_cnt = c->d_ocnt.as<u32>();
+        CP.out_occ_off = c->d_oocc_off.as<u64>(); CP.out_pos = c->d_opos.as<u32>(); CP.out_rid = c->d_orid.as<int>();
+        CP.histogram = c->d_hist.as<u64>(); CP.cursor = c->d_cursor.as<u64>();
+        CK(launch_count_filter(CP, c->d_cscratch.p, s));
+        c->end(c->ev_count);
+        c->stats.n_launches += 3;
+    }
+
+    CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ev_t1, s));
+    CK(cudaStreamSynchronize(s));
+    c->n_kept = c->h_cursor.as<u64>()[0];
+    c->n_occ = c->h_cursor.as<u64>()[1];
+    if (ext) {   // closing offset of the occurrence lists
+        CK(cudaMemcpyAsync(c->d_oocc_off.as<u64>() + c->n_kept, c->h_cursor.as<u64>() + 1, 8, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    c->stats.ms_extract = hsk_ctx::sum_ms(c->ev_extract);
+    c->stats.ms_exchange = hsk_ctx::sum_ms(c->ev_exchange);
+    c->stats.ms_expand = hsk_ctx::sum_ms(c->ev_expand);
+    c->stats.ms_sort = hsk_ctx::sum_ms(c->ev_sort);
+    c->stats.ms_count = hsk_ctx::sum_ms(c->ev_count);
+    CK(cudaEventElapsedTime(&c->stats.ms_total, ev_t0, ev_t1));
+    c->have_result = true;
+    return 0;
+}
+
+static void fill_device_result(hsk_ctx *c, hsk_device_result *out)
+{
+    out->nwords = c->nwords;
+    out->n_kept = c->n_kept;
+    out->n_occ = c->n_occ;
+    out->d_kmer_words = c->d_owords.as<uint64_t>();
+    out->d_cnt = c->d_ocnt.as<u32>();
+    out->d_occ_off = c->cfg.ext ? c->d_oocc_off.as<uint64_t>() : nullptr;
+    out->d_pos = c->cfg.ext ? c->d_opos.as<u32>() : nullptr;
+    out->d_rid = c->cfg.ext ? c->d_orid.as<int32_t>() : nullptr;
+    out->d_histogram = c->d_hist.as<uint64_t>();
+    out->stats = c->stats;
+}
+
+int hsk_count_device(hsk_ctx *c, const uint8_t *d_packed, uint64_t nbytes, const uint64_t *d_read_off,
+                     const uint32_t *d_read_len, uint64_t nreads, int32_t readid_base, hsk_device_result *out)
+{
+    if (!c || !out) return fail("hsk_count_device: null argument");
+    if (((uintptr_t)d_packed & 15) != 0) return fail("hsk_count_device: d_packed must be 16-byte aligned");
+    c->stats.ms_h2d = 0;
+    if (count_device(c, d_packed, nbytes, (nbytes + 15) & ~15ull, (const u64 *)d_read_off, d_read_len, nreads, readid_base)) return 1;
+    fill_device_result(c, out);
+    return 0;
+}
+
+int hsk_fetch_result(hsk_ctx *c, hsk_result *out)
+{
+    if (!c || !out) return fail("hsk_fetch_result: null argument");
+    if (!c->have_result) return fail("hsk_fetch_result: no result on this context");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    const int NW = c->nwords;
+    const bool ext = c->cfg.ext != 0;
+    const size_t hist_bins = (size_t)c->cfg.upper + 1;
+    CK(c->h_owords.ensure((c->n_kept + 1) * NW * 8));
+    CK(c->h_ocnt.ensure((c->n_kept + 1) * 4));
+    CK(c->h_hist.ensure(hist_bins * 8));
+    if (ext) {
+        CK(c->h_oocc_off.ensure((c->n_kept + 1) * 8));
+        CK(c->h_opos.ensure((c->n_occ + 1) * 4));
+        CK(c->h_orid.ensure((c->n_occ + 1) * 4));
+    }
+    cudaEvent_t e0 = c->ev(), e1 = c->ev();
+    CK(cudaEventRecord(e0, s));
+    if (c->n_kept) {
+        CK(cudaMemcpyAsync(c->h_owords.p, c->d_owords.p, c->n_kept * NW * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_ocnt.p, c->d_ocnt.p, c->n_kept * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, hist_bins * 8, cudaMemcpyDeviceToHost, s));
+    if (ext) {
+        CK(cudaMemcpyAsync(c->h_oocc_off.p, c->d_oocc_off.p, (c->n_kept + 1) * 8, cudaMemcpyDeviceToHost, s));
+        if (c->n_occ) {
+            CK(cudaMemcpyAsync(c->h_opos.p, c->d_opos.p, c->n_occ * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(c->h_orid.p, c->d_orid.p, c->n_occ * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CK(cudaEventRecord(e1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&c->stats.ms_d2h, e0, e1));
+    out->nwords = NW;
+    out->n_kept = c->n_kept;
+    out->n_occ = c->n_occ;
+    out->kmer_words = c->h_owords.as<uint64_t>();
+    out->cnt = c->h_ocnt.as<u32>();
+    out->occ_off = ext ? c->h_oocc_off.as<uint64_t>() : nullptr;
+    out->pos = ext ? c->h_opos.as<u32>() : nullptr;
+    out->rid = ext ? c->h_orid.as<int32_t>() : nullptr;
+    out->histogram = c->h_hist.as<uint64_t>();
+    out->stats = c->stats;
+    return 0;
+}
+
+// host -> device staging of a DnaBuffer: bytes as they are, byte offsets of the reads, 32-bit lengths
+static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads)
+{
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    const u64 padded = ((nbytes + 15) & ~15ull) + 64;
+    CK(c->d_packed.ensure(padded));
+    CK(c->d_read_off.ensure((nreads + 1) * 8));
+    CK(c->d_read_len.ensure((nreads + 1) * 4));
+    CK(c->h_read_off.ensure((nreads + 1) * 8));
+    CK(c->h_read_len.ensure((nreads + 1) * 4));
+    u64 *off = c->h_read_off.as<u64>();
+    u32 *len = c->h_read_len.as<u32>();
+    u64 acc = 0;
+    for (u64 i = 0; i < nreads; ++i) {
+        if (read_len[i] > 0xFFFFFFFFull) return fail("read %llu longer than 2^32-1 bases", (unsigned long long)i);
+        off[i] = acc; len[i] = (u32)read_len[i];
+        acc += (read_len[i] + 3) / 4;
+    }
+    off[nreads] = acc;
+    if (acc != nbytes) return fail("DnaBuffer size %llu does not match the read lengths (%llu bytes)", (unsigned long long)nbytes, (unsigned long long)acc);
+    cudaEvent_t e0 = c->ev(), e1 = c->ev();
+    CK(cudaEventRecord(e0, s));
+    CK(cudaMemsetAsync(c->d_packed.as<u8>() + (nbytes & ~15ull), 0, padded - (nbytes & ~15ull), s));
+    if (nbytes) CK(cudaMemcpyAsync(c->d_packed.p, packed, nbytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_read_off.p, off, (nreads + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_read_len.p, len, (nreads + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(e1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&c->stats.ms_h2d, e0, e1));
+    return 0;
+}
+
+int hsk_count(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
+              int32_t readid_base, hsk_result *out)
+{
+    if (!c || !out) return fail("hsk_count: null argument");
+    if (nreads && (!read_len)) return fail("hsk_count: null read_len");
+    c->ev_used = 0;
+    if (stage_input(c, packed, nbytes, read_len, nreads)) return 1;
+    const float h2d = c->stats.ms_h2d;
+    if (count_device(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(), nreads,
+                     readid_base)) return 1;
+    c->stats.ms_h2d = h2d;
+    return hsk_fetch_result(c, out);
+}
+
+int hsk_allreduce_histogram(hsk_ctx *c, uint64_t *hist)
+{
+    if (!c || !hist) return fail("hsk_allreduce_histogram: null argument");
+    if (!c->have_result) return fail("hsk_allreduce_histogram: no result on this context");
+    CK(cudaSetDevice(c->cfg.device));
+    const size_t bins = (size_t)c->cfg.upper + 1;
+    CK(c->h_hist.ensure(bins * 8));
+    if (c->cfg.nranks > 1) {
+        CK(c->d_alltot.ensure(bins * 8));
+        NK(g_nccl.AllReduce(c->d_hist.p, c->d_alltot.p, bins, ncclUint64, ncclSum, c->comm, c->stream));
+        CK(cudaMemcpyAsync(c->h_hist.p, c->d_alltot.p, bins * 8, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, bins * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(hist, c->h_hist.p, bins * 8);
+    return 0;
+}
+
+int hsk_fill_entries(hsk_ctx *c, void *entries, uint64_t capacity_entries)
+{
+    if (!c || !entries) return fail("hsk_fill_entries: null argument");
+    if (!c->have_result) return fail("hsk_fill_entries: no result on this context");
+    if (capacity_entries < c->n_kept) return fail("hsk_fill_entries: capacity %llu < %llu entries", (unsigned long long)capacity_entries, (unsigned long long)c->n_kept);
+    if (c->h_owords.cap < c->n_kept * c->nwords * 8) return fail("hsk_fill_entries: call hsk_count / hsk_fetch_result first");
+    const int NW = c->nwords;
+    const u64 *w = c->h_owords.as<u64>();
+    const u32 *cnt = c->h_ocnt.as<u32>();
+    u64 *dst = reinterpret_cast<u64 *>(entries);
+    for (u64 i = 0; i < c->n_kept; ++i) {
+        for (int l = 0; l < NW; ++l) dst[i * (NW + 1) + l] = w[i * NW + l];
+        dst[i * (NW + 1) + NW] = cnt[i];
+    }
+    return 0;
+}
+
+// ---- stage-level entry points -----------------------------------------------------------------------
+
+int hsk_debug_sort(hsk_ctx *c, uint64_t *const *d_keys, uint64_t *const *d_tmp, uint64_t *d_val, uint64_t *d_val_tmp, uint64_t n,
+                   int32_t nwords, int32_t k)
+{
+    if (!c) return fail("hsk_debug_sort: null ctx");
+    if (nwords != nwords_for_k(k)) return fail("hsk_debug_sort: nwords does not match k");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    Planes A, B;
+    for (int w = 0; w < MAX_WORDS; ++w) { A.p[w] = w < nwords ? (u64 *)d_keys[w] : nullptr; B.p[w] = w < nwords ? (u64 *)d_tmp[w] : nullptr; }
+    CK(c->d_rscratch.ensure(radix_scratch_bytes(n)));
+    bool in_b = false; int np = 0, nl = 0;
+    c->ev_used = 0;
+    cudaEvent_t e0 = c->ev(), e1 = c->ev();
+    CK(cudaEventRecord(e0, s));
+    CK(launch_radix_sort(A, B, (u64 *)d_val, (u64 *)d_val_tmp, n, nwords, k, c->d_rscratch.p, &in_b, &np, &nl, s));
+    CK(cudaEventRecord(e1, s));
+    if (in_b) {
+        for (int w = 0; w < nwords; ++w) CK(cudaMemcpyAsync(d_keys[w], d_tmp[w], n * 8, cudaMemcpyDeviceToDevice, s));
+        if (d_val) CK(cudaMemcpyAsync(d_val, d_val_tmp, n * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&c->stats.ms_sort, e0, e1));
+    c->stats.n_sort_passes = (u64)np;
+    return 0;
+}
+
+int hsk_debug_extract(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
+                      int32_t readid_base, hsk_supermers *out)
+{
+    if (!c || !out) return fail("hsk_debug_extract: null argument");
+    c->ev_used = 0;
+    c->ev_extract.clear();
+    if (stage_input(c, packed, nbytes, read_len, nreads)) return 1;
+    if (run_extract(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(), nreads,
+                    readid_base)) return 1;
+    const u32 T = c->tt;
+    const u64 *hb = c->h_bucket.as<u64>();
+    const u64 S = hb[3 * (size_t)T + T], W = hb[3 * (size_t)T + (T + 1) + T];
+    CK(c->h_ocnt.ensure((S + 1) * 2));
+    CK(c->h_owords.ensure((W + 1) * 4));
+    if (c->cfg.ext) CK(c->h_oocc_off.ensure((S + 1) * 8));
+    if (S) CK(cudaMemcpyAsync(c->h_ocnt.p, c->d_len.p, S * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (W) CK(cudaMemcpyAsync(c->h_owords.p, c->d_words.p, W * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (c->cfg.ext && S) CK(cudaMemcpyAsync(c->h_oocc_off.p, c->d_ext.p, S * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out->n_buckets = T;
+    out->bucket_kmers = reinterpret_cast<const uint64_t *>(hb);
+    out->bucket_count = reinterpret_cast<const uint64_t *>(hb + T);
+    out->bucket_words = reinterpret_cast<const uint64_t *>(hb + 2 * (size_t)T);
+    out->n_supermers = S;
+    out->n_words = W;
+    out->len = c->h_ocnt.as<u16>();
+    out->words = c->h_owords.as<u32>();
+    out->ext = c->cfg.ext ? c->h_oocc_off.as<uint64_t>() : nullptr;
+    c->have_result = false;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,80 @@
+// Launch interfaces of the hysortk_b200 kernels (one .cu per stage).
+#pragma once
+#include "common.cuh"
+
+namespace hsk {
+
+// ---- stage 1+2: extract.cu -----------------------------------------------------------------------
+struct ExtractParams {
+    const u8 *packed;        // DnaBuffer bytes on the device, 16-byte aligned
+    u64 nbytes;              // DnaBuffer::getbufsize()
+    u64 nbytes_padded;       // readable extent (multiple of 16)
+    const u64 *read_off;     // nreads+1 byte offsets (read_off[nreads] = nbytes)
+    const u32 *read_len;     // nreads lengths in bases
+    u64 nreads;
+    u64 ntiles, tiles_per_cta;
+    int k, m;                // m already clamped to <= 32
+    u32 nbuckets;            // all ranks' buckets
+    int readid_base;
+};
+
+size_t extract_count_smem(u32 nbuckets);
+size_t extract_scatter_smem(u32 nbuckets);
+cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, uint2 *cta_totals, u64 *bucket_kmers, cudaStream_t s);
+cudaError_t launch_bucket_scan(uint2 *cta_totals, u32 nctas, u32 nbuckets, u64 *bucket_count, u64 *bucket_words,
+                               u64 *bucket_start, u64 *word_start, cudaStream_t s);
+cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const uint2 *cta_base,
+                                    const u64 *bucket_start, const u64 *word_start, u16 *out_len, u32 *out_words,
+                                    u64 *out_ext, cudaStream_t s);
+
+// ---- stage 4: expand.cu ----------------------------------------------------------------------------
+constexpr int XP_THREADS = 256;
+constexpr int XP_SPT = 4;                          // supermers per thread in the scans
+constexpr int XP_TILE = XP_THREADS * XP_SPT;       // 1024 supermers per tile
+
+struct ExpandSegment {
+    const u16 *len;          // nsup lengths
+    const u32 *words;        // packed bases of the segment
+    const u64 *ext;          // (pos << 32) | rid per supermer, or null
+    u64 nsup;
+    u64 out_base;            // first output k-mer index of the segment inside the batch
+};
+
+// scratch: tile_sums / tile_base hold ceil(nsup/XP_TILE) entries each
+cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext, uint2 *tile_sums, ulonglong2 *tile_base,
+                          Planes out_keys, u64 *out_val, cudaStream_t s);
+
+// ---- stage 5a: radix.cu ------------------------------------------------------------------------------
+// scratch layout (u32 units): [RS_MAX_PASSES*256 bins][RS_MAX_PASSES tile counters][ntiles*256 look-back]
+size_t radix_scratch_bytes(u64 n);
+// Sorts n keys (planes `a`, optional payload va) using planes `b`/vb as the other half of the
+// ping-pong.  On return *result_in_b tells where the sorted data is.
+cudaError_t launch_radix_sort(Planes a, Planes b, u64 *va, u64 *vb, u64 n, int nwords, int k, void *scratch,
+                              bool *result_in_b, int *npasses, int *nlaunches, cudaStream_t s);
+
+// ---- stage 5b/5c: count.cu ---------------------------------------------------------------------------
+constexpr int CT_THREADS = 256;
+constexpr int CT_IPT = 8;
+constexpr int CT_TILE = CT_THREADS * CT_IPT;       // 2048 sorted k-mers per tile
+
+struct CountParams {
+    Planes keys;             // sorted keys of the batch
+    const u64 *val;          // payload plane (ext) or null
+    u64 n;
+    int nwords;
+    u32 lower, upper;
+    // result arena (shared by all batches of a call)
+    u64 *out_words;          // AoS: entry e -> out_words[e*nwords + w]
+    u32 *out_cnt;
+    u64 *out_occ_off;        // ext: exclusive occurrence offsets per entry
+    u32 *out_pos;            // ext: PosInRead per occurrence
+    int *out_rid;            // ext: ReadId per occurrence
+    u64 *histogram;          // upper+1 bins
+    u64 *cursor;             // [0] = entries emitted so far, [1] = occurrences emitted so far
+};
+
+// scratch: 2 * (ceil(n/CT_TILE)+1) u64
+size_t count_scratch_bytes(u64 n);
+cudaError_t launch_count_filter(const CountParams &P, void *scratch, cudaStream_t s);
+
+} // namespace hsk

@@ -1,0 +1,170 @@
+/*
+ * hsk_capi.h — C ABI of the B200-native kmer_count engine (libhysortk_b200.so).
+ *
+ * This is the drop-in boundary of the hot path: plain pointers and sizes, no C++/torch types.
+ * The reference (CornellHPC/HySortK) has no C layer; its boundary for this path is the C++
+ * function
+ *
+ *     std::unique_ptr<KmerListS> hysortk::kmer_count(const DnaBuffer&, MPI_Comm)
+ *                                       reference include/hysortk.hpp:12, src/hysortk.cpp:36-95
+ *
+ * whose body (prepare_supermer -> exchange_supermer -> filter_kmer, src/kmerops.cpp:23-250) this
+ * library replaces.  include/hysortk.hpp + hysortk_b200/cxx/hysortk.cpp in this repo keep the
+ * C++ signature and call the functions below; INTEGRATION.md shows the binding.
+ *
+ * One context per process per GPU (the reference is one MPI rank per NUMA domain; here one rank
+ * per GPU).  All functions return 0 on success, non-zero on error with a message available from
+ * hsk_last_error() (the reference throws / aborts: kmerops.cpp:357,472,532,725,1319).
+ * Not re-entrant per context, like the reference.
+ */
+#ifndef HSK_CAPI_H_
+#define HSK_CAPI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSK_VERSION 1
+#define HSK_NCCL_ID_BYTES 128
+#define HSK_MAX_KMER_WORDS 3 /* reference include/kmer.hpp:343-345: K<=32 -> 1, <=64 -> 2, <=95 -> 3 */
+
+typedef struct hsk_ctx hsk_ctx;
+
+/* Replaces the reference's compile-time -D parameters (Makefile:39-46, compiletime.h:7-22), which
+ * the C++ shim forwards here at run time. */
+typedef struct hsk_config {
+    int32_t k;     /* KMER_SIZE, 2 < k < 96                                   */
+    int32_t m;     /* MINIMIZER_SIZE, 0 < m < k (values above 32 use the first 32 bases' window; the
+                      result does not depend on the minimizer)  */
+    int32_t lower; /* LOWER_KMER_FREQ                                          */
+    int32_t upper; /* UPPER_KMER_FREQ, lower <= upper <= 65535                 */
+    int32_t ext;   /* EXTENSION: 1 = carry (ReadId, PosInRead) per occurrence  */
+    int32_t device;           /* CUDA device ordinal                            */
+    int32_t rank, nranks;     /* position in the job; replaces MPI_Comm_rank/size (hysortk.cpp:41-44) */
+    const void *nccl_id;      /* HSK_NCCL_ID_BYTES from hsk_get_unique_id on rank 0, broadcast by the
+                                 caller (MPI_Bcast / torch.distributed); NULL when nranks == 1 */
+    int32_t buckets_per_rank; /* minimizer-hash buckets owned by each rank (reference: tasks per
+                                 rank, kmerops.cpp:40-43); 0 = default */
+    uint64_t batch_kmers;     /* k-mers expanded + sorted at once; 0 = default (fits HBM) */
+    void *stream;             /* cudaStream_t to run on; NULL = the context's own stream */
+} hsk_config;
+
+/* Per-stage device time (CUDA events on the context stream, milliseconds) and algorithmic volume
+ * of the last hsk_count call; what `roofline` in bench.py is computed from. */
+typedef struct hsk_stats {
+    uint64_t n_kmers_local;   /* k-mers extracted from this rank's reads                     */
+    uint64_t n_kmers_owned;   /* k-mers this rank sorted after the exchange                  */
+    uint64_t n_supermers;     /* supermers produced locally                                  */
+    uint64_t supermer_bytes;  /* bytes of supermer records produced locally (wire volume)    */
+    uint64_t bytes_sent;      /* supermer bytes sent to other ranks                          */
+    uint64_t bytes_received;
+    uint64_t n_batches;
+    uint64_t n_sort_passes;   /* radix passes executed per batch                             */
+    uint64_t n_launches;      /* kernels launched                                            */
+    float ms_h2d, ms_extract, ms_exchange, ms_expand, ms_sort, ms_count, ms_d2h, ms_total;
+} hsk_stats;
+
+/* Result of one rank.  Arrays live in page-locked host memory owned by the context and stay valid
+ * until the next hsk_count / hsk_destroy on it.  Entry i: k-mer words kmer_words[i*nwords + w]
+ * (word 0 = bases 0..31, 2 bits per base from the most significant bit; reference
+ * include/kmer.hpp:165-185), count cnt[i].  Entries are grouped in batches of minimizer buckets;
+ * inside a batch they ascend by k-mer (reference: per-task sorted runs, kmerops.cpp:883-904).
+ * With ext, the occurrences of entry i are pos/rid[occ_off[i] .. occ_off[i+1]) (reference
+ * KmerListEntryS::pos/rid, kmer.hpp:383-400).  histogram[c] = number of kept k-mers with count c
+ * on this rank, upper+1 bins (hysortk.cpp:106-113). */
+typedef struct hsk_result {
+    int32_t nwords;
+    uint64_t n_kept;
+    uint64_t n_occ;
+    const uint64_t *kmer_words;
+    const uint32_t *cnt;
+    const uint64_t *occ_off;
+    const uint32_t *pos;
+    const int32_t *rid;
+    const uint64_t *histogram;
+    hsk_stats stats;
+} hsk_result;
+
+/* Result left on the device (for callers that keep working on the GPU, and for timing the
+ * HBM-resident path): same layout, device pointers, valid until the next call on the context. */
+typedef struct hsk_device_result {
+    int32_t nwords;
+    uint64_t n_kept;
+    uint64_t n_occ;
+    const uint64_t *d_kmer_words; /* entry i, word w at d_kmer_words[i*nwords + w] */
+    const uint32_t *d_cnt;
+    const uint64_t *d_occ_off;
+    const uint32_t *d_pos;
+    const int32_t *d_rid;
+    const uint64_t *d_histogram;
+    hsk_stats stats;
+} hsk_device_result;
+
+const char *hsk_last_error(void);
+int hsk_version(void);
+
+/* ncclGetUniqueId for the supermer all-to-all (replaces the MPI communicator of
+ * exchange_supermer, kmerops.cpp:130-195). */
+int hsk_get_unique_id(void *id_out /* HSK_NCCL_ID_BYTES */);
+
+int hsk_create(hsk_ctx **ctx, const hsk_config *cfg);
+void hsk_destroy(hsk_ctx *ctx);
+
+/* kmer_count on host buffers — what hysortk::kmer_count(const DnaBuffer&, MPI_Comm) binds to.
+ *   packed     DnaBuffer bytes (reference include/dnabuffer.hpp:14-47, src/dnaseq.cpp:9-31): reads
+ *              back to back, each starting on a fresh byte, 4 bases per byte, first base in bits 7..6
+ *   nbytes     DnaBuffer::getbufsize()
+ *   read_len   DnaSeq::size() of every read, nreads entries
+ *   readid_base  number of reads on lower ranks (the MPI_Exscan of kmerops.cpp:65-70)
+ * Collective over the ranks of the context (every rank must call it).  H2D/D2H copies are part
+ * of the call. */
+int hsk_count(hsk_ctx *ctx, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
+              int32_t readid_base, hsk_result *out);
+
+/* Same with the reads already resident in HBM: d_packed (nbytes, 16-byte aligned, readable up to
+ * nbytes rounded up to 16), d_read_off (nreads+1 byte offsets of the reads, uint64) and d_read_len
+ * (nreads, uint32) are device pointers.  The result stays on the device. */
+int hsk_count_device(hsk_ctx *ctx, const uint8_t *d_packed, uint64_t nbytes, const uint64_t *d_read_off,
+                     const uint32_t *d_read_len, uint64_t nreads, int32_t readid_base, hsk_device_result *out);
+
+/* Copies the last device result of the context to page-locked host arrays (hsk_result layout). */
+int hsk_fetch_result(hsk_ctx *ctx, hsk_result *out);
+
+/* Sum of the per-rank histograms over all ranks (replaces the MPI_Allreduce of
+ * hysortk.cpp:104,115); hist has upper+1 bins.  Collective. */
+int hsk_allreduce_histogram(hsk_ctx *ctx, uint64_t *hist);
+
+/* Fills caller memory laid out as the reference's EXTENSION==0 KmerListEntryS array
+ * ({uint64_t kmer[nwords]; uint64_t cnt;}, include/kmer.hpp:368-382) from the last result. */
+int hsk_fill_entries(hsk_ctx *ctx, void *entries, uint64_t capacity_entries);
+
+/* ---- stage-level entry points (tests, profiling); device pointers, run on the context stream ---- */
+
+/* LSD radix sort of n keys held as nwords planes (plane 0 most significant) with an optional
+ * 64-bit payload plane, over the significant bits of a k-mer of size k.  Result in the same
+ * planes (tmp planes are scratch of the same size). */
+int hsk_debug_sort(hsk_ctx *ctx, uint64_t *const *d_keys, uint64_t *const *d_tmp, uint64_t *d_val, uint64_t *d_val_tmp,
+                   uint64_t n, int32_t nwords, int32_t k);
+
+/* Extraction + bucketing only: returns the local supermer streams (host copies) so tests can check
+ * that the supermers of every bucket re-expand to exactly the k-mers of the input. */
+typedef struct hsk_supermers {
+    uint64_t n_buckets;
+    const uint64_t *bucket_count;  /* supermers per bucket                              */
+    const uint64_t *bucket_words;  /* 32-bit words of packed bases per bucket           */
+    const uint64_t *bucket_kmers;  /* k-mers per bucket                                 */
+    uint64_t n_supermers, n_words;
+    const uint16_t *len;           /* bases per supermer, bucket-major                  */
+    const uint32_t *words;         /* packed bases: 16 per word from the top bits       */
+    const uint64_t *ext;           /* (pos << 32) | (uint32_t)rid per supermer, if ext  */
+} hsk_supermers;
+int hsk_debug_extract(hsk_ctx *ctx, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
+                      int32_t readid_base, hsk_supermers *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSK_CAPI_H_ */
