@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the kmer_count hot path (BASELINE.json metric: k-mers counted / second, whole job).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one full kmer_count over the synthetic read set of BASELINE.json configs[1]
+(K=31 M=17, 30x reads of a 5 Mbp uniform genome, ~150 Mbp, 1 % substitutions) per GPU; with N GPUs
+the genome is N times larger and every rank holds its own contiguous 150 Mbp share of the reads
+(weak scaling), the supermer all-to-all running over NCCL.
+
+  value  device path: reads resident in HBM when the timed region starts, result left in HBM
+         (hsk_count_device), timed with CUDA events on the launching stream, max over ranks.
+  e2e    the same metric through the host-buffer C-ABI call hsk_count (what
+         hysortk::kmer_count(const DnaBuffer&, MPI_Comm) binds to): pinned host input, H2D copy,
+         count, D2H copy of the (k-mer, count) list inside the timed region.
+  roofline   dominant kernel = the per-digit radix pass k_onesweep: algorithmic bytes per launch
+             (read + write of every key record) / average launch time from CUDA events recorded
+             around the pass kernels, against the measured HBM copy bandwidth.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, built from /root/reference with the
+             single-rank MPI shim) on this box's host cores, on a bounded prefix of the same reads.
+
+`--impl reference` times that reference build as its own arm (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, M, LOWER, UPPER, EXT = 31, 17, 2, 50, 0
+METRIC = "kmers_counted_per_sec"
+UNIT = "kmers/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_150Mbp_10kbp")
+    ap.add_argument("--batch-kmers", type=int, default=0)
+    ap.add_argument("--buckets-per-rank", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-mbp", type=float, default=60.0)
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: genome length per GPU, coverage, read length, error rate
+    "c2_150Mbp_10kbp": dict(genome_len=5_000_000, coverage=30.0, read_len=10_000, err=0.01),
+    "c2_150Mbp_150bp": dict(genome_len=5_000_000, coverage=30.0, read_len=150, err=0.01),
+    "c1_100Mbp_150bp": dict(genome_len=3_340_000, coverage=30.0, read_len=150, err=0.01),
+    "tiny": dict(genome_len=200_000, coverage=10.0, read_len=1000, err=0.01),
+}
+
+
+def make_shard(workload: str, rank: int, nranks: int, seed: int = 42):
+    """Rank's contiguous share of the reads: genome of nranks * genome_len bases shared by all ranks,
+    reads of this rank sampled with a rank-specific stream."""
+    from hysortk_b200 import synth
+    p = WORKLOADS[workload]
+    G = p["genome_len"] * nranks
+    genome = synth.make_genome(G, seed)
+    rng = np.random.Generator(np.random.Philox(seed + 1000 + rank))
+    L = p["read_len"]
+    n = int(p["genome_len"] * p["coverage"] / L)
+    nb = (L + 3) // 4
+    packed = np.empty(n * nb, dtype=np.uint8)
+    ar = np.arange(L, dtype=np.int64)
+    chunk = max(1, (1 << 24) // L)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        starts = rng.integers(0, G - L + 1, size=e - s, dtype=np.int64)
+        reads = genome[starts[:, None] + ar[None, :]]
+        reads = synth._mutate_and_flip(reads, p["err"], rng)
+        packed[s * nb:e * nb] = synth.pack_codes_matrix(reads).reshape(-1)
+    return synth.ReadSet(packed, np.full(n, L, dtype=np.uint64)), dict(p, genome_len_total=G, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def run_reference(rs, sample_bases: float, steps: int, warmup: int):
+    """Times the unmodified reference's kmer_count (oracle/_ref) on a prefix of the reads."""
+    from oracle import pyoracle as po
+    if not po.ref_available(K, M, LOWER, UPPER, EXT):
+        return None
+    L = int(rs.readlens[0])
+    n = max(1, min(rs.nreads, int(sample_bases // L)))
+    nb = (L + 3) // 4
+    packed, lens = rs.packed[: n * nb], rs.readlens[:n]
+    nk = int(np.maximum(lens.astype(np.int64) - K + 1, 0).sum())
+    os.environ.setdefault("SLURM_TASKS_PER_NODE", "1")   # keeps the reference on RADULS (kmerops.cpp:1358-1362)
+    times = []
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    try:
+        os.dup2(devnull, 1)   # the reference logs to stdout
+        for i in range(warmup + steps):
+            c = po.ref_kmer_count(packed, lens, K, M, LOWER, UPPER, EXT)
+            if i >= warmup:
+                times.append(c.seconds)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    sec = float(np.mean(times))
+    return dict(value=nk / sec, seconds_per_step=sec, kmers=nk, cores=os.cpu_count(),
+                sample=f"first {n} reads ({n * L / 1e6:.1f} Mbp, {nk} k-mers) of the workload, 1 rank x {os.cpu_count()} OpenMP threads, RADULS")
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rs, meta = make_shard(args.workload, 0, 1)
+    steps, warmup = args.steps, min(args.warmup, 1) if args.steps <= 2 else args.warmup
+    r = run_reference(rs, args.cpu_sample_mbp * 1e6 / 2, steps, warmup)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference; run oracle/build_ref.sh)"}))
+        return
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": args.workload, "k": K, "m": M, "lower": LOWER, "upper": UPPER, "ext": EXT, **meta},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hysortk_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        idt = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    rs, meta = make_shard(args.workload, rank, world)
+    nk_local = rs.num_kmers(K)
+    stream = torch.cuda.current_stream()
+    ctx = capi.Context(K, M, LOWER, UPPER, EXT, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id,
+                       buckets_per_rank=args.buckets_per_rank, batch_kmers=args.batch_kmers, stream=stream.cuda_stream)
+    readid_base = rank * rs.nreads
+
+    # device-resident inputs
+    off = rs.byte_offsets()
+    d_packed = torch.zeros(((rs.packed.nbytes + 15) // 16) * 16 + 64, dtype=torch.uint8, device=dev)
+    d_packed[: rs.packed.nbytes].copy_(torch.from_numpy(rs.packed))
+    d_off = torch.from_numpy(off.view(np.int64)).to(dev)
+    d_len = torch.from_numpy(rs.readlens.astype(np.uint32).view(np.int32)).to(dev)
+    # pinned host inputs for the end-to-end call
+    h_packed = torch.from_numpy(rs.packed).pin_memory()
+    h_lens = torch.from_numpy(rs.readlens.view(np.int64)).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return ctx.count_device(d_packed.data_ptr(), rs.packed.nbytes, d_off.data_ptr(), d_len.data_ptr(), rs.nreads, readid_base)
+
+    def step_e2e():
+        r = capi.Result()
+        capi._check(ctx.lib.hsk_count(ctx.handle, h_packed.data_ptr(), rs.packed.nbytes, h_lens.data_ptr(), rs.nreads,
+                                      readid_base, capi.C.byref(r)))
+        return r
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device path --------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats_acc = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        r = step_device()
+        stats_acc.append(r.stats.as_dict())
+    e1.record(stream)
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    n_kept = int(r.n_kept)
+    total_kmers = sum_over_ranks(float(nk_local))
+    value = total_kmers * args.steps / (ms_dev * 1e-3)
+
+    # ---- end-to-end path (host buffers) ---------------------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        re = step_e2e()
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = total_kmers * args.steps / (ms_e2e * 1e-3)
+    h2d = rs.packed.nbytes + (rs.nreads + 1) * 8 + (rs.nreads + 1) * 4
+    d2h = int(re.n_kept) * (8 * ctx.nwords + 4) + (UPPER + 1) * 8 + 16
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    st = {k: float(np.mean([s[k] for s in stats_acc])) for k in stats_acc[0]}
+    rec = 8 * ctx.nwords + (8 if EXT else 0)
+    n_owned = st["n_kmers_owned"]
+    launches_per_step = st["n_sort_passes"] * st["n_batches"]
+    bytes_per_launch = 2.0 * rec * n_owned / max(st["n_batches"], 1)
+    ms_per_launch = st["ms_sort_passes"] / max(launches_per_step, 1)
+    achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
+    peak, peak_kind = measured_hbm_peak()
+    roofline = {"bound": "hbm", "kernel": "k_onesweep (one 8-bit LSD radix pass)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": ms_per_launch,
+                "launches_per_step": launches_per_step,
+                "sort_stage": {"algorithmic_bytes": rec * n_owned * (1 + 2 * st["n_sort_passes"]), "ms": st["ms_sort"],
+                               "gbs": rec * n_owned * (1 + 2 * st["n_sort_passes"]) / max(st["ms_sort"], 1e-9) / 1e6},
+                "stage_ms": {k: st[k] for k in ["ms_extract", "ms_exchange", "ms_expand", "ms_sort", "ms_count", "ms_total"]}}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rr = run_reference(rs, args.cpu_sample_mbp * 1e6, 2, 1)
+        if rr is not None:
+            cpu = {"value": rr["value"], "unit": UNIT, "cores": rr["cores"], "kind": "reference", "sample": rr["sample"]}
+        else:
+            from oracle import pyoracle as po
+            L = int(rs.readlens[0]); n = max(1, int(5e6 // L)); nb = (L + 3) // 4
+            t0 = time.time()
+            c = po.kmer_count(rs.packed[: n * nb], rs.readlens[:n], K, M, LOWER, UPPER, EXT, ntasks=5)
+            dt = time.time() - t0
+            cpu = {"value": c.total_kmers / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"first {n} reads ({n * L / 1e6:.1f} Mbp) through oracle/oracle.c (scalar)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic",
+                "config": {"workload": args.workload, "k": K, "m": M, "lower": LOWER, "upper": UPPER, "ext": EXT,
+                           "kmers_per_gpu": nk_local, "reads_per_gpu": rs.nreads, "kept_kmers_rank0": n_kept,
+                           "l2_policy": "inputs larger than L2 (1.2 GB of keys per pass vs 126 MB L2), no flush",
+                           "buckets_per_rank": int(ctx.lib and (args.buckets_per_rank or 256)),
+                           "batches": st["n_batches"], **meta},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(round(st["n_launches"] * args.steps)),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -36,7 +36,8 @@ class Stats(C.Structure):
                 ("supermer_bytes", C.c_uint64), ("bytes_sent", C.c_uint64), ("bytes_received", C.c_uint64),
                 ("n_batches", C.c_uint64), ("n_sort_passes", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_h2d", C.c_float), ("ms_extract", C.c_float), ("ms_exchange", C.c_float), ("ms_expand", C.c_float),
-                ("ms_sort", C.c_float), ("ms_count", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float)]
+                ("ms_sort", C.c_float), ("ms_count", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+                ("ms_sort_passes", C.c_float), ("reserved_", C.c_float)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -160,7 +160,7 @@ struct hsk_ctx {
 
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
-    std::vector<EvPair> ev_extract, ev_exchange, ev_expand, ev_sort, ev_count;
+    std::vector<EvPair> ev_extract, ev_exchange, ev_expand, ev_sort, ev_count, ev_pass;
 
     cudaEvent_t ev()
     {
@@ -329,7 +329,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     const int NW = c->nwords;
     const bool ext = c->cfg.ext != 0;
     c->ev_used = 0;
-    c->ev_extract.clear(); c->ev_exchange.clear(); c->ev_expand.clear(); c->ev_sort.clear(); c->ev_count.clear();
+    c->ev_extract.clear(); c->ev_exchange.clear(); c->ev_expand.clear(); c->ev_sort.clear(); c->ev_count.clear(); c->ev_pass.clear();
     hsk_stats keep = c->stats;
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.ms_h2d = keep.ms_h2d;
@@ -495,7 +495,9 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
 
         c->begin(c->ev_sort);
         bool in_b = false; int np = 0, nl = 0;
-        CK(launch_radix_sort(A, B, VA, VB, bt.n, NW, c->cfg.k, c->d_rscratch.p, &in_b, &np, &nl, s));
+        EvPair pp{c->ev(), c->ev()};
+        c->ev_pass.push_back(pp);
+        CK(launch_radix_sort(A, B, VA, VB, bt.n, NW, c->cfg.k, c->d_rscratch.p, &in_b, &np, &nl, s, pp.a, pp.b));
         c->end(c->ev_sort);
         c->stats.n_sort_passes = (u64)np;
         c->stats.n_launches += (u64)nl;
@@ -527,6 +529,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     c->stats.ms_expand = hsk_ctx::sum_ms(c->ev_expand);
     c->stats.ms_sort = hsk_ctx::sum_ms(c->ev_sort);
     c->stats.ms_count = hsk_ctx::sum_ms(c->ev_count);
+    c->stats.ms_sort_passes = hsk_ctx::sum_ms(c->ev_pass);
     CK(cudaEventElapsedTime(&c->stats.ms_total, ev_t0, ev_t1));
     c->have_result = true;
     return 0;

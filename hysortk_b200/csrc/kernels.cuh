@@ -49,8 +49,10 @@ cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext,
 size_t radix_scratch_bytes(u64 n);
 // Sorts n keys (planes `a`, optional payload va) using planes `b`/vb as the other half of the
 // ping-pong.  On return *result_in_b tells where the sorted data is.
+// ev_pass0/ev_pass1 (optional) are recorded around the per-digit pass kernels.
 cudaError_t launch_radix_sort(Planes a, Planes b, u64 *va, u64 *vb, u64 n, int nwords, int k, void *scratch,
-                              bool *result_in_b, int *npasses, int *nlaunches, cudaStream_t s);
+                              bool *result_in_b, int *npasses, int *nlaunches, cudaStream_t s,
+                              cudaEvent_t ev_pass0 = nullptr, cudaEvent_t ev_pass1 = nullptr);
 
 // ---- stage 5b/5c: count.cu ---------------------------------------------------------------------------
 constexpr int CT_THREADS = 256;

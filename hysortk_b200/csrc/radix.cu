@@ -210,7 +210,7 @@ size_t radix_scratch_bytes(u64 n)
 
 template <int NW, bool HAS_VAL>
 static cudaError_t run_passes(Planes a, Planes b, u64 *va, u64 *vb, u32 n, int k, u32 *bins, u32 *counters, u32 *lookback,
-                              const PassTable &pt, bool *result_in_b, cudaStream_t s)
+                              const PassTable &pt, bool *result_in_b, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1)
 {
     const u32 ntiles = (n + RS_TILE - 1) / RS_TILE;
     const size_t smem = sizeof(RadixSmem);
@@ -219,6 +219,7 @@ static cudaError_t run_passes(Planes a, Planes b, u64 *va, u64 *vb, u32 n, int k
     k_radix_hist<NW><<<148 * 4, 512, pt.npasses * 256 * sizeof(u32), s>>>(a, n, k, bins);
     k_radix_scan_bins<<<pt.npasses, 256, 0, s>>>(bins);
     bool in_b = false;
+    if (ev0) cudaEventRecord(ev0, s);
     for (int p = 0; p < pt.npasses; ++p) {
         Planes &src = in_b ? b : a;
         Planes &dst = in_b ? a : b;
@@ -227,12 +228,14 @@ static cudaError_t run_passes(Planes a, Planes b, u64 *va, u64 *vb, u32 n, int k
                                                                  (p & 1) ? 2u : 0u);
         in_b = !in_b;
     }
+    if (ev1) cudaEventRecord(ev1, s);
     *result_in_b = in_b;
     return cudaGetLastError();
 }
 
 cudaError_t launch_radix_sort(Planes a, Planes b, u64 *va, u64 *vb, u64 n, int nwords, int k, void *scratch,
-                              bool *result_in_b, int *npasses, int *nlaunches, cudaStream_t s)
+                              bool *result_in_b, int *npasses, int *nlaunches, cudaStream_t s, cudaEvent_t ev0,
+                              cudaEvent_t ev1)
 {
     *result_in_b = false;
     PassTable pt = make_pass_table(k);
@@ -247,12 +250,12 @@ cudaError_t launch_radix_sort(Planes a, Planes b, u64 *va, u64 *vb, u64 n, int n
     if (e != cudaSuccess) return e;
     if (nlaunches) *nlaunches = 2 + pt.npasses;
     const bool hv = va != nullptr;
-    if (nwords == 1) return hv ? run_passes<1, true>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s)
-                              : run_passes<1, false>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s);
-    if (nwords == 2) return hv ? run_passes<2, true>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s)
-                              : run_passes<2, false>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s);
-    return hv ? run_passes<3, true>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s)
-              : run_passes<3, false>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s);
+    if (nwords == 1) return hv ? run_passes<1, true>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s, ev0, ev1)
+                              : run_passes<1, false>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s, ev0, ev1);
+    if (nwords == 2) return hv ? run_passes<2, true>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s, ev0, ev1)
+                              : run_passes<2, false>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s, ev0, ev1);
+    return hv ? run_passes<3, true>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s, ev0, ev1)
+              : run_passes<3, false>(a, b, va, vb, (u32)n, k, bins, counters, lookback, pt, result_in_b, s, ev0, ev1);
 }
 
 } // namespace hsk
