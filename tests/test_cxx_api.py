@@ -1,0 +1,103 @@
+"""The C++ drop-in layer: public value types (host only), the Makefile artefacts, and — on the GPU —
+the standalone CLI end to end against the reference's golden output."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hysortk_b200 import synth
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+def make(k, m, l, u, ext, target="standalone", log=0):
+    tag = f"k{k}_m{m}_l{l}_u{u}_e{ext}"
+    obj = os.path.join(BUILD, "obj_" + tag)
+    binp = os.path.join(BUILD, "hysortk_" + tag)
+    subprocess.check_call(["make", "-s", "-j8", target, f"K={k}", f"M={m}", f"L={l}", f"U={u}", f"EXT={ext}", f"LOG={log}",
+                           f"OBJ={obj}", f"BIN={binp}"], cwd=ROOT, stdout=subprocess.DEVNULL)
+    return obj, binp
+
+
+@pytest.mark.parametrize("k,ext", [(31, 0), (55, 0), (31, 1), (70, 0), (32, 0)])
+def test_value_types_match_oracle(k, ext):
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, f"test_types_k{k}_e{ext}")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", f"-DKMER_SIZE={k}", "-DMINIMIZER_SIZE=17", "-DLOWER_KMER_FREQ=2",
+                           "-DUPPER_KMER_FREQ=50", f"-DEXTENSION={ext}", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cxx", "test_types.cpp"),
+                           os.path.join(ROOT, "hysortk_b200", "cxx", "dnaseq.cpp"),
+                           os.path.join(ROOT, "hysortk_b200", "cxx", "dnabuffer.cpp"),
+                           os.path.join(ROOT, "hysortk_b200", "cxx", "hashfuncs.cpp"), "-o", exe])
+    rng = np.random.default_rng(k)
+    reads = ["".join("ACGT"[c] for c in rng.integers(0, 4, n)) for n in (k, k + 1, 150, 2 * k + 3)]
+    reads.append("ACGTN" * 30)
+    out = subprocess.run([exe] + reads, capture_output=True, text=True, check=True).stdout.splitlines()
+    L = po.lib()
+    nw = 1 if k <= 32 else (2 if k <= 64 else 3)
+    it = iter(out)
+    hdr = next(it).split()
+    assert int(hdr[1]) == len(reads)
+    assert int(hdr[3]) == sum((len(r) + 3) // 4 for r in reads) == int(hdr[5])
+    for r in reads:
+        line = next(it).split()
+        assert line[1] == r.replace("N", "A") and int(line[2]) == (len(r) + 3) // 4
+        packed = np.zeros((len(r) + 3) // 4, dtype=np.uint8)
+        L.orc_pack_read(r.encode(), len(r), packed.ctypes.data)
+        km, tw, rp = (C.c_uint64 * 3)(), (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+        buf = C.create_string_buffer(128)
+        for p in range(len(r) - k + 1):
+            got = next(it).split()
+            L.orc_kmer_set(packed.ctypes.data, p, k, km)
+            L.orc_kmer_twin(km, k, tw)
+            L.orc_kmer_rep(km, k, rp)
+            exp = []
+            for x in (km, tw, rp):
+                L.orc_kmer_string(x, k, buf)
+                exp.append(buf.value.decode())
+            assert got[:3] == exp
+            assert int(got[3]) == L.orc_murmur3_64(rp, 8 * nw)
+    sizes = next(it).split()
+    assert int(sizes[1]) == 8 * nw
+    if not ext:
+        assert int(sizes[2]) == 8 * nw + 8 and int(sizes[3]) == 8 * nw
+    else:
+        assert int(sizes[2]) == 8 * nw + 8 + 48 and int(sizes[3]) == 8 * nw + 8   # two std::vector + (pos, rid)
+
+
+def test_makefile_artefacts():
+    obj, binp = make(31, 17, 2, 50, 0)
+    assert os.path.exists(os.path.join(obj, "libhysortk.o")) and os.path.exists(binp)
+    syms = subprocess.run(["nm", "-C", os.path.join(obj, "libhysortk.o")], capture_output=True, text=True).stdout
+    for s in ["hysortk::kmer_count(", "hysortk::read_dna_buffer(", "hysortk::print_kmer_histogram(",
+              "hysortk::write_output_file(", "hsk_count", "hsk_create"]:
+        assert s in syms, s
+    r = subprocess.run(["make", "K=17", "M=17"], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode != 0 and "must be less than" in (r.stderr + r.stdout)   # reference Makefile:50-52
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,line_width", [("k31_e0_mixed", 0), ("k55_e0_mixed", 80), ("k31_e0_lowcomplexity", 60)])
+def test_standalone_cli_matches_reference_output(name, line_width, tmp_path):
+    from conftest import load_golden
+    g = load_golden(name)
+    _, binp = make(g["k"], g["m"], g["lower"], g["upper"], g["ext"], log=1)
+    rs = synth.ReadSet(g["packed"], g["readlens"])
+    keep = [i for i in range(rs.nreads) if rs.readlens[i] > 0]   # FASTA cannot hold empty records portably
+    if len(keep) != rs.nreads:
+        rs = synth.pack_reads([rs.codes(i) for i in keep])
+    fasta = str(tmp_path / "reads.fa")
+    synth.write_fasta(fasta, rs, line_width)
+    outdir = tmp_path / "out"
+    outdir.mkdir()
+    r = subprocess.run([binp, fasta, str(outdir)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert g["histogram_text"] in r.stdout
+    assert "Overall kmer counting (Excluding I/O)" in r.stdout
+    lines = sorted(open(outdir / "0.out").read().splitlines())
+    assert hashlib.md5("\n".join(lines).encode()).hexdigest() == g["sorted_output_md5"]
