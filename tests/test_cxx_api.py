@@ -16,7 +16,7 @@ BUILD = os.path.join(ROOT, "tests", "_build")
 
 
 def make(k, m, l, u, ext, target="standalone", log=0):
-    tag = f"k{k}_m{m}_l{l}_u{u}_e{ext}"
+    tag = f"k{k}_m{m}_l{l}_u{u}_e{ext}_log{log}"
     obj = os.path.join(BUILD, "obj_" + tag)
     binp = os.path.join(BUILD, "hysortk_" + tag)
     subprocess.check_call(["make", "-s", "-j8", target, f"K={k}", f"M={m}", f"L={l}", f"U={u}", f"EXT={ext}", f"LOG={log}",
