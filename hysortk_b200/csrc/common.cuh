@@ -118,8 +118,8 @@ constexpr int EX_HALO = 128;                   // >= K - M (window - 1), multipl
 constexpr int EX_TSK = EX_TS - EX_HALO;        // 3968 k-mer slots per tile (992 bytes, 16-byte multiple)
 constexpr int EX_TILE_BYTES = EX_TSK / 4;      // 992
 constexpr int EX_WORDS = EX_TS / 16 + 4;       // 260 big-endian 32-bit words of bases staged per tile
-constexpr u32 EX_INVALID = 0xFFFFu;
-constexpr int MAX_BUCKETS = 8192;
+constexpr u32 EX_INVALID = 0xFFFFFFFFu;
+constexpr u32 MAX_BINS = 1u << 26;
 
 // ---- radix geometry --------------------------------------------------------------------------
 constexpr int RS_THREADS = 384;

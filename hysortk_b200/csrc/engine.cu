@@ -143,7 +143,7 @@ struct hsk_ctx {
     DevBuf d_packed, d_read_off, d_read_len;
     HostBuf h_read_off, h_read_len;
     // extraction
-    DevBuf d_cta_totals, d_bucket;   // d_bucket: [kmers T][count T][words T][start T+1][wstart T+1] u64
+    DevBuf d_bucket, d_run_list, d_tile_hdr;   // d_bucket: see run_extract
     HostBuf h_bucket;
     DevBuf d_len, d_words, d_ext;
     // exchange
@@ -158,6 +158,7 @@ struct hsk_ctx {
     bool have_result = false;
     hsk_stats stats;
 
+    std::vector<u64> h_dbg;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<EvPair> ev_extract, ev_exchange, ev_expand, ev_sort, ev_count, ev_pass;
@@ -227,11 +228,12 @@ int hsk_create(hsk_ctx **out, const hsk_config *cfg)
     c->m_eff = std::min(cfg->m, 32);
     if (cfg->k - c->m_eff > EX_HALO - 1) c->m_eff = cfg->k - (EX_HALO - 1);
     c->sm_count = prop.multiProcessorCount;
-    u32 tg = cfg->buckets_per_rank > 0 ? (u32)cfg->buckets_per_rank : 256u;
-    if ((u64)tg * cfg->nranks > MAX_BUCKETS) tg = MAX_BUCKETS / cfg->nranks;
-    if (tg < 1) { delete c; return fail("hsk_create: too many ranks for %d buckets", MAX_BUCKETS); }
-    c->tg = tg;
-    c->tt = tg * (u32)cfg->nranks;
+    if (cfg->buckets_per_rank > 0 && (u64)cfg->buckets_per_rank * cfg->nranks > MAX_BINS) {
+        delete c;
+        return fail("hsk_create: buckets_per_rank * nranks exceeds %u", MAX_BINS);
+    }
+    c->tg = cfg->buckets_per_rank > 0 ? (u32)cfg->buckets_per_rank : 0;   // 0: chosen per call from the input size
+    c->tt = c->tg * (u32)cfg->nranks;
     if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
     else {
         cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -256,7 +258,7 @@ void hsk_destroy(hsk_ctx *c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_cta_totals, &c->d_bucket, &c->d_len, &c->d_words,
+    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_bucket, &c->d_len, &c->d_words,
                     &c->d_ext, &c->d_alltot, &c->d_rlen, &c->d_rwords, &c->d_rext, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
@@ -271,11 +273,38 @@ void hsk_destroy(hsk_ctx *c)
 }
 
 // ---- extraction (stages 1+2) -------------------------------------------------------------------------
-// On return h_bucket holds [kmers T][count T][words T][start T+1][wstart T+1] and d_len/d_words/d_ext
-// the bucket-major supermer streams.
+// Bins per rank: fixed by the config, or sized so that a bin holds ~HSK_TARGET_BIN k-mer slots; every
+// rank must use the same number, so the largest input of any rank decides.
+static const u64 HSK_TARGET_BIN = 3072;
+
+static int choose_bins(hsk_ctx *c, u64 nbytes)
+{
+    if (c->cfg.buckets_per_rank > 0) return 0;
+    u64 mx = nbytes;
+    if (c->cfg.nranks > 1) {
+        CK(c->d_cursor.ensure(64));
+        CK(c->h_cursor.ensure(64));
+        c->h_cursor.as<u64>()[4] = nbytes;
+        CK(cudaMemcpyAsync(c->d_cursor.as<u64>() + 4, c->h_cursor.as<u64>() + 4, 8, cudaMemcpyHostToDevice, c->stream));
+        NK(g_nccl.AllReduce(c->d_cursor.as<u64>() + 4, c->d_cursor.as<u64>() + 5, 1, ncclUint64, ncclMax, c->comm, c->stream));
+        CK(cudaMemcpyAsync(c->h_cursor.as<u64>() + 5, c->d_cursor.as<u64>() + 5, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        mx = c->h_cursor.as<u64>()[5];
+    }
+    u64 tg = (mx * 4 + HSK_TARGET_BIN - 1) / HSK_TARGET_BIN;
+    tg = std::max<u64>(64, (tg + 63) / 64 * 64);
+    tg = std::min<u64>(tg, MAX_BINS / (u64)c->cfg.nranks);
+    c->tg = (u32)tg;
+    c->tt = c->tg * (u32)c->cfg.nranks;
+    return 0;
+}
+
+// Device layout of d_bucket (u64 units): [bin_k T][bin_cw T][start T+1][wstart T+1][cursor T][run_cursor 1]
+// On return h_bucket holds the first four arrays and d_len/d_words/d_ext the bin-major supermer streams.
 static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
                        const u32 *d_read_len, u64 nreads, int readid_base)
 {
+    if (choose_bins(c, nbytes)) return 1;
     const u32 T = c->tt;
     cudaStream_t s = c->stream;
     ExtractParams P;
@@ -284,32 +313,47 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     P.ntiles = (nbytes + EX_TILE_BYTES - 1) / EX_TILE_BYTES;
     u32 nctas = (u32)std::min<u64>(std::max<u64>(P.ntiles, 1), (u64)c->sm_count * 4);
     P.tiles_per_cta = (P.ntiles + nctas - 1) / nctas;
-    P.k = c->cfg.k; P.m = c->m_eff; P.nbuckets = T; P.readid_base = readid_base;
-    if (P.tiles_per_cta * (u64)EX_TSK >= (1ull << 31)) return fail("input too large for one rank (%llu bytes)", (unsigned long long)nbytes);
+    P.k = c->cfg.k; P.m = c->m_eff; P.nbins = T; P.readid_base = readid_base;
 
-    const size_t bucket_u64 = 3 * (size_t)T + 2 * ((size_t)T + 1);
-    CK(c->d_cta_totals.ensure((size_t)nctas * T * sizeof(uint2)));
-    CK(c->d_bucket.ensure(bucket_u64 * 8));
-    CK(c->h_bucket.ensure(bucket_u64 * 8));
+    const size_t host_u64 = 2 * (size_t)T + 2 * ((size_t)T + 1);
+    const size_t dev_u64 = host_u64 + (size_t)T + 1;
+    CK(c->d_bucket.ensure(dev_u64 * 8));
+    CK(c->h_bucket.ensure((host_u64 + 1) * 8));
+    CK(c->d_tile_hdr.ensure((P.ntiles + 1) * sizeof(ulonglong2)));
     u64 *d_kmers = c->d_bucket.as<u64>();
-    u64 *d_count = d_kmers + T, *d_wordsn = d_count + T, *d_start = d_wordsn + T, *d_wstart = d_start + T + 1;
-    CK(cudaMemsetAsync(d_kmers, 0, bucket_u64 * 8, s));
+    u64 *d_cw = d_kmers + T, *d_start = d_cw + T, *d_wstart = d_start + T + 1, *d_cur = d_wstart + T + 1, *d_runcur = d_cur + T;
 
+    const u64 nslots = nbytes * 4;
+    u64 run_cap = nslots / 3 + 1024;
     c->begin(c->ev_extract);
-    CK(launch_supermer_count(P, nctas, c->d_cta_totals.as<uint2>(), d_kmers, s));
-    CK(launch_bucket_scan(c->d_cta_totals.as<uint2>(), nctas, T, d_count, d_wordsn, d_start, d_wstart, s));
-    CK(cudaMemcpyAsync(c->h_bucket.p, c->d_bucket.p, bucket_u64 * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const u64 *h_start = c->h_bucket.as<u64>() + 3 * (size_t)T;
+    for (int attempt = 0;; ++attempt) {
+        CK(c->d_run_list.ensure(run_cap * 8));
+        CK(cudaMemsetAsync(d_kmers, 0, dev_u64 * 8, s));
+        CK(launch_supermer_count(P, nctas, d_cw, d_kmers, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur,
+                                 run_cap, s));
+        CK(launch_bin_scan(d_cw, T, d_start, d_wstart, s));
+        CK(cudaMemcpyAsync(c->h_bucket.p, c->d_bucket.p, host_u64 * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_bucket.as<u64>() + host_u64, d_runcur, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        c->stats.n_launches += 2;
+        if (c->h_bucket.as<u64>()[host_u64] <= run_cap) break;
+        if (attempt) return fail("internal: run list overflow after resize");
+        run_cap = nslots + 1024;   // pathological input (runs shorter than 3 k-mers on average): worst-case list
+    }
+    const u64 *h_cw = c->h_bucket.as<u64>() + T;
+    const u64 *h_start = c->h_bucket.as<u64>() + 2 * (size_t)T;
     const u64 *h_wstart = h_start + T + 1;
     const u64 S = h_start[T], W = h_wstart[T];
+    for (u32 b = 0; b < T; ++b)
+        if ((h_cw[b] >> 32) >= 0xFFFFFFF0ull || (h_cw[b] & 0xFFFFFFFFull) >= 0xFFFFFFF0ull)
+            return fail("bin %u holds too many supermers for 32-bit in-bin offsets; raise buckets_per_rank", b);
     CK(c->d_len.ensure((S + 8) * sizeof(u16)));
     CK(c->d_words.ensure((W + 8) * sizeof(u32)));
     if (c->cfg.ext) CK(c->d_ext.ensure((S + 8) * sizeof(u64)));
-    CK(launch_supermer_scatter(P, nctas, c->cfg.ext != 0, c->d_cta_totals.as<uint2>(), d_start, d_wstart, c->d_len.as<u16>(),
-                               c->d_words.as<u32>(), c->d_ext.as<u64>(), s));
+    CK(launch_supermer_scatter(P, nctas, c->cfg.ext != 0, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_cur, d_start,
+                               d_wstart, c->d_len.as<u16>(), c->d_words.as<u32>(), c->d_ext.as<u64>(), s));
     c->end(c->ev_extract);
-    c->stats.n_launches += 3;
+    c->stats.n_launches += 1;
     c->stats.n_supermers = S;
     c->stats.supermer_bytes = S * (2 + (c->cfg.ext ? 8 : 0)) + W * 4;
     u64 nk = 0;
@@ -324,7 +368,6 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
 {
     CK(cudaSetDevice(c->cfg.device));
     cudaStream_t s = c->stream;
-    const u32 T = c->tt, TG = c->tg;
     const int G = c->cfg.nranks, me = c->cfg.rank;
     const int NW = c->nwords;
     const bool ext = c->cfg.ext != 0;
@@ -338,26 +381,26 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     CK(cudaEventRecord(ev_t0, s));
 
     if (run_extract(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base)) return 1;
+    const u32 T = c->tt, TG = c->tg;
     const u64 *hb = c->h_bucket.as<u64>();
-    const u64 *h_kmers = hb, *h_count = hb + T, *h_wordsn = hb + 2 * (size_t)T, *h_start = hb + 3 * (size_t)T,
-              *h_wstart = h_start + T + 1;
+    const u64 *h_start = hb + 2 * (size_t)T, *h_wstart = h_start + T + 1;
 
-    // ---- totals of every source rank for every bucket: tot[src][3][T] (kmers, count, words)
-    std::vector<u64> tot((size_t)G * 3 * T);
+    // ---- totals of every source rank for every bin: tot[src][2][T] = (k-mers, supermers << 32 | words)
+    std::vector<u64> tot((size_t)G * 2 * T);
     if (G == 1) {
-        memcpy(tot.data(), hb, (size_t)3 * T * 8);
+        memcpy(tot.data(), hb, (size_t)2 * T * 8);
     } else {
-        CK(c->d_alltot.ensure((size_t)G * 3 * T * 8));
-        CK(c->h_alltot.ensure((size_t)G * 3 * T * 8));
+        CK(c->d_alltot.ensure((size_t)G * 2 * T * 8));
+        CK(c->h_alltot.ensure((size_t)G * 2 * T * 8));
         c->begin(c->ev_exchange);
-        NK(g_nccl.AllGather(c->d_bucket.p, c->d_alltot.p, (size_t)3 * T, ncclUint64, c->comm, s));
-        CK(cudaMemcpyAsync(c->h_alltot.p, c->d_alltot.p, (size_t)G * 3 * T * 8, cudaMemcpyDeviceToHost, s));
+        NK(g_nccl.AllGather(c->d_bucket.p, c->d_alltot.p, (size_t)2 * T, ncclUint64, c->comm, s));
+        CK(cudaMemcpyAsync(c->h_alltot.p, c->d_alltot.p, (size_t)G * 2 * T * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        memcpy(tot.data(), c->h_alltot.p, (size_t)G * 3 * T * 8);
+        memcpy(tot.data(), c->h_alltot.p, (size_t)G * 2 * T * 8);
     }
-    auto TK = [&](int src, u32 b) { return tot[((size_t)src * 3 + 0) * T + b]; };
-    auto TC = [&](int src, u32 b) { return tot[((size_t)src * 3 + 1) * T + b]; };
-    auto TW = [&](int src, u32 b) { return tot[((size_t)src * 3 + 2) * T + b]; };
+    auto TK = [&](int src, u32 b) { return tot[((size_t)src * 2 + 0) * T + b]; };
+    auto TC = [&](int src, u32 b) { return tot[((size_t)src * 2 + 1) * T + b] >> 32; };
+    auto TW = [&](int src, u32 b) { return tot[((size_t)src * 2 + 1) * T + b] & 0xFFFFFFFFull; };
     const u32 b_lo = (u32)me * TG, b_hi = b_lo + TG;
 
     // ---- stage 3: supermer all-to-all (whole bucket ranges, one grouped send/recv per peer)
@@ -467,7 +510,6 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
             if (b < b_hi) { ai += TC(src, b); aw += TW(src, b); }
         }
     }
-    (void)h_count; (void)h_wordsn; (void)h_kmers;
     for (auto &bt : batches) {
         Planes A, B;
         for (int w = 0; w < MAX_WORDS; ++w) { A.p[w] = w < NW ? c->d_keys[0][w].as<u64>() : nullptr; B.p[w] = w < NW ? c->d_keys[1][w].as<u64>() : nullptr; }
@@ -729,7 +771,9 @@ int hsk_debug_extract(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const 
                     readid_base)) return 1;
     const u32 T = c->tt;
     const u64 *hb = c->h_bucket.as<u64>();
-    const u64 S = hb[3 * (size_t)T + T], W = hb[3 * (size_t)T + (T + 1) + T];
+    const u64 S = hb[2 * (size_t)T + T], W = hb[2 * (size_t)T + (T + 1) + T];
+    c->h_dbg.resize(2 * (size_t)T);
+    for (u32 b = 0; b < T; ++b) { c->h_dbg[b] = hb[T + b] >> 32; c->h_dbg[T + b] = hb[T + b] & 0xFFFFFFFFull; }
     CK(c->h_ocnt.ensure((S + 1) * 2));
     CK(c->h_owords.ensure((W + 1) * 4));
     if (c->cfg.ext) CK(c->h_oocc_off.ensure((S + 1) * 8));
@@ -739,8 +783,8 @@ int hsk_debug_extract(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const 
     CK(cudaStreamSynchronize(c->stream));
     out->n_buckets = T;
     out->bucket_kmers = reinterpret_cast<const uint64_t *>(hb);
-    out->bucket_count = reinterpret_cast<const uint64_t *>(hb + T);
-    out->bucket_words = reinterpret_cast<const uint64_t *>(hb + 2 * (size_t)T);
+    out->bucket_count = reinterpret_cast<const uint64_t *>(c->h_dbg.data());
+    out->bucket_words = reinterpret_cast<const uint64_t *>(c->h_dbg.data() + T);
     out->n_supermers = S;
     out->n_words = W;
     out->len = c->h_ocnt.as<u16>();

@@ -6,40 +6,49 @@
 // SupermerEncoder::encode / copy_bits (:1096-1148), plus the per-thread ScatteredSupermers staging
 // (:253-358).  Not a translation: the reference walks each read with a deque and materialises one
 // int per k-mer; here the whole packed buffer is treated as one flat sequence of 2-bit slots,
-// processed in tiles by persistent CTAs:
+// processed in tiles by persistent CTAs, in two passes:
 //
-//   A. tile bytes -> shared memory as big-endian 32-bit words (16 bases per word)
-//   B. every thread rolls forward/reverse m-mers over 16 consecutive slots, hashes the canonical
-//      m-mer of every slot into shared memory, and derives a 16-bit "valid k-mer start" mask from
-//      the read offset table
-//   C. window minimum over the K-M+1 hashes of every k-mer slot -> bucket id (or INVALID)
-//   D. run boundaries (bucket change / validity change / tile edge) -> bitmap -> compacted run list
-//   E. one supermer per valid run: count pass accumulates per-CTA per-bucket totals, scatter pass
-//      claims (index, word offset) from a shared-memory cursor and writes the length, optional
-//      (pos, rid) and the re-packed bases into the bucket's region.
+//   pass A (k_supermer_count), per tile
+//     A. tile bytes -> shared memory as big-endian 32-bit words (16 bases per word)
+//     B. every thread rolls forward/reverse m-mers over 16 consecutive slots, hashes the canonical
+//        m-mer of every slot into shared memory, and derives a 16-bit "valid k-mer start" mask from
+//        the read offset table
+//     C. window minimum over the K-M+1 hashes of every k-mer slot (block-wise suffix/prefix minima,
+//        O(1) shared-memory traffic per slot) -> bin id (or INVALID)
+//     D. run boundaries (bin change / validity change / tile edge) -> bitmap -> compacted run list
+//     E. per valid run: reduce (count, words, k-mers) into the global per-bin totals, and store the
+//        run list (start, bin) of the tile for pass B
+//   k_bin_scan: exclusive prefix of the per-bin totals -> bin starts in the supermer streams
+//   pass B (k_supermer_scatter), per tile: re-stage the bytes, read the run list, and for every
+//     valid run claim (index, word offset) in its bin with one 64-bit atomic and write the length,
+//     optional (pos, rid) and the re-packed bases.  No hashing is repeated.
 //
-// A supermer is a run of consecutive k-mers of one read with the same bucket, stored as
-// len (u16 bases) + ceil(len/16) 32-bit words, 16 bases per word from the top bits.  Where the
-// reference splits supermers (250-base cap, kmerops.cpp:1120) and how it hashes are free choices:
-// only the multiset of k-mers per bucket matters, and a canonical k-mer always lands in the same
-// bucket because the bucket is a function of its set of canonical m-mers.
+// A supermer is a run of consecutive k-mers of one read with the same bin, stored as
+// len (u16 bases) + ceil(len/16) 32-bit words, 16 bases per word from the top bits.  Bins are
+// fine-grained (a few thousand k-mers each) so that a bin can later be expanded, sorted and counted
+// entirely inside one CTA's shared memory.  Where the reference splits supermers (250-base cap,
+// kmerops.cpp:1120) and how it hashes are free choices: only the multiset of k-mers per bin matters,
+// and a canonical k-mer always lands in the same bin because the bin is a function of its set of
+// canonical m-mers.
 #include "kernels.cuh"
 
 namespace hsk {
 
 struct ExtractSmem {
     u32 wbe[EX_WORDS];                 // bases of the tile, 16 per word, first base in the top bits
-    u32 hs[EX_TS + EX_TS / 32 + 8];    // m-mer hashes, padded 1 word per 32 to spread banks
-    u16 st[EX_TS];                     // per k-mer slot: bucket or EX_INVALID
+    u32 hs[EX_TS + EX_TS / 32 + 8];    // m-mer hashes, then in-place suffix minima (1 pad word per 32)
+    u32 pm[EX_TS + EX_TS / 32 + 8];    // prefix minima inside blocks of w
+    u32 st[EX_TSK];                    // per k-mer slot: bin or EX_INVALID
     u16 runs[EX_TSK + 8];              // compacted run starts (+ sentinel)
     u32 bm[EX_TS / 32];                // run-boundary bitmap
     u32 woff[EX_TS / 32 + 1];          // exclusive popcount prefix of bm
     u16 vm[EX_THREADS];                // valid-start mask of the thread's 16 slots
     u64 rlo, rhi;                      // reads overlapping the tile
+    u64 run_base;                      // where this tile's run list starts in the global list
     u32 nruns;
 };
 
-__device__ __forceinline__ int hs_idx(int q) { return q + (q >> 5); }
+__device__ __forceinline__ int hx(int q) { return q + (q >> 5); }
 
 // largest r in [lo, hi] with off[r] <= byte (off is non-decreasing; caller guarantees off[lo] <= byte)
 __device__ __forceinline__ u64 find_read(const u64 *__restrict__ off, u64 lo, u64 hi, u64 byte)
@@ -51,15 +60,10 @@ __device__ __forceinline__ u64 find_read(const u64 *__restrict__ off, u64 lo, u6
     return lo;
 }
 
-// Phases A-D for one tile.  On return sm.runs[0..nruns] / sm.st describe the runs of the tile.
-__device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &P, u64 tile)
+__device__ __forceinline__ void stage_tile(ExtractSmem &sm, const ExtractParams &P, u64 tile)
 {
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
     const u64 byte0 = tile * (u64)EX_TILE_BYTES;
-    const u64 slot0 = byte0 * 4;
-
-    // ---- A: stage bytes (16-byte vectors, byte-swapped to big-endian words)
     if (tid < EX_WORDS / 4) {
         u64 b = byte0 + (u64)tid * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -69,15 +73,25 @@ __device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &
         sm.wbe[4 * tid + 2] = __byte_perm(v.z, 0, 0x0123);
         sm.wbe[4 * tid + 3] = __byte_perm(v.w, 0, 0x0123);
     }
-    if (tid == 0) {
+    if (tid == 32) {
         // reads overlapping [byte0, byte0 + tile bytes): read_off[nreads] = nbytes
-        u64 lo = 0;
-        if (P.nreads > 0 && byte0 < P.nbytes) lo = find_read(P.read_off, 0, P.nreads - 1, byte0);
-        u64 last = byte0 + EX_TILE_BYTES;
-        u64 hi = lo;
-        if (P.nreads > 0 && byte0 < P.nbytes) hi = find_read(P.read_off, lo, P.nreads - 1, last);
+        u64 lo = 0, hi = 0;
+        if (P.nreads > 0 && byte0 < P.nbytes) {
+            lo = find_read(P.read_off, 0, P.nreads - 1, byte0);
+            hi = find_read(P.read_off, lo, P.nreads - 1, byte0 + EX_TILE_BYTES);
+        }
         sm.rlo = lo; sm.rhi = hi;
     }
+}
+
+// Phases A-D for one tile.  On return sm.runs[0..nruns] / sm.st describe the runs of the tile.
+__device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &P, u64 tile)
+{
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const u64 slot0 = tile * (u64)EX_TSK;
+
+    stage_tile(sm, P, tile);
     __syncthreads();
 
     // ---- B: rolling canonical m-mer hashes of 16 consecutive slots
@@ -87,21 +101,23 @@ __device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &
         u64 lo = ((u64)sm.wbe[tid + 2] << 32);
         const u64 mask = (m == 32) ? ~0ull : ((1ull << (2 * m)) - 1);
         const int rcs = 2 * (m - 1);
-        u64 fwd = 0, rc = 0;
-        for (int j = 0; j < m - 1; ++j) {
-            u64 c = hi >> 62;
-            hi = (hi << 2) | (lo >> 62); lo <<= 2;
-            fwd = ((fwd << 2) | c) & mask;
-            rc = (rc >> 2) | ((3 - c) << rcs);
+        // m-mer at my first slot: the top m bases of the window, and their reverse complement
+        u64 fwd = hi >> (64 - 2 * m);
+        u64 rc = revcomp64(hi) & mask;
+        // consume the m bases
+        if (m == 32) { hi = lo; lo = 0; } else { hi = (hi << (2 * m)) | (lo >> (64 - 2 * m)); lo <<= 2 * m; }
+        {
+            u64 canon = fwd < rc ? fwd : rc;
+            sm.hs[hx(tid * EX_R)] = mmer_hash(canon);
         }
 #pragma unroll
-        for (int j = 0; j < EX_R; ++j) {
+        for (int j = 1; j < EX_R; ++j) {
             u64 c = hi >> 62;
             hi = (hi << 2) | (lo >> 62); lo <<= 2;
             fwd = ((fwd << 2) | c) & mask;
             rc = (rc >> 2) | ((3 - c) << rcs);
             u64 canon = fwd < rc ? fwd : rc;
-            sm.hs[hs_idx(tid * EX_R + j)] = mmer_hash(canon);
+            sm.hs[hx(tid * EX_R + j)] = mmer_hash(canon);
         }
 
         // valid k-mer starts among my 16 slots
@@ -112,36 +128,47 @@ __device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &
             u64 rstart = __ldg(P.read_off + r) * 4;
             u64 rnext = __ldg(P.read_off + r + 1) * 4;
             u64 rend = rstart + __ldg(P.read_len + r);
+            if (p0 + EX_R + (u64)P.k <= rend + 1 && p0 >= rstart) {
+                vmask = 0xFFFFu;   // common case: all 16 windows inside the read
+            } else {
 #pragma unroll
-            for (int j = 0; j < EX_R; ++j) {
-                u64 p = p0 + j;
-                while (p >= rnext && r + 1 < P.nreads) {
-                    ++r;
-                    rstart = rnext;
-                    rnext = __ldg(P.read_off + r + 1) * 4;
-                    rend = rstart + __ldg(P.read_len + r);
+                for (int j = 0; j < EX_R; ++j) {
+                    u64 p = p0 + j;
+                    while (p >= rnext && r + 1 < P.nreads) {
+                        ++r;
+                        rstart = rnext;
+                        rnext = __ldg(P.read_off + r + 1) * 4;
+                        rend = rstart + __ldg(P.read_len + r);
+                    }
+                    if (p >= rstart && p + (u64)P.k <= rend) vmask |= 1u << j;
                 }
-                if (p >= rstart && p + (u64)P.k <= rend) vmask |= 1u << j;
             }
         }
         sm.vm[tid] = (u16)vmask;
     }
     __syncthreads();
 
-    // ---- C: minimizer = window minimum of the hashes of the k-mer's m-mers -> bucket
+    // ---- C: minimizer = minimum of the w = K-M+1 hashes starting at the slot.
+    // Blocks of w slots: pm = prefix minima inside a block, hs becomes suffix minima inside a block;
+    // min over [q, q+w) = min(suffix[q], prefix[q+w-1]).
     {
         const int w = P.k - P.m + 1;
+        const int nblocks = (EX_TS + w - 1) / w;
+        for (int b = tid; b < nblocks; b += EX_THREADS) {
+            const int s = b * w, e = min(s + w, (int)EX_TS);
+            u32 run = 0xFFFFFFFFu;
+            for (int q = s; q < e; ++q) { run = min(run, sm.hs[hx(q)]); sm.pm[hx(q)] = run; }
+            run = 0xFFFFFFFFu;
+            for (int q = e - 1; q >= s; --q) { run = min(run, sm.hs[hx(q)]); sm.hs[hx(q)] = run; }
+        }
+        __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < EX_R; ++j) {
             int q = j * EX_THREADS + tid;
             if (q < EX_TSK) {
                 u32 st = EX_INVALID;
-                if ((sm.vm[q >> 4] >> (q & 15)) & 1) {
-                    u32 mn = 0xFFFFFFFFu;
-                    for (int x = 0; x < w; ++x) mn = min(mn, sm.hs[hs_idx(q + x)]);
-                    st = hash_bucket(mn, P.nbuckets);
-                }
-                sm.st[q] = (u16)st;
+                if ((sm.vm[q >> 4] >> (q & 15)) & 1) st = hash_bucket(min(sm.hs[hx(q)], sm.pm[hx(q + w - 1)]), P.nbins);
+                sm.st[q] = st;
             }
         }
     }
@@ -185,65 +212,81 @@ __device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &
     __syncthreads();
 }
 
-// ---- count pass: per-CTA per-bucket totals (supermers, words) + global k-mers per bucket --------
-__global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, uint2 *__restrict__ cta_totals,
-                                                                u64 *__restrict__ bucket_kmers)
+// ---- pass A: per-bin totals + the run list of every tile ------------------------------------------
+// bin_cw[b] = (supermers << 32) | words, bin_k[b] = k-mers.  Run list entry = (start << 32) | bin for
+// valid runs only; tile_hdr[tile] = (first entry, number of entries).
+__global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, u64 *__restrict__ bin_cw,
+                                                                u64 *__restrict__ bin_k, u64 *__restrict__ run_list,
+                                                                ulonglong2 *__restrict__ tile_hdr,
+                                                                u64 *__restrict__ run_cursor, u64 run_capacity)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     ExtractSmem &sm = *reinterpret_cast<ExtractSmem *>(smraw);
-    u32 *s_cnt = reinterpret_cast<u32 *>(smraw + sizeof(ExtractSmem));
-    u32 *s_words = s_cnt + P.nbuckets;
-    u32 *s_kmers = s_words + P.nbuckets;
-    for (u32 b = threadIdx.x; b < 3 * P.nbuckets; b += EX_THREADS) s_cnt[b] = 0;
-    __syncthreads();
-
+    __shared__ u32 s_nvalid;
     const u64 t0 = (u64)blockIdx.x * P.tiles_per_cta;
     const u64 t1 = min(t0 + P.tiles_per_cta, P.ntiles);
     for (u64 tile = t0; tile < t1; ++tile) {
+        if (threadIdx.x == 0) s_nvalid = 0;
         tile_runs(sm, P, tile);
         const u32 nruns = sm.nruns;
-        for (u32 j = threadIdx.x; j < nruns; j += EX_THREADS) {
-            u32 start = sm.runs[j], end = sm.runs[j + 1];
-            u32 b = sm.st[start];
-            if (b == EX_INVALID) continue;
-            u32 n = end - start;
-            u32 len = n + P.k - 1;
-            atomicAdd(&s_cnt[b], 1u);
-            atomicAdd(&s_words[b], (len + 15) >> 4);
-            atomicAdd(&s_kmers[b], n);
+        // compact the valid runs of the tile: warp-aggregated claim inside the tile
+        for (u32 base = 0; base < nruns; base += EX_THREADS) {
+            const u32 j = base + threadIdx.x;
+            bool valid = false;
+            u32 start = 0, b = 0, n = 0;
+            if (j < nruns) {
+                start = sm.runs[j];
+                b = sm.st[start];
+                valid = (b != EX_INVALID);
+                n = sm.runs[j + 1] - start;
+            }
+            const u32 bal = __ballot_sync(0xFFFFFFFFu, valid);
+            u32 wbase = 0;
+            if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_nvalid, (u32)__popc(bal));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (valid) {
+                const u32 len = n + P.k - 1;
+                atomicAdd(&bin_cw[b], (1ull << 32) | (u64)((len + 15) >> 4));
+                atomicAdd(&bin_k[b], (u64)n);
+                // reuse pm[] as the tile's staging area for (start, bin)
+                const u32 slot = wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
+                sm.pm[slot] = b;
+                sm.hs[slot] = start | (n << 16);
+            }
         }
         __syncthreads();
-    }
-    for (u32 b = threadIdx.x; b < P.nbuckets; b += EX_THREADS) {
-        cta_totals[(u64)blockIdx.x * P.nbuckets + b] = make_uint2(s_cnt[b], s_words[b]);
-        if (s_kmers[b]) atomicAdd(&bucket_kmers[b], (u64)s_kmers[b]);
+        const u32 nv = s_nvalid;
+        if (threadIdx.x == 0) {
+            sm.run_base = atomicAdd(run_cursor, (u64)nv);
+            tile_hdr[tile] = make_ulonglong2(sm.run_base, (u64)nv);
+        }
+        __syncthreads();
+        const u64 rb = sm.run_base;
+        if (rb + nv <= run_capacity)   // otherwise the host sees run_cursor > capacity and retries with a larger list
+            for (u32 j = threadIdx.x; j < nv; j += EX_THREADS) run_list[rb + j] = ((u64)sm.hs[j] << 32) | sm.pm[j];
+        __syncthreads();
     }
 }
 
-// ---- bucket scan: per bucket, exclusive prefix over CTAs (in place) and bucket totals; then
-// exclusive prefix over buckets -> bucket starts.  One block.
-__global__ void __launch_bounds__(1024) k_bucket_scan(uint2 *__restrict__ cta_totals, u32 nctas, u32 nbuckets,
-                                                       u64 *__restrict__ bucket_count, u64 *__restrict__ bucket_words,
-                                                       u64 *__restrict__ bucket_start, u64 *__restrict__ word_start)
+// ---- bin scan: exclusive prefix over bins of (supermers, words) -> bin starts.  One block. ---------
+__global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_cw, u32 nbins, u64 *__restrict__ bin_start,
+                                                    u64 *__restrict__ word_start)
 {
     __shared__ u64 s_c[32], s_w[32];
     __shared__ u64 carry_c, carry_w;
     if (threadIdx.x == 0) { carry_c = 0; carry_w = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u32 base = 0; base < nbuckets; base += 1024) {
-        u32 b = base + threadIdx.x;
-        u64 tc = 0, tw = 0;
-        if (b < nbuckets) {
-            for (u32 c = 0; c < nctas; ++c) {
-                uint2 v = cta_totals[(u64)c * nbuckets + b];
-                cta_totals[(u64)c * nbuckets + b] = make_uint2((u32)tc, (u32)tw);
-                tc += v.x; tw += v.y;
-            }
-            bucket_count[b] = tc;
-            bucket_words[b] = tw;
+    constexpr int PER = 4;
+    for (u32 base = 0; base < nbins; base += 1024 * PER) {
+        u64 c[PER], w[PER], tc = 0, tw = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            u32 b = base + threadIdx.x * PER + i;
+            u64 v = b < nbins ? bin_cw[b] : 0;
+            c[i] = v >> 32; w[i] = v & 0xFFFFFFFFull;
+            tc += c[i]; tw += w[i];
         }
-        // block exclusive scan of (tc, tw)
         u64 ic = tc, iw = tw;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -267,58 +310,77 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(uint2 *__restrict__ cta_to
         __syncthreads();
         u64 ec = carry_c + s_c[warp] + ic - tc;
         u64 ew = carry_w + s_w[warp] + iw - tw;
-        if (b < nbuckets) { bucket_start[b] = ec; word_start[b] = ew; }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            u32 b = base + threadIdx.x * PER + i;
+            if (b < nbins) { bin_start[b] = ec; word_start[b] = ew; }
+            ec += c[i]; ew += w[i];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) { carry_c = ec + tc; carry_w = ew + tw; }
+        if (threadIdx.x == 1023) { carry_c = ec; carry_w = ew; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { bucket_start[nbuckets] = carry_c; word_start[nbuckets] = carry_w; }
+    if (threadIdx.x == 0) { bin_start[nbins] = carry_c; word_start[nbins] = carry_w; }
 }
 
-// ---- scatter pass ------------------------------------------------------------------------------
+// ---- pass B ---------------------------------------------------------------------------------------
 template <bool EXT>
-__global__ void __launch_bounds__(EX_THREADS) k_supermer_scatter(ExtractParams P, const uint2 *__restrict__ cta_base,
-                                                                  const u64 *__restrict__ bucket_start,
+__global__ void __launch_bounds__(EX_THREADS) k_supermer_scatter(ExtractParams P, const u64 *__restrict__ run_list,
+                                                                  const ulonglong2 *__restrict__ tile_hdr,
+                                                                  u64 *__restrict__ bin_cursor,
+                                                                  const u64 *__restrict__ bin_start,
                                                                   const u64 *__restrict__ word_start,
                                                                   u16 *__restrict__ out_len, u32 *__restrict__ out_words,
                                                                   u64 *__restrict__ out_ext)
 {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    ExtractSmem &sm = *reinterpret_cast<ExtractSmem *>(smraw);
-    u64 *s_cur = reinterpret_cast<u64 *>(smraw + ((sizeof(ExtractSmem) + 7) & ~(size_t)7));
-    for (u32 b = threadIdx.x; b < P.nbuckets; b += EX_THREADS) s_cur[b] = 0;
-    __syncthreads();
-    const uint2 *my_base = cta_base + (u64)blockIdx.x * P.nbuckets;
-
+    __shared__ u32 wbe[EX_WORDS];
+    __shared__ u64 s_rlo, s_rhi;
+    const int tid = threadIdx.x;
     const u64 t0 = (u64)blockIdx.x * P.tiles_per_cta;
     const u64 t1 = min(t0 + P.tiles_per_cta, P.ntiles);
     for (u64 tile = t0; tile < t1; ++tile) {
-        tile_runs(sm, P, tile);
-        const u32 nruns = sm.nruns;
+        const u64 byte0 = tile * (u64)EX_TILE_BYTES;
+        if (tid < EX_WORDS / 4) {
+            u64 b = byte0 + (u64)tid * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b < P.nbytes_padded) v = __ldg(reinterpret_cast<const uint4 *>(P.packed + b));
+            wbe[4 * tid + 0] = __byte_perm(v.x, 0, 0x0123);
+            wbe[4 * tid + 1] = __byte_perm(v.y, 0, 0x0123);
+            wbe[4 * tid + 2] = __byte_perm(v.z, 0, 0x0123);
+            wbe[4 * tid + 3] = __byte_perm(v.w, 0, 0x0123);
+        }
+        if (EXT && tid == 32) {
+            u64 lo = 0, hi = 0;
+            if (P.nreads > 0 && byte0 < P.nbytes) {
+                lo = find_read(P.read_off, 0, P.nreads - 1, byte0);
+                hi = find_read(P.read_off, lo, P.nreads - 1, byte0 + EX_TILE_BYTES);
+            }
+            s_rlo = lo; s_rhi = hi;
+        }
+        const ulonglong2 hdr = tile_hdr[tile];
+        __syncthreads();
         const u64 slot0 = tile * (u64)EX_TSK;
-        for (u32 j = threadIdx.x; j < nruns; j += EX_THREADS) {
-            u32 start = sm.runs[j], end = sm.runs[j + 1];
-            u32 b = sm.st[start];
-            if (b == EX_INVALID) continue;
-            u32 n = end - start;
-            u32 len = n + P.k - 1;
-            u32 nw = (len + 15) >> 4;
-            u64 old = atomicAdd(&s_cur[b], (1ull << 40) | (u64)nw);
-            uint2 cb = __ldg(my_base + b);
-            u64 gi = __ldg(bucket_start + b) + cb.x + (old >> 40);
-            u64 gw = __ldg(word_start + b) + cb.y + (old & ((1ull << 40) - 1));
+        for (u32 j = tid; j < (u32)hdr.y; j += EX_THREADS) {
+            const u64 e = __ldg(run_list + hdr.x + j);
+            const u32 b = (u32)e;
+            const u32 start = (u32)(e >> 32) & 0xFFFFu, n = (u32)(e >> 48);
+            const u32 len = n + P.k - 1;
+            const u32 nw = (len + 15) >> 4;
+            const u64 old = atomicAdd(&bin_cursor[b], (1ull << 32) | (u64)nw);
+            const u64 gi = __ldg(bin_start + b) + (old >> 32);
+            const u64 gw = __ldg(word_start + b) + (old & 0xFFFFFFFFull);
             out_len[gi] = (u16)len;
             if (EXT) {
-                u64 p = slot0 + start;
-                u64 r = find_read(P.read_off, sm.rlo, sm.rhi, p >> 2);
-                u64 pos = p - __ldg(P.read_off + r) * 4;
-                u32 rid = (u32)((long long)r + (long long)P.readid_base);
+                const u64 p = slot0 + start;
+                const u64 r = find_read(P.read_off, s_rlo, s_rhi, p >> 2);
+                const u64 pos = p - __ldg(P.read_off + r) * 4;
+                const u32 rid = (u32)((long long)r + (long long)P.readid_base);
                 out_ext[gi] = (pos << 32) | (u64)rid;
             }
             for (u32 x = 0; x < nw; ++x) {
-                u32 q = start + 16 * x;
-                u32 wv = __funnelshift_l(sm.wbe[(q >> 4) + 1], sm.wbe[q >> 4], 2 * (q & 15));
-                u32 rem = len - 16 * x;
+                const u32 q = start + 16 * x;
+                u32 wv = __funnelshift_l(wbe[(q >> 4) + 1], wbe[q >> 4], 2 * (q & 15));
+                const u32 rem = len - 16 * x;
                 if (rem < 16) wv &= ~0u << (32 - 2 * rem);
                 out_words[gw + x] = wv;
             }
@@ -327,40 +389,31 @@ __global__ void __launch_bounds__(EX_THREADS) k_supermer_scatter(ExtractParams P
     }
 }
 
-size_t extract_count_smem(u32 nbuckets) { return sizeof(ExtractSmem) + 3 * (size_t)nbuckets * sizeof(u32); }
-size_t extract_scatter_smem(u32 nbuckets) { return ((sizeof(ExtractSmem) + 7) & ~(size_t)7) + (size_t)nbuckets * sizeof(u64); }
-
-cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, uint2 *cta_totals, u64 *bucket_kmers, cudaStream_t s)
+cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_cw, u64 *bin_k, u64 *run_list,
+                                  ulonglong2 *tile_hdr, u64 *run_cursor, u64 run_capacity, cudaStream_t s)
 {
-    size_t smem = extract_count_smem(P.nbuckets);
-    cudaError_t e = cudaFuncSetAttribute(k_supermer_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_supermer_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExtractSmem));
     if (e != cudaSuccess) return e;
-    k_supermer_count<<<nctas, EX_THREADS, smem, s>>>(P, cta_totals, bucket_kmers);
+    k_supermer_count<<<nctas, EX_THREADS, sizeof(ExtractSmem), s>>>(P, bin_cw, bin_k, run_list, tile_hdr, run_cursor, run_capacity);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bucket_scan(uint2 *cta_totals, u32 nctas, u32 nbuckets, u64 *bucket_count, u64 *bucket_words,
-                               u64 *bucket_start, u64 *word_start, cudaStream_t s)
+cudaError_t launch_bin_scan(const u64 *bin_cw, u32 nbins, u64 *bin_start, u64 *word_start, cudaStream_t s)
 {
-    k_bucket_scan<<<1, 1024, 0, s>>>(cta_totals, nctas, nbuckets, bucket_count, bucket_words, bucket_start, word_start);
+    k_bin_scan<<<1, 1024, 0, s>>>(bin_cw, nbins, bin_start, word_start);
     return cudaGetLastError();
 }
 
-cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const uint2 *cta_base,
-                                    const u64 *bucket_start, const u64 *word_start, u16 *out_len, u32 *out_words,
-                                    u64 *out_ext, cudaStream_t s)
+cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const u64 *run_list,
+                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, const u64 *bin_start,
+                                    const u64 *word_start, u16 *out_len, u32 *out_words, u64 *out_ext, cudaStream_t s)
 {
-    size_t smem = extract_scatter_smem(P.nbuckets);
-    cudaError_t e;
-    if (ext) {
-        e = cudaFuncSetAttribute(k_supermer_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_supermer_scatter<true><<<nctas, EX_THREADS, smem, s>>>(P, cta_base, bucket_start, word_start, out_len, out_words, out_ext);
-    } else {
-        e = cudaFuncSetAttribute(k_supermer_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_supermer_scatter<false><<<nctas, EX_THREADS, smem, s>>>(P, cta_base, bucket_start, word_start, out_len, out_words, out_ext);
-    }
+    if (ext)
+        k_supermer_scatter<true><<<nctas, EX_THREADS, 0, s>>>(P, run_list, tile_hdr, bin_cursor, bin_start, word_start, out_len,
+                                                              out_words, out_ext);
+    else
+        k_supermer_scatter<false><<<nctas, EX_THREADS, 0, s>>>(P, run_list, tile_hdr, bin_cursor, bin_start, word_start, out_len,
+                                                               out_words, out_ext);
     return cudaGetLastError();
 }
 

@@ -14,18 +14,19 @@ struct ExtractParams {
     u64 nreads;
     u64 ntiles, tiles_per_cta;
     int k, m;                // m already clamped to <= 32
-    u32 nbuckets;            // all ranks' buckets
+    u32 nbins;               // all ranks' bins
     int readid_base;
 };
 
-size_t extract_count_smem(u32 nbuckets);
-size_t extract_scatter_smem(u32 nbuckets);
-cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, uint2 *cta_totals, u64 *bucket_kmers, cudaStream_t s);
-cudaError_t launch_bucket_scan(uint2 *cta_totals, u32 nctas, u32 nbuckets, u64 *bucket_count, u64 *bucket_words,
-                               u64 *bucket_start, u64 *word_start, cudaStream_t s);
-cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const uint2 *cta_base,
-                                    const u64 *bucket_start, const u64 *word_start, u16 *out_len, u32 *out_words,
-                                    u64 *out_ext, cudaStream_t s);
+// pass A: bin_cw[b] += (1 << 32 | words), bin_k[b] += k-mers per supermer; run list + tile headers for pass B
+cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_cw, u64 *bin_k, u64 *run_list,
+                                  ulonglong2 *tile_hdr, u64 *run_cursor, u64 run_capacity, cudaStream_t s);
+// bin_start / word_start: nbins+1 exclusive prefixes of the supermer / word counts
+cudaError_t launch_bin_scan(const u64 *bin_cw, u32 nbins, u64 *bin_start, u64 *word_start, cudaStream_t s);
+// pass B: bin_cursor (zeroed, nbins) hands out (index << 32 | word offset) inside every bin
+cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const u64 *run_list,
+                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, const u64 *bin_start,
+                                    const u64 *word_start, u16 *out_len, u32 *out_words, u64 *out_ext, cudaStream_t s);
 
 // ---- stage 4: expand.cu ----------------------------------------------------------------------------
 constexpr int XP_THREADS = 256;
