@@ -37,7 +37,7 @@ class Stats(C.Structure):
                 ("n_batches", C.c_uint64), ("n_sort_passes", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_h2d", C.c_float), ("ms_extract", C.c_float), ("ms_exchange", C.c_float), ("ms_expand", C.c_float),
                 ("ms_sort", C.c_float), ("ms_count", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
-                ("ms_sort_passes", C.c_float), ("reserved_", C.c_float)]
+                ("ms_sort_passes", C.c_float), ("ms_bins", C.c_float), ("n_overflow_bins", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -147,8 +147,9 @@ struct hsk_ctx {
     HostBuf h_bucket;
     DevBuf d_len, d_words, d_ext;
     // exchange
-    DevBuf d_alltot, d_rlen, d_rwords, d_rext;
-    HostBuf h_alltot;
+    DevBuf d_alltot, d_rlen, d_rwords, d_rext, d_seg, d_lb;
+    HostBuf h_alltot, h_meta;
+    std::vector<u64> rbase_idx, rbase_w;
     // batch buffers
     DevBuf d_keys[2][MAX_WORDS], d_val[2], d_rscratch, d_cscratch, d_tsum, d_tbase;
     // result arena
@@ -161,7 +162,7 @@ struct hsk_ctx {
     std::vector<u64> h_dbg;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
-    std::vector<EvPair> ev_extract, ev_exchange, ev_expand, ev_sort, ev_count, ev_pass;
+    std::vector<EvPair> ev_extract, ev_exchange, ev_expand, ev_sort, ev_count, ev_pass, ev_bins;
 
     cudaEvent_t ev()
     {
@@ -259,12 +260,12 @@ void hsk_destroy(hsk_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_bucket, &c->d_len, &c->d_words,
-                    &c->d_ext, &c->d_alltot, &c->d_rlen, &c->d_rwords, &c->d_rext, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
+                    &c->d_ext, &c->d_alltot, &c->d_rlen, &c->d_rwords, &c->d_rext, &c->d_seg, &c->d_lb, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
     for (int h = 0; h < 2; ++h) for (int w = 0; w < MAX_WORDS; ++w) c->d_keys[h][w].release();
-    HostBuf *hb[] = {&c->h_read_off, &c->h_read_len, &c->h_bucket, &c->h_alltot, &c->h_cursor, &c->h_owords, &c->h_ocnt,
+    HostBuf *hb[] = {&c->h_read_off, &c->h_read_len, &c->h_bucket, &c->h_alltot, &c->h_meta, &c->h_cursor, &c->h_owords, &c->h_ocnt,
                      &c->h_oocc_off, &c->h_opos, &c->h_orid, &c->h_hist};
     for (auto *b : hb) b->release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -273,9 +274,9 @@ void hsk_destroy(hsk_ctx *c)
 }
 
 // ---- extraction (stages 1+2) -------------------------------------------------------------------------
-// Bins per rank: fixed by the config, or sized so that a bin holds ~HSK_TARGET_BIN k-mer slots; every
-// rank must use the same number, so the largest input of any rank decides.
-static const u64 HSK_TARGET_BIN = 3072;
+// Bins per rank: fixed by the config, or sized so that a bin holds on average half of what the on-chip
+// path can take (bins.cu: bin_capacity); every rank must use the same number, so the largest input of
+// any rank decides.
 
 static int choose_bins(hsk_ctx *c, u64 nbytes)
 {
@@ -291,7 +292,8 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
         CK(cudaStreamSynchronize(c->stream));
         mx = c->h_cursor.as<u64>()[5];
     }
-    u64 tg = (mx * 4 + HSK_TARGET_BIN - 1) / HSK_TARGET_BIN;
+    const u64 target = (u64)bin_capacity(c->nwords, c->cfg.ext != 0) / 2;
+    u64 tg = (mx * 4 + target - 1) / target;
     tg = std::max<u64>(64, (tg + 63) / 64 * 64);
     tg = std::min<u64>(tg, MAX_BINS / (u64)c->cfg.nranks);
     c->tg = (u32)tg;
@@ -299,10 +301,11 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
     return 0;
 }
 
-// Device layout of d_bucket (u64 units): [bin_k T][bin_cw T][start T+1][wstart T+1][cursor T][run_cursor 1]
-// On return h_bucket holds the first four arrays and d_len/d_words/d_ext the bin-major supermer streams.
+// Device layout of d_bucket (u64 units): [bin_k T][bin_cw T][start T+1][wstart T+1][cursor T][run_cursor][kmers_total]
+// Host (h_meta): S, W, run cursor, local k-mer total.  With full_d2h the four per-bin arrays are also copied to
+// h_bucket (debug entry point).  d_len/d_words/d_ext receive the bin-major supermer streams.
 static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
-                       const u32 *d_read_len, u64 nreads, int readid_base)
+                       const u32 *d_read_len, u64 nreads, int readid_base, bool full_d2h)
 {
     if (choose_bins(c, nbytes)) return 1;
     const u32 T = c->tt;
@@ -316,12 +319,14 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     P.k = c->cfg.k; P.m = c->m_eff; P.nbins = T; P.readid_base = readid_base;
 
     const size_t host_u64 = 2 * (size_t)T + 2 * ((size_t)T + 1);
-    const size_t dev_u64 = host_u64 + (size_t)T + 1;
+    const size_t dev_u64 = host_u64 + (size_t)T + 2;
     CK(c->d_bucket.ensure(dev_u64 * 8));
-    CK(c->h_bucket.ensure((host_u64 + 1) * 8));
+    CK(c->h_meta.ensure(128 * 8));
     CK(c->d_tile_hdr.ensure((P.ntiles + 1) * sizeof(ulonglong2)));
     u64 *d_kmers = c->d_bucket.as<u64>();
-    u64 *d_cw = d_kmers + T, *d_start = d_cw + T, *d_wstart = d_start + T + 1, *d_cur = d_wstart + T + 1, *d_runcur = d_cur + T;
+    u64 *d_cw = d_kmers + T, *d_start = d_cw + T, *d_wstart = d_start + T + 1, *d_cur = d_wstart + T + 1, *d_runcur = d_cur + T,
+        *d_ktot = d_runcur + 1;
+    u64 *hm = c->h_meta.as<u64>();
 
     const u64 nslots = nbytes * 4;
     u64 run_cap = nslots / 3 + 1024;
@@ -331,22 +336,17 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
         CK(cudaMemsetAsync(d_kmers, 0, dev_u64 * 8, s));
         CK(launch_supermer_count(P, nctas, d_cw, d_kmers, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur,
                                  run_cap, s));
-        CK(launch_bin_scan(d_cw, T, d_start, d_wstart, s));
-        CK(cudaMemcpyAsync(c->h_bucket.p, c->d_bucket.p, host_u64 * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(c->h_bucket.as<u64>() + host_u64, d_runcur, 8, cudaMemcpyDeviceToHost, s));
+        CK(launch_bin_scan(d_cw, d_kmers, T, d_start, d_wstart, d_ktot, s));
+        CK(cudaMemcpyAsync(hm + 0, d_start + T, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hm + 1, d_wstart + T, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hm + 2, d_runcur, 16, cudaMemcpyDeviceToHost, s));   // run cursor, k-mer total
         CK(cudaStreamSynchronize(s));
         c->stats.n_launches += 2;
-        if (c->h_bucket.as<u64>()[host_u64] <= run_cap) break;
+        if (hm[2] <= run_cap) break;
         if (attempt) return fail("internal: run list overflow after resize");
         run_cap = nslots + 1024;   // pathological input (runs shorter than 3 k-mers on average): worst-case list
     }
-    const u64 *h_cw = c->h_bucket.as<u64>() + T;
-    const u64 *h_start = c->h_bucket.as<u64>() + 2 * (size_t)T;
-    const u64 *h_wstart = h_start + T + 1;
-    const u64 S = h_start[T], W = h_wstart[T];
-    for (u32 b = 0; b < T; ++b)
-        if ((h_cw[b] >> 32) >= 0xFFFFFFF0ull || (h_cw[b] & 0xFFFFFFFFull) >= 0xFFFFFFF0ull)
-            return fail("bin %u holds too many supermers for 32-bit in-bin offsets; raise buckets_per_rank", b);
+    const u64 S = hm[0], W = hm[1];
     CK(c->d_len.ensure((S + 8) * sizeof(u16)));
     CK(c->d_words.ensure((W + 8) * sizeof(u32)));
     if (c->cfg.ext) CK(c->d_ext.ensure((S + 8) * sizeof(u64)));
@@ -356,9 +356,95 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     c->stats.n_launches += 1;
     c->stats.n_supermers = S;
     c->stats.supermer_bytes = S * (2 + (c->cfg.ext ? 8 : 0)) + W * 4;
-    u64 nk = 0;
-    for (u32 b = 0; b < T; ++b) nk += c->h_bucket.as<u64>()[b];
-    c->stats.n_kmers_local = nk;
+    c->stats.n_kmers_local = hm[3];
+    if (full_d2h) {
+        CK(c->h_bucket.ensure((host_u64 + 1) * 8));
+        CK(cudaMemcpyAsync(c->h_bucket.p, c->d_bucket.p, host_u64 * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+// ---- HBM path for the bins the on-chip path left over (skewed bins): expand -> radix sort -> count ------
+struct OvfSeg { int src; u64 i0, nsup, w0, kmers; };
+
+static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
+{
+    cudaStream_t s = c->stream;
+    const int NW = c->nwords;
+    const bool ext = c->cfg.ext != 0;
+    const int me = c->cfg.rank;
+    u64 cap = c->cfg.batch_kmers ? c->cfg.batch_kmers : (1ull << 28);
+    cap = std::min<u64>(cap, (1ull << 29) - 1);
+    size_t first = 0;
+    while (first < segs.size()) {   // batches of whole segments
+        size_t last = first;
+        u64 n = 0, max_sup = 0;
+        while (last < segs.size() && (n == 0 || n + segs[last].kmers <= cap)) {
+            n += segs[last].kmers;
+            max_sup = std::max(max_sup, segs[last].nsup);
+            ++last;
+        }
+        if (n > (1ull << 29) - 1)
+            return fail("a minimizer bin holds %llu k-mers (> 2^29-1); raise buckets_per_rank", (unsigned long long)n);
+        for (int h = 0; h < 2; ++h) {
+            for (int w = 0; w < NW; ++w) CK(c->d_keys[h][w].ensure((n + 8) * 8));
+            if (ext) CK(c->d_val[h].ensure((n + 8) * 8));
+        }
+        CK(c->d_rscratch.ensure(radix_scratch_bytes(n)));
+        CK(c->d_cscratch.ensure(count_scratch_bytes(n)));
+        const u64 seg_tiles = (max_sup + XP_TILE - 1) / XP_TILE + 1;
+        CK(c->d_tsum.ensure(seg_tiles * sizeof(uint2)));
+        CK(c->d_tbase.ensure(seg_tiles * sizeof(ulonglong2)));
+        Planes A, B;
+        for (int w = 0; w < MAX_WORDS; ++w) {
+            A.p[w] = w < NW ? c->d_keys[0][w].as<u64>() : nullptr;
+            B.p[w] = w < NW ? c->d_keys[1][w].as<u64>() : nullptr;
+        }
+        u64 *VA = ext ? c->d_val[0].as<u64>() : nullptr, *VB = ext ? c->d_val[1].as<u64>() : nullptr;
+
+        c->begin(c->ev_expand);
+        u64 out_base = 0;
+        for (size_t i = first; i < last; ++i) {
+            const OvfSeg &g = segs[i];
+            if (g.nsup == 0) continue;
+            const bool local = (g.src == me);
+            ExpandSegment seg;
+            seg.len = (local ? c->d_len.as<u16>() : c->d_rlen.as<u16>() + c->rbase_idx[g.src]) + g.i0;
+            seg.words = (local ? c->d_words.as<u32>() : c->d_rwords.as<u32>() + c->rbase_w[g.src]) + g.w0;
+            seg.ext = ext ? ((local ? c->d_ext.as<u64>() : c->d_rext.as<u64>() + c->rbase_idx[g.src]) + g.i0) : nullptr;
+            seg.nsup = g.nsup;
+            seg.out_base = out_base;
+            CK(launch_expand(seg, c->cfg.k, NW, ext, c->d_tsum.as<uint2>(), c->d_tbase.as<ulonglong2>(), A, VA, s));
+            c->stats.n_launches += 3;
+            out_base += g.kmers;
+        }
+        c->end(c->ev_expand);
+        if (out_base != n) return fail("internal: batch k-mer count mismatch");
+
+        c->begin(c->ev_sort);
+        bool in_b = false; int np = 0, nl = 0;
+        EvPair pp{c->ev(), c->ev()};
+        c->ev_pass.push_back(pp);
+        CK(launch_radix_sort(A, B, VA, VB, n, NW, c->cfg.k, c->d_rscratch.p, &in_b, &np, &nl, s, pp.a, pp.b));
+        c->end(c->ev_sort);
+        c->stats.n_sort_passes = (u64)np;
+        c->stats.n_launches += (u64)nl;
+
+        c->begin(c->ev_count);
+        CountParams CP;
+        CP.keys = in_b ? B : A;
+        CP.val = ext ? (in_b ? VB : VA) : nullptr;
+        CP.n = n; CP.nwords = NW; CP.lower = (u32)c->cfg.lower; CP.upper = (u32)c->cfg.upper;
+        CP.out_words = c->d_owords.as<u64>(); CP.out_cnt = c->d_ocnt.as<u32>();
+        CP.out_occ_off = c->d_oocc_off.as<u64>(); CP.out_pos = c->d_opos.as<u32>(); CP.out_rid = c->d_orid.as<int>();
+        CP.histogram = c->d_hist.as<u64>(); CP.cursor = c->d_cursor.as<u64>();
+        CK(launch_count_filter(CP, c->d_cscratch.p, s));
+        c->end(c->ev_count);
+        c->stats.n_launches += 3;
+        c->stats.n_batches += 1;
+        first = last;
+    }
     return 0;
 }
 
@@ -371,8 +457,10 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     const int G = c->cfg.nranks, me = c->cfg.rank;
     const int NW = c->nwords;
     const bool ext = c->cfg.ext != 0;
+    if (G > BN_MAX_SRC) return fail("more than %d ranks are not supported yet", BN_MAX_SRC);
     c->ev_used = 0;
     c->ev_extract.clear(); c->ev_exchange.clear(); c->ev_expand.clear(); c->ev_sort.clear(); c->ev_count.clear(); c->ev_pass.clear();
+    c->ev_bins.clear();
     hsk_stats keep = c->stats;
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.ms_h2d = keep.ms_h2d;
@@ -380,37 +468,55 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     cudaEvent_t ev_t0 = c->ev(), ev_t1 = c->ev();
     CK(cudaEventRecord(ev_t0, s));
 
-    if (run_extract(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base)) return 1;
+    if (run_extract(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base, false)) return 1;
     const u32 T = c->tt, TG = c->tg;
-    const u64 *hb = c->h_bucket.as<u64>();
-    const u64 *h_start = hb + 2 * (size_t)T, *h_wstart = h_start + T + 1;
+    const u32 b_lo = (u32)me * TG;
+    u64 *d_kmers = c->d_bucket.as<u64>();
+    u64 *d_start = d_kmers + 2 * (size_t)T, *d_wstart = d_start + T + 1;
+    u64 *hm = c->h_meta.as<u64>();
 
-    // ---- totals of every source rank for every bin: tot[src][2][T] = (k-mers, supermers << 32 | words)
-    std::vector<u64> tot((size_t)G * 2 * T);
+    // ---- small device state of this call: [cursor 2][owned total 1][ticket, ovf_count (u32 x2)]
+    CK(c->d_cursor.ensure(64));
+    CK(c->h_cursor.ensure(64));
+    CK(cudaMemsetAsync(c->d_cursor.p, 0, 64, s));
+    u64 *d_cursor = c->d_cursor.as<u64>();
+    u64 *d_owned = d_cursor + 2;
+    u32 *d_ticket = reinterpret_cast<u32 *>(d_cursor + 3), *d_ovfc = d_ticket + 1;
+
+    BinParams BP;
+    memset(&BP, 0, sizeof(BP));
+    BP.k = c->cfg.k; BP.lower = (u32)c->cfg.lower; BP.upper = (u32)c->cfg.upper;
+    BP.nbins = TG; BP.nsrc = G;
+    c->rbase_idx.assign(G, 0); c->rbase_w.assign(G, 0);
+    u64 owned = 0;
+
     if (G == 1) {
-        memcpy(tot.data(), hb, (size_t)2 * T * 8);
+        BP.len[0] = c->d_len.as<u16>(); BP.words[0] = c->d_words.as<u32>(); BP.ext[0] = c->d_ext.as<u64>();
+        BP.seg_start[0] = d_start; BP.seg_wstart[0] = d_wstart;
+        BP.bin_kmers = d_kmers;
+        owned = c->stats.n_kmers_local;
     } else {
+        // ---- stage 3: supermer all-to-all.  Bin totals of every rank -> segment tables and transfer sizes
+        const size_t meta_n = 2 * (size_t)G + 2 * ((size_t)G + 1);
         CK(c->d_alltot.ensure((size_t)G * 2 * T * 8));
-        CK(c->h_alltot.ensure((size_t)G * 2 * T * 8));
+        CK(c->d_seg.ensure(((size_t)2 * G * (TG + 1) + TG + meta_n) * 8));
+        u64 *d_seg_start = c->d_seg.as<u64>(), *d_seg_wstart = d_seg_start + (size_t)G * (TG + 1);
+        u64 *d_binkm = d_seg_wstart + (size_t)G * (TG + 1), *d_meta = d_binkm + TG;
         c->begin(c->ev_exchange);
         NK(g_nccl.AllGather(c->d_bucket.p, c->d_alltot.p, (size_t)2 * T, ncclUint64, c->comm, s));
-        CK(cudaMemcpyAsync(c->h_alltot.p, c->d_alltot.p, (size_t)G * 2 * T * 8, cudaMemcpyDeviceToHost, s));
+        CK(launch_seg_scan(c->d_alltot.as<u64>(), T, b_lo, TG, G, d_start, d_wstart, d_seg_start, d_seg_wstart, d_meta, d_binkm,
+                           d_owned, s));
+        c->stats.n_launches += 2;
+        CK(cudaMemcpyAsync(hm + 8, d_meta, meta_n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hm + 7, d_owned, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        memcpy(tot.data(), c->h_alltot.p, (size_t)G * 2 * T * 8);
-    }
-    auto TK = [&](int src, u32 b) { return tot[((size_t)src * 2 + 0) * T + b]; };
-    auto TC = [&](int src, u32 b) { return tot[((size_t)src * 2 + 1) * T + b] >> 32; };
-    auto TW = [&](int src, u32 b) { return tot[((size_t)src * 2 + 1) * T + b] & 0xFFFFFFFFull; };
-    const u32 b_lo = (u32)me * TG, b_hi = b_lo + TG;
-
-    // ---- stage 3: supermer all-to-all (whole bucket ranges, one grouped send/recv per peer)
-    std::vector<u64> rbase_idx(G, 0), rbase_w(G, 0);
-    if (G > 1) {
+        owned = hm[7];
+        const u64 *rtot = hm + 8, *bounds = hm + 8 + 2 * (size_t)G;
         u64 ri = 0, rw = 0;
         for (int src = 0; src < G; ++src) {
             if (src == me) continue;
-            rbase_idx[src] = ri; rbase_w[src] = rw;
-            for (u32 b = b_lo; b < b_hi; ++b) { ri += TC(src, b); rw += TW(src, b); }
+            c->rbase_idx[src] = ri; c->rbase_w[src] = rw;
+            ri += rtot[2 * src]; rw += rtot[2 * src + 1];
         }
         CK(c->d_rlen.ensure((ri + 8) * sizeof(u16)));
         CK(c->d_rwords.ensure((rw + 8) * sizeof(u32)));
@@ -418,71 +524,36 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         NK(g_nccl.GroupStart());
         for (int peer = 0; peer < G; ++peer) {
             if (peer == me) continue;
-            const u32 p_lo = (u32)peer * TG, p_hi = p_lo + TG;
-            const u64 si = h_start[p_lo], sn = h_start[p_hi] - h_start[p_lo];
-            const u64 sw = h_wstart[p_lo], swn = h_wstart[p_hi] - h_wstart[p_lo];
-            u64 rn = 0, rwn = 0;
-            for (u32 b = b_lo; b < b_hi; ++b) { rn += TC(peer, b); rwn += TW(peer, b); }
+            const u64 si = bounds[2 * peer], sn = bounds[2 * (peer + 1)] - si;
+            const u64 sw = bounds[2 * peer + 1], swn = bounds[2 * (peer + 1) + 1] - sw;
+            const u64 rn = rtot[2 * peer], rwn = rtot[2 * peer + 1];
             if (sn) NK(g_nccl.Send(c->d_len.as<u16>() + si, sn * 2, ncclUint8, peer, c->comm, s));
-            if (rn) NK(g_nccl.Recv(c->d_rlen.as<u16>() + rbase_idx[peer], rn * 2, ncclUint8, peer, c->comm, s));
+            if (rn) NK(g_nccl.Recv(c->d_rlen.as<u16>() + c->rbase_idx[peer], rn * 2, ncclUint8, peer, c->comm, s));
             if (swn) NK(g_nccl.Send(c->d_words.as<u32>() + sw, swn, ncclUint32, peer, c->comm, s));
-            if (rwn) NK(g_nccl.Recv(c->d_rwords.as<u32>() + rbase_w[peer], rwn, ncclUint32, peer, c->comm, s));
+            if (rwn) NK(g_nccl.Recv(c->d_rwords.as<u32>() + c->rbase_w[peer], rwn, ncclUint32, peer, c->comm, s));
             if (ext) {
                 if (sn) NK(g_nccl.Send(c->d_ext.as<u64>() + si, sn, ncclUint64, peer, c->comm, s));
-                if (rn) NK(g_nccl.Recv(c->d_rext.as<u64>() + rbase_idx[peer], rn, ncclUint64, peer, c->comm, s));
+                if (rn) NK(g_nccl.Recv(c->d_rext.as<u64>() + c->rbase_idx[peer], rn, ncclUint64, peer, c->comm, s));
             }
             c->stats.bytes_sent += sn * (2 + (ext ? 8 : 0)) + swn * 4;
             c->stats.bytes_received += rn * (2 + (ext ? 8 : 0)) + rwn * 4;
         }
         NK(g_nccl.GroupEnd());
         c->end(c->ev_exchange);
-    }
-
-    // ---- batches of owned buckets
-    u64 owned = 0, max_bucket = 0;
-    std::vector<u64> bk(TG, 0);
-    for (u32 b = b_lo; b < b_hi; ++b) {
-        u64 kk = 0;
-        for (int src = 0; src < G; ++src) kk += TK(src, b);
-        bk[b - b_lo] = kk; owned += kk; max_bucket = std::max(max_bucket, kk);
+        for (int src = 0; src < G; ++src) {
+            const bool local = (src == me);
+            BP.len[src] = local ? c->d_len.as<u16>() : c->d_rlen.as<u16>() + c->rbase_idx[src];
+            BP.words[src] = local ? c->d_words.as<u32>() : c->d_rwords.as<u32>() + c->rbase_w[src];
+            BP.ext[src] = ext ? (local ? c->d_ext.as<u64>() : c->d_rext.as<u64>() + c->rbase_idx[src]) : nullptr;
+            // the local stream is addressed with its own (absolute) bin starts, the received ones with the scanned tables
+            BP.seg_start[src] = local ? d_start + b_lo : d_seg_start + (size_t)src * (TG + 1);
+            BP.seg_wstart[src] = local ? d_wstart + b_lo : d_seg_wstart + (size_t)src * (TG + 1);
+        }
+        BP.bin_kmers = d_binkm;
     }
     c->stats.n_kmers_owned = owned;
-    u64 cap = c->cfg.batch_kmers ? c->cfg.batch_kmers : (1ull << 28);
-    cap = std::min<u64>(cap, (1ull << 29) - 1);
-    if (max_bucket > (1ull << 29) - 1)
-        return fail("a minimizer bucket holds %llu k-mers (> 2^29-1); raise buckets_per_rank", (unsigned long long)max_bucket);
-    struct Batch { u32 b0, b1; u64 n; };
-    std::vector<Batch> batches;
-    {
-        u32 b0 = b_lo; u64 acc = 0;
-        for (u32 b = b_lo; b < b_hi; ++b) {
-            u64 kk = bk[b - b_lo];
-            if (acc > 0 && acc + kk > cap) { batches.push_back({b0, b, acc}); b0 = b; acc = 0; }
-            acc += kk;
-        }
-        if (acc > 0) batches.push_back({b0, b_hi, acc});
-    }
-    u64 max_batch = 0, max_seg_sup = 0;
-    for (auto &bt : batches) {
-        max_batch = std::max(max_batch, bt.n);
-        for (int src = 0; src < G; ++src) {
-            u64 ns = 0;
-            for (u32 b = bt.b0; b < bt.b1; ++b) ns += TC(src, b);
-            max_seg_sup = std::max(max_seg_sup, ns);
-        }
-    }
-    c->stats.n_batches = batches.size();
 
-    // ---- buffers
-    for (int h = 0; h < 2; ++h) {
-        for (int w = 0; w < NW; ++w) CK(c->d_keys[h][w].ensure((max_batch + 8) * 8));
-        if (ext) CK(c->d_val[h].ensure((max_batch + 8) * 8));
-    }
-    CK(c->d_rscratch.ensure(radix_scratch_bytes(max_batch)));
-    CK(c->d_cscratch.ensure(count_scratch_bytes(max_batch)));
-    const u64 seg_tiles = (max_seg_sup + XP_TILE - 1) / XP_TILE + 1;
-    CK(c->d_tsum.ensure(seg_tiles * sizeof(uint2)));
-    CK(c->d_tbase.ensure(seg_tiles * sizeof(ulonglong2)));
+    // ---- result arena + look-back state
     const u64 arena = owned / (u64)c->cfg.lower + 8;
     CK(c->d_owords.ensure(arena * NW * 8));
     CK(c->d_ocnt.ensure(arena * 4));
@@ -493,71 +564,50 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     }
     const size_t hist_bins = (size_t)c->cfg.upper + 1;
     CK(c->d_hist.ensure(hist_bins * 8));
-    CK(c->d_cursor.ensure(16));
-    CK(c->h_cursor.ensure(16));
     CK(cudaMemsetAsync(c->d_hist.p, 0, hist_bins * 8, s));
-    CK(cudaMemsetAsync(c->d_cursor.p, 0, 16, s));
+    CK(c->d_lb.ensure(((size_t)2 * TG + 2) * 8 + ((size_t)TG + 2) * 4));
+    CK(cudaMemsetAsync(c->d_lb.p, 0, ((size_t)2 * TG + 2) * 8, s));
+    BP.out_words = c->d_owords.as<u64>(); BP.out_cnt = c->d_ocnt.as<u32>();
+    BP.out_occ_off = c->d_oocc_off.as<u64>(); BP.out_pos = c->d_opos.as<u32>(); BP.out_rid = c->d_orid.as<int>();
+    BP.histogram = c->d_hist.as<u64>(); BP.cursor = d_cursor;
+    BP.lb_kept = c->d_lb.as<u64>(); BP.lb_occ = BP.lb_kept + TG + 1;
+    BP.ticket = d_ticket; BP.ovf_count = d_ovfc;
+    BP.ovf_list = reinterpret_cast<u32 *>(BP.lb_occ + TG + 1);
 
-    // ---- per batch: expand -> sort -> count/filter
-    // idx/word start of bucket b inside source src's stream
-    std::vector<u64> seg_i((size_t)G * (TG + 1)), seg_w((size_t)G * (TG + 1));
-    for (int src = 0; src < G; ++src) {
-        u64 ai = (src == me) ? h_start[b_lo] : rbase_idx[src];
-        u64 aw = (src == me) ? h_wstart[b_lo] : rbase_w[src];
-        for (u32 b = b_lo; b <= b_hi; ++b) {
-            seg_i[(size_t)src * (TG + 1) + (b - b_lo)] = ai;
-            seg_w[(size_t)src * (TG + 1) + (b - b_lo)] = aw;
-            if (b < b_hi) { ai += TC(src, b); aw += TW(src, b); }
+    // ---- stages 4+5 on chip
+    c->begin(c->ev_bins);
+    CK(launch_bin_sort_count(BP, NW, ext, c->sm_count, s));
+    c->end(c->ev_bins);
+    c->stats.n_launches += 1;
+    c->stats.n_batches = 1;
+    CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const u32 novf = reinterpret_cast<u32 *>(c->h_cursor.as<u64>() + 3)[1];
+    c->stats.n_overflow_bins = novf;
+
+    if (novf) {
+        // ---- leftovers through HBM: fetch the tables of the overflow bins
+        std::vector<u32> ovf(novf);
+        CK(cudaMemcpy(ovf.data(), BP.ovf_list, (size_t)novf * 4, cudaMemcpyDeviceToHost));
+        std::sort(ovf.begin(), ovf.end());
+        std::vector<OvfSeg> segs;
+        for (u32 lb : ovf) {
+            for (int src = 0; src < G; ++src) {
+                u64 st2[2], ws, km;
+                CK(cudaMemcpy(st2, BP.seg_start[src] + lb, 16, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&ws, BP.seg_wstart[src] + lb, 8, cudaMemcpyDeviceToHost));
+                const u64 *kp = (G == 1) ? d_kmers + lb : c->d_alltot.as<u64>() + ((size_t)src * 2) * T + b_lo + lb;
+                CK(cudaMemcpy(&km, kp, 8, cudaMemcpyDeviceToHost));
+                // segment offsets are relative to the stream the bin kernel was given for this source
+                const bool local = (src == me);
+                u64 i0 = st2[0], w0 = ws;
+                (void)local;
+                segs.push_back({src, i0, st2[1] - st2[0], w0, km});
+            }
         }
+        if (run_hbm_path(c, segs)) return 1;
+        CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 16, cudaMemcpyDeviceToHost, s));
     }
-    for (auto &bt : batches) {
-        Planes A, B;
-        for (int w = 0; w < MAX_WORDS; ++w) { A.p[w] = w < NW ? c->d_keys[0][w].as<u64>() : nullptr; B.p[w] = w < NW ? c->d_keys[1][w].as<u64>() : nullptr; }
-        u64 *VA = ext ? c->d_val[0].as<u64>() : nullptr, *VB = ext ? c->d_val[1].as<u64>() : nullptr;
-
-        c->begin(c->ev_expand);
-        u64 out_base = 0;
-        for (int src = 0; src < G; ++src) {
-            const u64 i0 = seg_i[(size_t)src * (TG + 1) + (bt.b0 - b_lo)], i1 = seg_i[(size_t)src * (TG + 1) + (bt.b1 - b_lo)];
-            const u64 w0 = seg_w[(size_t)src * (TG + 1) + (bt.b0 - b_lo)];
-            if (i1 == i0) continue;
-            ExpandSegment seg;
-            const bool local = (src == me);
-            seg.len = (local ? c->d_len.as<u16>() : c->d_rlen.as<u16>()) + i0;
-            seg.words = (local ? c->d_words.as<u32>() : c->d_rwords.as<u32>()) + w0;
-            seg.ext = ext ? ((local ? c->d_ext.as<u64>() : c->d_rext.as<u64>()) + i0) : nullptr;
-            seg.nsup = i1 - i0;
-            seg.out_base = out_base;
-            CK(launch_expand(seg, c->cfg.k, NW, ext, c->d_tsum.as<uint2>(), c->d_tbase.as<ulonglong2>(), A, VA, s));
-            c->stats.n_launches += 3;
-            for (u32 b = bt.b0; b < bt.b1; ++b) out_base += TK(src, b);
-        }
-        c->end(c->ev_expand);
-        if (out_base != bt.n) return fail("internal: batch k-mer count mismatch (%llu vs %llu)", (unsigned long long)out_base, (unsigned long long)bt.n);
-
-        c->begin(c->ev_sort);
-        bool in_b = false; int np = 0, nl = 0;
-        EvPair pp{c->ev(), c->ev()};
-        c->ev_pass.push_back(pp);
-        CK(launch_radix_sort(A, B, VA, VB, bt.n, NW, c->cfg.k, c->d_rscratch.p, &in_b, &np, &nl, s, pp.a, pp.b));
-        c->end(c->ev_sort);
-        c->stats.n_sort_passes = (u64)np;
-        c->stats.n_launches += (u64)nl;
-
-        c->begin(c->ev_count);
-        CountParams CP;
-        CP.keys = in_b ? B : A;
-        CP.val = ext ? (in_b ? VB : VA) : nullptr;
-        CP.n = bt.n; CP.nwords = NW; CP.lower = (u32)c->cfg.lower; CP.upper = (u32)c->cfg.upper;
-        CP.out_words = c->d_owords.as<u64>(); CP.out_cnt = c->d_ocnt.as<u32>();
-        CP.out_occ_off = c->d_oocc_off.as<u64>(); CP.out_pos = c->d_opos.as<u32>(); CP.out_rid = c->d_orid.as<int>();
-        CP.histogram = c->d_hist.as<u64>(); CP.cursor = c->d_cursor.as<u64>();
-        CK(launch_count_filter(CP, c->d_cscratch.p, s));
-        c->end(c->ev_count);
-        c->stats.n_launches += 3;
-    }
-
-    CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 16, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ev_t1, s));
     CK(cudaStreamSynchronize(s));
     c->n_kept = c->h_cursor.as<u64>()[0];
@@ -572,6 +622,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     c->stats.ms_sort = hsk_ctx::sum_ms(c->ev_sort);
     c->stats.ms_count = hsk_ctx::sum_ms(c->ev_count);
     c->stats.ms_sort_passes = hsk_ctx::sum_ms(c->ev_pass);
+    c->stats.ms_bins = hsk_ctx::sum_ms(c->ev_bins);
     CK(cudaEventElapsedTime(&c->stats.ms_total, ev_t0, ev_t1));
     c->have_result = true;
     return 0;
@@ -768,7 +819,7 @@ int hsk_debug_extract(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const 
     c->ev_extract.clear();
     if (stage_input(c, packed, nbytes, read_len, nreads)) return 1;
     if (run_extract(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(), nreads,
-                    readid_base)) return 1;
+                    readid_base, true)) return 1;
     const u32 T = c->tt;
     const u64 *hb = c->h_bucket.as<u64>();
     const u64 S = hb[2 * (size_t)T + T], W = hb[2 * (size_t)T + (T + 1) + T];

@@ -269,11 +269,13 @@ __global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, 
 }
 
 // ---- bin scan: exclusive prefix over bins of (supermers, words) -> bin starts.  One block. ---------
-__global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_cw, u32 nbins, u64 *__restrict__ bin_start,
-                                                    u64 *__restrict__ word_start)
+__global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_cw, const u64 *__restrict__ bin_k, u32 nbins,
+                                                    u64 *__restrict__ bin_start, u64 *__restrict__ word_start,
+                                                    u64 *__restrict__ kmers_total)
 {
     __shared__ u64 s_c[32], s_w[32];
     __shared__ u64 carry_c, carry_w;
+    u64 ksum = 0;
     if (threadIdx.x == 0) { carry_c = 0; carry_w = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_c
         for (int i = 0; i < PER; ++i) {
             u32 b = base + threadIdx.x * PER + i;
             u64 v = b < nbins ? bin_cw[b] : 0;
+            if (b < nbins) ksum += bin_k[b];
             c[i] = v >> 32; w[i] = v & 0xFFFFFFFFull;
             tc += c[i]; tw += w[i];
         }
@@ -321,6 +324,9 @@ __global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_c
         __syncthreads();
     }
     if (threadIdx.x == 0) { bin_start[nbins] = carry_c; word_start[nbins] = carry_w; }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ksum += __shfl_xor_sync(0xFFFFFFFFu, ksum, d);
+    if (lane == 0 && ksum) atomicAdd(kmers_total, ksum);
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------
@@ -398,9 +404,10 @@ cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_cw
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_scan(const u64 *bin_cw, u32 nbins, u64 *bin_start, u64 *word_start, cudaStream_t s)
+cudaError_t launch_bin_scan(const u64 *bin_cw, const u64 *bin_k, u32 nbins, u64 *bin_start, u64 *word_start, u64 *kmers_total,
+                            cudaStream_t s)
 {
-    k_bin_scan<<<1, 1024, 0, s>>>(bin_cw, nbins, bin_start, word_start);
+    k_bin_scan<<<1, 1024, 0, s>>>(bin_cw, bin_k, nbins, bin_start, word_start, kmers_total);
     return cudaGetLastError();
 }
 

@@ -22,7 +22,8 @@ struct ExtractParams {
 cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_cw, u64 *bin_k, u64 *run_list,
                                   ulonglong2 *tile_hdr, u64 *run_cursor, u64 run_capacity, cudaStream_t s);
 // bin_start / word_start: nbins+1 exclusive prefixes of the supermer / word counts
-cudaError_t launch_bin_scan(const u64 *bin_cw, u32 nbins, u64 *bin_start, u64 *word_start, cudaStream_t s);
+cudaError_t launch_bin_scan(const u64 *bin_cw, const u64 *bin_k, u32 nbins, u64 *bin_start, u64 *word_start, u64 *kmers_total,
+                            cudaStream_t s);
 // pass B: bin_cursor (zeroed, nbins) hands out (index << 32 | word offset) inside every bin
 cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const u64 *run_list,
                                     const ulonglong2 *tile_hdr, u64 *bin_cursor, const u64 *bin_start,
@@ -44,6 +45,37 @@ struct ExpandSegment {
 // scratch: tile_sums / tile_base hold ceil(nsup/XP_TILE) entries each
 cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext, uint2 *tile_sums, ulonglong2 *tile_base,
                           Planes out_keys, u64 *out_val, cudaStream_t s);
+
+// ---- stages 4+5 on chip: bins.cu ---------------------------------------------------------------------
+constexpr int BN_THREADS = 512;
+constexpr int BN_SCAP = 2048;        // supermers per bin that the on-chip path handles
+constexpr int BN_MAX_SRC = 16;       // source ranks per bin
+
+struct BinParams {
+    int k;
+    u32 lower, upper;
+    u32 nbins;                           // owned bins, local index 0..nbins-1
+    int nsrc;
+    const u16 *len[BN_MAX_SRC];          // supermer streams per source rank
+    const u32 *words[BN_MAX_SRC];
+    const u64 *ext[BN_MAX_SRC];
+    const u64 *seg_start[BN_MAX_SRC];    // nbins+1: first supermer of every bin inside the source's stream
+    const u64 *seg_wstart[BN_MAX_SRC];   // nbins+1: first word
+    const u64 *bin_kmers;                // nbins: k-mers per bin over all sources
+    u64 *out_words; u32 *out_cnt; u64 *out_occ_off; u32 *out_pos; int *out_rid;
+    u64 *histogram;
+    u64 *cursor;                         // [0] entries, [1] occurrences: written by the last bin
+    u64 *lb_kept, *lb_occ;               // nbins look-back words each, zeroed
+    u32 *ticket;                         // zeroed
+    u32 *ovf_list, *ovf_count;           // bins left to the HBM path
+};
+
+int bin_capacity(int nwords, bool ext);  // k-mers per bin the on-chip path can hold
+cudaError_t launch_bin_sort_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
+// multi-rank: segment tables of the owned bins inside the per-source streams + send/recv sizes (meta)
+cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start,
+                            const u64 *local_wstart, u64 *seg_start, u64 *seg_wstart, u64 *meta, u64 *bin_kmers,
+                            u64 *owned_total, cudaStream_t s);
 
 // ---- stage 5a: radix.cu ------------------------------------------------------------------------------
 // scratch layout (u32 units): [RS_MAX_PASSES*256 bins][RS_MAX_PASSES tile counters][ntiles*256 look-back]

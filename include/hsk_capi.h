@@ -64,9 +64,10 @@ typedef struct hsk_stats {
     uint64_t n_batches;
     uint64_t n_sort_passes;   /* radix passes executed per batch                             */
     uint64_t n_launches;      /* kernels launched                                            */
-    float ms_h2d, ms_extract, ms_exchange, ms_expand, ms_sort, ms_count, ms_d2h, ms_total;
+    float ms_h2d, ms_extract, ms_exchange, ms_expand, ms_sort, ms_count, ms_d2h, ms_total; /* expand/sort/count: HBM path only */
     float ms_sort_passes;     /* part of ms_sort spent in the per-digit pass kernels (n_sort_passes * n_batches launches) */
-    float reserved_;
+    float ms_bins;            /* fused on-chip expand + sort + count kernel (stages 4+5)     */
+    uint64_t n_overflow_bins; /* bins too large / too skewed for the on-chip path, handled through HBM */
 } hsk_stats;
 
 /* Result of one rank.  Arrays live in page-locked host memory owned by the context and stay valid
