@@ -1,28 +1,37 @@
-// Stages 4+5 fused, on chip: one CTA takes one bin of supermers and expands it to canonical k-mers,
-// sorts them, run-length counts, filters and emits — without the k-mers ever touching HBM.
+// Stages 4+5 fused, on chip: one CTA takes one bin of supermers, expands it to canonical k-mers and
+// counts them in shared memory — the k-mers themselves never touch HBM.
 //
 // Replaces, for bins that fit in shared memory, the reference's HOT LOOPS C+D+E:
 //   receive_from_buffer_stage2 + GetRepKmers  (src/kmerops.cpp:484-521, include/kmer.hpp:313-340)
 //   sort_task -> RADULS / PARADIS             (src/kmerops.cpp:1382-1407)
 //   count_sorted_kmers                        (src/kmerops.cpp:1410-1445), histogram (hysortk.cpp:106-113)
-// Like RADULS (an MSD radix sort that finishes small buckets with small sorts, raduls.h:26-27) the
-// sort is MSD-first, but staged entirely in shared memory: one counting pass on a 10-12 bit digit
-// (shared-memory atomics, no stability needed for MSD), an exclusive scan, a scatter into sub-bucket
-// order, then every thread finishes the handful of keys of its own consecutive sub-buckets with a
-// selection sort over the DISTINCT keys (the k-mers of a bin are ~30x duplicated at 30x coverage, so
-// cost is n * distinct, not n^2) and run-length counts them in place.
-// The k-mers of one bin share a few minimizers, i.e. they are overlapping windows of a few genomic
-// loci: their leading bases take only a few hundred values, so the MSD digit is taken from a
-// bijective scramble of the first key word (odd multiplier); the bin is therefore sorted by
-// (digit of scrambled key, key) — a total order under which equal k-mers are adjacent, which is all
-// that counting needs.  Bins are sized by the extraction stage so that they fit (CAP k-mers); the rare
-// bin that does not (skew) is reported in an overflow list and goes through the HBM path
-// (expand.cu -> radix.cu -> count.cu).
 //
-// Output order is deterministic: bins are taken in index order through a ticket, and every bin
-// resolves its position in the result arena by decoupled look-back over the preceding bins, so the
-// arena holds the bins in index order and sorted k-mers inside each bin (the reference: per-task
-// sorted runs in task order, kmerops.cpp:883-904).
+// The reference sorts every k-mer occurrence and then run-length counts.  At 30x coverage a bin of
+// ~3000 occurrences holds only ~100 genomic k-mers x 30 copies plus error singletons, and all of
+// them are overlapping windows of a few loci (they share minimizers), so their leading bases take
+// few values: sorting the occurrences is both unbalanced (30-copy lumps) and wasted work.  Here:
+//
+//   k_bin_count   (one CTA per bin, bins taken in index order through a ticket)
+//     1. supermer table of the bin: block scan of k-mer / word offsets
+//     2. every thread expands its share of consecutive k-mers (rolling forward / reverse words inside a
+//        supermer) and inserts each into an open-addressing table in shared memory keyed by the
+//        canonical k-mer (64-bit CAS; for K > 32 a 64-bit fingerprint of the words is the CAS key and
+//        the full words are verified afterwards — a fingerprint clash sends the bin to the HBM path,
+//        so the result stays exact).  The slot's 16-bit counter gives the count AND the index of this
+//        occurrence among its k-mer's occurrences (used to place (pos, rid) when EXTENSION).
+//     3. every thread filters its slots with LOWER <= count <= UPPER, a block scan compacts the kept
+//        (k-mer, count) pairs and they are written to a staging area at an atomically claimed offset
+//   k_bin_offsets  exclusive scan of the per-bin kept / occurrence totals -> final positions
+//   k_bin_gather   (one CTA per bin) sorts the bin's kept k-mers by key (bitonic sort in shared
+//                  memory over the few distinct kept keys) and writes them, with their occurrence
+//                  lists, to the final arena.
+//
+// So the SORT is still there, but it runs over the distinct kept k-mers (D) instead of over every
+// occurrence (N): D/N is ~4 % at 30x coverage with 1 % errors.  The arena holds the bins in index order
+// and ascending k-mers inside each bin (the reference: per-task sorted runs in task order,
+// kmerops.cpp:883-904), deterministically.  Bins are sized by the extraction stage so that they fit
+// (CAP k-mers); the rare bin that does not (skew) is reported in an overflow list and goes through the
+// HBM path (expand.cu -> radix.cu -> count.cu).
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -31,30 +40,28 @@ namespace hsk {
 
 constexpr int BN_SPT = BN_SCAP / BN_THREADS;   // supermers per thread in the table scan
 constexpr int BN_HCAP = 2048;                  // shared-memory histogram bins
-constexpr u64 LBF_AGG = 1ull << 62, LBF_INC = 2ull << 62, LBF_MASK = (1ull << 62) - 1;
+constexpr u64 BN_EMPTY = ~0ull;                // never a canonical k-mer: a K-mer of all T is not canonical
 
-template <int NW, bool EXT>
+template <int NW>
 struct BinCfg {
-    static constexpr int REC = 8 * NW + (EXT ? 8 : 0);
-    static constexpr int KPT = REC == 8 ? 12 : (REC == 16 ? 6 : (REC == 24 ? 4 : 3));
-    static constexpr int CAP = BN_THREADS * KPT;
-    static constexpr int NB_BITS = CAP >= 4096 ? 12 : (CAP >= 2048 ? 11 : 10);
-    static constexpr int NB = 1 << NB_BITS;
-    static constexpr int BPT = NB / BN_THREADS;
+    static constexpr int KPT = NW == 1 ? 12 : (NW == 2 ? 6 : 4);
+    static constexpr int CAP = BN_THREADS * KPT;           // 6144 / 3072 / 2048 k-mers per bin
+    static constexpr int TS_BITS = NW == 1 ? 13 : 12;      // table slots: 8192 / 4096 / 4096
+    static constexpr int TS = 1 << TS_BITS;
+    static constexpr int SLOTS_PT = TS / BN_THREADS;       // slots per thread in the filter: 16 / 8 / 8
 };
 
 int bin_capacity(int nwords, bool ext)
 {
-    const int rec = 8 * nwords + (ext ? 8 : 0);
-    return BN_THREADS * (rec == 8 ? 12 : (rec == 16 ? 6 : (rec == 24 ? 4 : 3)));
+    (void)ext;
+    return BN_THREADS * (nwords == 1 ? 12 : (nwords == 2 ? 6 : 4));
 }
 
-template <int NW, bool EXT>
+template <int NW>
 struct BinSmem {
-    u64 keys[NW][BinCfg<NW, EXT>::CAP];
-    u64 val[EXT ? BinCfg<NW, EXT>::CAP : 1];
-    u32 cnt[BinCfg<NW, EXT>::NB + 1];
-    u32 cplx[BinCfg<NW, EXT>::NB / 32];   // sub-buckets holding more than one distinct key
+    u64 fp[BinCfg<NW>::TS];                                 // CAS key: the k-mer (NW == 1) or its fingerprint
+    u64 kw[NW > 1 ? NW : 1][NW > 1 ? BinCfg<NW>::TS : 1];   // full key words (NW > 1)
+    u32 cnt2[BinCfg<NW>::TS / 2];                           // two 16-bit counters per word
     u32 woff[BN_SCAP + 1];
     u16 koff[BN_SCAP + 2];
     u8 ssrc[BN_SCAP];
@@ -62,13 +69,9 @@ struct BinSmem {
     u64 src_i0[BN_MAX_SRC], src_w0[BN_MAX_SRC];
     u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1], src_wbase[BN_MAX_SRC + 1];
     u32 wa[BN_THREADS / 32], wb[BN_THREADS / 32];
-    u64 gbase_kept, gbase_occ;
-    u32 tot_kept, tot_occ;
+    u64 stage_kept, stage_occ;
     u32 bin, nk, S, bail;
 };
-
-__device__ __forceinline__ u64 ldv64(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
-__device__ __forceinline__ void stv64(u64 *p, u64 v) { *reinterpret_cast<volatile u64 *>(p) = v; }
 
 // block-wide exclusive scan of two u32 values (BN_THREADS threads); returns exclusive prefixes and totals
 __device__ __forceinline__ void block_scan2(u32 a, u32 b, u32 *wa, u32 *wb, u32 &ea, u32 &eb, u32 &ta, u32 &tb)
@@ -96,10 +99,6 @@ __device__ __forceinline__ void block_scan2(u32 a, u32 b, u32 *wa, u32 *wb, u32 
     eb = ob + ib - b;
 }
 
-// sub-bucket of a key: top bits of a bijective scramble of its first word
-template <int BITS>
-__device__ __forceinline__ u32 sub_bucket(u64 w0) { return (u32)((w0 * 0x9E3779B97F4A7C15ull) >> (64 - BITS)); }
-
 template <int NW>
 __device__ __forceinline__ bool key_less(const u64 (&a)[NW], const u64 (&b)[NW])
 {
@@ -110,13 +109,30 @@ __device__ __forceinline__ bool key_less(const u64 (&a)[NW], const u64 (&b)[NW])
     return false;
 }
 
-template <int NW, bool EXT>
-__global__ void __launch_bounds__(BN_THREADS, 2) k_bin_sort_count(BinParams P)
+// CAS key of a k-mer: the k-mer itself when it is one word, else a 64-bit fingerprint of its words
+template <int NW>
+__device__ __forceinline__ u64 fingerprint(const u64 (&w)[NW])
 {
-    using Cfg = BinCfg<NW, EXT>;
+    if (NW == 1) return w[0];
+    u64 h = w[0] * 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int l = 1; l < NW; ++l) {
+        h ^= h >> 29;
+        h = (h + w[l]) * 0xBF58476D1CE4E5B9ull;
+    }
+    h ^= h >> 32;
+    return h == BN_EMPTY ? 0x5851F42D4C957F2Dull : h;
+}
+
+__device__ __forceinline__ u32 half16(u32 word, u32 slot) { return (word >> (16 * (slot & 1))) & 0xFFFFu; }
+
+template <int NW, bool EXT>
+__global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinParams P)
+{
+    using Cfg = BinCfg<NW>;
     extern __shared__ __align__(16) unsigned char smraw[];
-    BinSmem<NW, EXT> &sm = *reinterpret_cast<BinSmem<NW, EXT> *>(smraw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    BinSmem<NW> &sm = *reinterpret_cast<BinSmem<NW> *>(smraw);
+    const int tid = threadIdx.x;
     const int k = P.k;
     const int padbits = 2 * (32 * NW - k);
 
@@ -125,8 +141,8 @@ __global__ void __launch_bounds__(BN_THREADS, 2) k_bin_sort_count(BinParams P)
     while (true) {
         __syncthreads();   // end of the previous bin: shared memory is free again
         if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; }
-        for (int i = tid; i <= Cfg::NB; i += BN_THREADS) sm.cnt[i] = 0;
-        for (int i = tid; i < Cfg::NB / 32; i += BN_THREADS) sm.cplx[i] = 0;
+        for (int i = tid; i < Cfg::TS; i += BN_THREADS) sm.fp[i] = BN_EMPTY;
+        for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) sm.cnt2[i] = 0;
         __syncthreads();
         const u32 lb = sm.bin;
         if (lb >= P.nbins) break;
@@ -178,21 +194,21 @@ __global__ void __launch_bounds__(BN_THREADS, 2) k_bin_sort_count(BinParams P)
             }
             if (tid == 0) {
                 sm.koff[S] = (u16)totn; sm.woff[S] = totw;
-                if (totn != nk) sm.bail = 2;   // inconsistent totals: never emit from a corrupt table
+                if (totn != nk) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
             }
             __syncthreads();
             if (tid < P.nsrc) sm.src_wbase[tid] = sm.woff[min(sm.src_sbase[tid], S)];
             __syncthreads();
         }
 
-        u64 kreg[Cfg::KPT][NW];
+        u64 kreg[NW > 1 ? Cfg::KPT : 1][NW];   // full keys are only needed again for the K > 32 verification
         u64 vreg[EXT ? Cfg::KPT : 1];
-        u16 rank[Cfg::KPT];
+        u16 slot_of[Cfg::KPT], occ_idx[EXT ? Cfg::KPT : 1];
         const u32 q = (nk + BN_THREADS - 1) / BN_THREADS;   // k-mers per thread, <= KPT
         const u32 a = tid * q, e = min(nk, a + q);
 
         if (!sm.bail && a < e) {
-            // ---- expansion: my q consecutive k-mers, rolling inside a supermer
+            // ---- expansion + insertion: my q consecutive k-mers, rolling inside a supermer
             u32 j = 0;
             for (u32 step = BN_SCAP / 2; step >= 1; step >>= 1)
                 if (j + step < S && sm.koff[j + step] <= a) j += step;
@@ -243,10 +259,32 @@ __global__ void __launch_bounds__(BN_THREADS, 2) k_bin_sort_count(BinParams P)
                         if (padbits) rc[NW - 1] &= ~0ull << padbits;
                     }
                     const bool use_rc = key_less<NW>(rc, fwd);
+                    u64 key[NW];
 #pragma unroll
-                    for (int l = 0; l < NW; ++l) kreg[i][l] = use_rc ? rc[l] : fwd[l];
+                    for (int l = 0; l < NW; ++l) key[l] = use_rc ? rc[l] : fwd[l];
+                    if (NW > 1) {
+#pragma unroll
+                        for (int l = 0; l < NW; ++l) kreg[i][l] = key[l];
+                    }
                     if (EXT) vreg[i] = extv + ((u64)o << 32);
-                    rank[i] = (u16)atomicAdd(&sm.cnt[sub_bucket<Cfg::NB_BITS>(kreg[i][0])], 1u);
+                    // insert: claim or find the slot of this k-mer, bump its counter
+                    const u64 f = fingerprint<NW>(key);
+                    u32 slot = (u32)((f * 0x9E3779B97F4A7C15ull) >> (64 - Cfg::TS_BITS));
+                    while (true) {
+                        const u64 old = atomicCAS(&sm.fp[slot], BN_EMPTY, f);
+                        if (old == BN_EMPTY) {
+                            if (NW > 1) {
+#pragma unroll
+                                for (int l = 0; l < NW; ++l) sm.kw[l][slot] = key[l];
+                            }
+                            break;
+                        }
+                        if (old == f) break;
+                        slot = (slot + 1) & (Cfg::TS - 1);
+                    }
+                    const u32 prev = atomicAdd(&sm.cnt2[slot >> 1], 1u << (16 * (slot & 1)));
+                    slot_of[i] = (u16)slot;
+                    if (EXT) occ_idx[i] = (u16)half16(prev, slot);
                     ++o;
                     if (o >= nj) { ++j; o = 0; fresh = true; }
                 }
@@ -254,191 +292,91 @@ __global__ void __launch_bounds__(BN_THREADS, 2) k_bin_sort_count(BinParams P)
         }
         __syncthreads();
 
-        // ---- exclusive scan of the sub-bucket counters; my consecutive sub-buckets = my sort range
-        u32 rs = 0, re = 0;
-        {
-            u32 c[Cfg::BPT], sum = 0;
+        if (NW > 1) {
+            // ---- the CAS key was a fingerprint: every occurrence checks the full words of its slot
+            if (!sm.bail && a < e) {
+                bool ok = true;
 #pragma unroll
-            for (int i = 0; i < Cfg::BPT; ++i) { c[i] = sm.cnt[tid * Cfg::BPT + i]; sum += c[i]; }
-            u32 ex, dummy_e, tot, dummy_t;
-            block_scan2(sum, 0u, sm.wa, sm.wb, ex, dummy_e, tot, dummy_t);
-            rs = ex; re = ex + sum;
-            (void)rs; (void)re;
+                for (int i = 0; i < Cfg::KPT; ++i) {
+                    if (a + i < e) {
 #pragma unroll
-            for (int i = 0; i < Cfg::BPT; ++i) { sm.cnt[tid * Cfg::BPT + i] = ex; ex += c[i]; }
-            if (tid == BN_THREADS - 1) sm.cnt[Cfg::NB] = ex;
-        }
-        __syncthreads();
-
-        // ---- scatter into sub-bucket order
-        if (!sm.bail && a < e) {
-#pragma unroll
-            for (int i = 0; i < Cfg::KPT; ++i) {
-                if (a + i < e) {
-                    const u32 pos = sm.cnt[sub_bucket<Cfg::NB_BITS>(kreg[i][0])] + rank[i];
-#pragma unroll
-                    for (int l = 0; l < NW; ++l) sm.keys[l][pos] = kreg[i][l];
-                    if (EXT) sm.val[pos] = vreg[i];
+                        for (int l = 0; l < NW; ++l) ok = ok && (sm.kw[l][slot_of[i]] == kreg[i][l]);
+                    }
                 }
+                if (!ok) atomicOr(&sm.bail, 8u);
             }
+            __syncthreads();
         }
-        __syncthreads();
 
         if (sm.bail) {
-            // bin goes to the HBM path; it contributes nothing here but must not block its successors
+            // bin goes to the HBM path
             if (tid == 0) {
                 P.ovf_list[atomicAdd(P.ovf_count, 1u)] = lb;
-                const u64 f = (lb == 0) ? LBF_INC : LBF_AGG;
-                stv64(P.lb_occ + lb, f);
-                stv64(P.lb_kept + lb, f);
-                if (lb == P.nbins - 1) {   // still has to close the arena cursor: needs the prefix
-                    u64 ek = 0, eo = 0;
-                    for (long t = (long)lb - 1; t >= 0; --t) {
-                        u64 vk, vo;
-                        do { vk = ldv64(P.lb_kept + t); vo = ldv64(P.lb_occ + t); } while ((vk >> 62) == 0 || (vk >> 62) != (vo >> 62));
-                        ek += vk & LBF_MASK; eo += vo & LBF_MASK;
-                        if ((vk >> 62) == 2) break;
-                    }
-                    P.cursor[0] = ek; P.cursor[1] = eo;
-                }
+                P.bin_rec[4 * (size_t)lb + 0] = 0; P.bin_rec[4 * (size_t)lb + 1] = 0;
+                P.bin_rec[4 * (size_t)lb + 2] = 0; P.bin_rec[4 * (size_t)lb + 3] = 0;
             }
             continue;
         }
 
-        // ---- which sub-buckets hold more than one distinct key?  One comparison per k-mer, balanced:
-        // every position checks its key against the first key of its sub-bucket.
-        for (u32 p = tid; p < nk; p += BN_THREADS) {
-            const u32 d = sub_bucket<Cfg::NB_BITS>(sm.keys[0][p]);
-            const u32 h = sm.cnt[d];
-            bool same = true;
+        // ---- filter my slots, compact the kept (k-mer, count) pairs into the staging area
+        u32 kept = 0, occ = 0, keepmask = 0;
 #pragma unroll
-            for (int l = 0; l < NW; ++l) same = same && (sm.keys[l][p] == sm.keys[l][h]);
-            if (!same) atomicOr(&sm.cplx[d >> 5], 1u << (d & 31));
-        }
-        __syncthreads();
-
-        // ---- my sub-buckets: a simple one is a single run (its size is the count); a complex one is
-        // finished with a selection sort over its distinct keys (each round finds the smallest remaining
-        // key and gathers its copies to the front).  Complex sub-buckets are re-marked as sorted.
-        u32 kept = 0, occ = 0;
-#pragma unroll 1
-        for (int sb = 0; sb < Cfg::BPT; ++sb) {
-            const u32 d = tid * Cfg::BPT + sb;
-            const u32 s0 = sm.cnt[d], s1 = sm.cnt[d + 1];
-            if (s1 == s0) continue;
-            if (!((sm.cplx[d >> 5] >> (d & 31)) & 1)) {
-                const u32 c = s1 - s0;
-                if (c >= P.lower && c <= P.upper) { ++kept; occ += c; }
-                continue;
-            }
-            for (u32 i = s0; i < s1;) {
-                u64 mn[NW];
-#pragma unroll
-                for (int l = 0; l < NW; ++l) mn[l] = sm.keys[l][i];
-                for (u32 t = i + 1; t < s1; ++t) {
-                    u64 y[NW];
-#pragma unroll
-                    for (int l = 0; l < NW; ++l) y[l] = sm.keys[l][t];
-                    if (key_less<NW>(y, mn)) {
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) mn[l] = y[l];
-                    }
-                }
-                u32 j = i;
-                for (u32 t = i; t < s1; ++t) {
-                    bool eq = true;
-#pragma unroll
-                    for (int l = 0; l < NW; ++l) eq = eq && (sm.keys[l][t] == mn[l]);
-                    if (eq) {
-                        if (t != j) {
-#pragma unroll
-                            for (int l = 0; l < NW; ++l) { sm.keys[l][t] = sm.keys[l][j]; sm.keys[l][j] = mn[l]; }
-                            if (EXT) { const u64 v = sm.val[t]; sm.val[t] = sm.val[j]; sm.val[j] = v; }
-                        }
-                        ++j;
-                    }
-                }
-                const u32 c = j - i;
-                if (c >= P.lower && c <= P.upper) { ++kept; occ += c; }
-                i = j;
-            }
+        for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
+            const u32 slot = tid * Cfg::SLOTS_PT + i;
+            const u32 c = half16(sm.cnt2[slot >> 1], slot);
+            if (c >= P.lower && c <= P.upper) { keepmask |= 1u << i; ++kept; occ += c; }
         }
         u32 ek, eo, tk, to;
         block_scan2(kept, occ, sm.wa, sm.wb, ek, eo, tk, to);
-
-        // ---- position of the bin in the arena: decoupled look-back over the preceding bins
-        if (warp == 0) {
-            u64 bk = 0, bo = 0;
-            if (lb == 0) {
-                if (lane == 0) { stv64(P.lb_occ, LBF_INC | to); stv64(P.lb_kept, LBF_INC | tk); }
-            } else {
-                if (lane == 0) { stv64(P.lb_occ + lb, LBF_AGG | to); stv64(P.lb_kept + lb, LBF_AGG | tk); }
-                long look = (long)lb - 1;
-                while (true) {
-                    const long idx = look - lane;
-                    u64 vk = LBF_INC, vo = LBF_INC;
-                    if (idx >= 0) {
-                        do { vk = ldv64(P.lb_kept + idx); vo = ldv64(P.lb_occ + idx); } while ((vk >> 62) == 0 || (vk >> 62) != (vo >> 62));
-                    }
-                    const u32 inc = __ballot_sync(0xFFFFFFFFu, (vk >> 62) == 2);
-                    const int first = inc ? __ffs(inc) - 1 : 32;
-                    u64 ck = (lane <= first) ? (vk & LBF_MASK) : 0, co = (lane <= first) ? (vo & LBF_MASK) : 0;
-#pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) {
-                        ck += __shfl_xor_sync(0xFFFFFFFFu, ck, d);
-                        co += __shfl_xor_sync(0xFFFFFFFFu, co, d);
-                    }
-                    bk += ck; bo += co;
-                    if (inc) break;
-                    look -= 32;
-                }
-                if (lane == 0) { stv64(P.lb_occ + lb, LBF_INC | (bo + to)); stv64(P.lb_kept + lb, LBF_INC | (bk + tk)); }
-            }
-            if (lane == 0) {
-                sm.gbase_kept = bk; sm.gbase_occ = bo;
-                if (lb == P.nbins - 1) { P.cursor[0] = bk + tk; P.cursor[1] = bo + to; }
-            }
+        if (tid == 0) {
+            const u64 sk = tk ? atomicAdd(P.stage_cursor, (u64)tk) : 0;
+            const u64 so = (EXT && to) ? atomicAdd(P.stage_cursor + 1, (u64)to) : 0;
+            sm.stage_kept = sk; sm.stage_occ = so;
+            P.bin_rec[4 * (size_t)lb + 0] = sk; P.bin_rec[4 * (size_t)lb + 1] = tk;
+            P.bin_rec[4 * (size_t)lb + 2] = so; P.bin_rec[4 * (size_t)lb + 3] = EXT ? to : 0;
         }
         __syncthreads();
-
-        // ---- emit the kept runs of my sub-buckets, in order
         {
-            u64 g = sm.gbase_kept + ek, go = sm.gbase_occ + eo;
-#pragma unroll 1
-            for (int sb = 0; sb < Cfg::BPT; ++sb) {
-                const u32 d = tid * Cfg::BPT + sb;
-                const u32 s0 = sm.cnt[d], s1 = sm.cnt[d + 1];
-                const bool complex_sb = (sm.cplx[d >> 5] >> (d & 31)) & 1;
-                for (u32 i = s0; i < s1;) {
-                    u32 r = s1;
-                    if (complex_sb) {
-                        r = i + 1;
-                        while (r < s1) {
-                            bool eq = true;
+            u64 g = sm.stage_kept + ek;
+            u32 lo = eo;   // occurrence offset inside the bin
 #pragma unroll
-                            for (int l = 0; l < NW; ++l) eq = eq && (sm.keys[l][r] == sm.keys[l][i]);
-                            if (!eq) break;
-                            ++r;
-                        }
-                    }
-                    const u32 c = r - i;
-                    if (c >= P.lower && c <= P.upper) {
+            for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
+                const u32 slot = tid * Cfg::SLOTS_PT + i;
+                const u32 word = sm.cnt2[slot >> 1];
+                const u32 c = half16(word, slot);
+                u32 mark = 0xFFFFu;   // "not kept" for the occurrence pass
+                if ((keepmask >> i) & 1) {
+                    if (NW == 1) P.st_words[g] = sm.fp[slot];
+                    else {
 #pragma unroll
-                        for (int l = 0; l < NW; ++l) P.out_words[g * NW + l] = sm.keys[l][i];
-                        P.out_cnt[g] = c;
-                        if (c < (u32)BN_HCAP) atomicAdd(&sm.hist[c], 1u); else atomicAdd(&P.histogram[c], 1ull);
-                        if (EXT) {
-                            P.out_occ_off[g] = go;
-                            for (u32 t = 0; t < c; ++t) {
-                                const u64 v = sm.val[i + t];
-                                P.out_pos[go + t] = (u32)(v >> 32);
-                                P.out_rid[go + t] = (int)(u32)v;
-                            }
-                            go += c;
-                        }
-                        ++g;
+                        for (int l = 0; l < NW; ++l) P.st_words[g * NW + l] = sm.kw[l][slot];
                     }
-                    i = r;
+                    P.st_cnt[g] = c;
+                    if (c < (u32)BN_HCAP) atomicAdd(&sm.hist[c], 1u); else atomicAdd(&P.histogram[c], 1ull);
+                    mark = lo;
+                    lo += c;
+                    ++g;
+                }
+                if (EXT) {   // both halves of a word belong to this thread (SLOTS_PT is even)
+                    const u32 sh = 16 * (slot & 1);
+                    sm.cnt2[slot >> 1] = (word & ~(0xFFFFu << sh)) | (mark << sh);
+                }
+            }
+        }
+        if (EXT) {
+            // ---- occurrences: (pos, rid) of every occurrence of a kept k-mer, grouped per k-mer
+            __syncthreads();
+            const u64 so = sm.stage_occ;
+#pragma unroll
+            for (int i = 0; i < Cfg::KPT; ++i) {
+                if (a + i < e) {
+                    const u32 slot = slot_of[i];
+                    const u32 off = half16(sm.cnt2[slot >> 1], slot);
+                    if (off != 0xFFFFu) {
+                        const u64 p = so + off + occ_idx[i];
+                        P.st_pos[p] = (u32)(vreg[i] >> 32);
+                        P.st_rid[p] = (int)(u32)vreg[i];
+                    }
                 }
             }
         }
@@ -447,6 +385,165 @@ __global__ void __launch_bounds__(BN_THREADS, 2) k_bin_sort_count(BinParams P)
     __syncthreads();
     for (int i = tid; i < BN_HCAP; i += BN_THREADS)
         if (sm.hist[i]) atomicAdd(&P.histogram[i], (u64)sm.hist[i]);
+}
+
+// ---- final positions of the bins: exclusive scan of (kept, occurrences) over the bins; one block ----
+__global__ void __launch_bounds__(1024) k_bin_offsets(const u64 *__restrict__ bin_rec, u32 nbins, u64 *__restrict__ fin,
+                                                       u64 *__restrict__ cursor, u32 big_from, u32 *__restrict__ big_list,
+                                                       u32 *__restrict__ big_count)
+{
+    __shared__ u64 s_a[32], s_b[32];
+    __shared__ u64 carry_a, carry_b;
+    if (threadIdx.x == 0) { carry_a = cursor[0]; carry_b = cursor[1]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 base = 0; base < nbins; base += 1024) {
+        const u32 b = base + threadIdx.x;
+        u64 x = 0, y = 0;
+        if (b < nbins) { x = bin_rec[4 * (size_t)b + 1]; y = bin_rec[4 * (size_t)b + 3]; }
+        if (x > (u64)big_from) big_list[atomicAdd(big_count, 1u)] = b;   // handled by the large gather launch
+        u64 ix = x, iy = y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 p = __shfl_up_sync(0xFFFFFFFFu, ix, d);
+            u64 q = __shfl_up_sync(0xFFFFFFFFu, iy, d);
+            if (lane >= d) { ix += p; iy += q; }
+        }
+        if (lane == 31) { s_a[warp] = ix; s_b[warp] = iy; }
+        __syncthreads();
+        if (warp == 0) {
+            u64 p = s_a[lane], q = s_b[lane], ip = p, iq = q;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u64 u = __shfl_up_sync(0xFFFFFFFFu, ip, d);
+                u64 v = __shfl_up_sync(0xFFFFFFFFu, iq, d);
+                if (lane >= d) { ip += u; iq += v; }
+            }
+            s_a[lane] = ip - p; s_b[lane] = iq - q;
+        }
+        __syncthreads();
+        const u64 ex = carry_a + s_a[warp] + ix - x, ey = carry_b + s_b[warp] + iy - y;
+        if (b < nbins) { fin[2 * (size_t)b] = ex; fin[2 * (size_t)b + 1] = ey; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry_a = ex + x; carry_b = ey + y; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { cursor[0] = carry_a; cursor[1] = carry_b; }
+}
+
+// ---- per bin: sort the kept k-mers by key and move them (and their occurrences) to the arena ----------
+// One CTA per bin.  CAPD = most kept entries this instantiation handles; bins with more than CAPD or at
+// most skip_upto entries are left to the other launch.
+template <int NW, bool EXT, int CAPD, int THREADS, bool FROM_LIST>
+__global__ void __launch_bounds__(THREADS) k_bin_gather(BinParams P)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    u64 *s_key = reinterpret_cast<u64 *>(smraw);                       // [NW][CAPD]
+    u32 *s_cnt = reinterpret_cast<u32 *>(s_key + (size_t)NW * CAPD);  // [CAPD]
+    u32 *s_src = s_cnt + CAPD;                                        // [CAPD] occurrence start inside the bin (staging order)
+    __shared__ u32 s_warp[THREADS / 32];
+  for (u32 work = blockIdx.x; work < (FROM_LIST ? *P.big_count : P.nbins); work += gridDim.x) {
+    const u32 lb = FROM_LIST ? P.big_list[work] : work;
+    const u64 sk = P.bin_rec[4 * (size_t)lb + 0];
+    const u32 D = (u32)P.bin_rec[4 * (size_t)lb + 1];
+    const u64 so = P.bin_rec[4 * (size_t)lb + 2];
+    if (D == 0 || D > (u32)CAPD) continue;
+    __syncthreads();   // shared memory of the previous bin is free
+    const u64 fk = P.fin[2 * (size_t)lb], fo = P.fin[2 * (size_t)lb + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 n2 = 1;
+    while (n2 < D) n2 <<= 1;
+
+    // load; entries beyond D are padding that sorts last
+    for (u32 i = tid; i < n2; i += THREADS) {
+        if (i < D) {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) s_key[(size_t)l * CAPD + i] = P.st_words[(sk + i) * NW + l];
+            s_cnt[i] = P.st_cnt[sk + i];
+        } else {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) s_key[(size_t)l * CAPD + i] = ~0ull;
+            s_cnt[i] = 0;
+        }
+    }
+    __syncthreads();
+    if (EXT) {
+        // occurrence start of every entry in staging order: exclusive scan of the counts
+        u32 carry = 0;
+        for (u32 base = 0; base < n2; base += THREADS) {
+            const u32 i = base + tid;
+            const u32 c = i < D ? s_cnt[i] : 0;
+            u32 inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            u32 off = carry, tot = 0;
+            for (int w = 0; w < THREADS / 32; ++w) { if (w < warp) off += s_warp[w]; tot += s_warp[w]; }
+            if (i < n2) s_src[i] = off + inc - c;
+            carry += tot;
+            __syncthreads();
+        }
+    }
+
+    // bitonic sort by key (ascending, word 0 most significant), payload (cnt, src) follows
+    for (u32 size = 2; size <= n2; size <<= 1) {
+        for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
+            for (u32 t = tid; t < n2 / 2; t += THREADS) {
+                const u32 i = 2 * t - (t & (stride - 1));
+                const u32 j = i + stride;
+                const bool up = ((i & size) == 0);
+                u64 a[NW], b[NW];
+#pragma unroll
+                for (int l = 0; l < NW; ++l) { a[l] = s_key[(size_t)l * CAPD + i]; b[l] = s_key[(size_t)l * CAPD + j]; }
+                const bool swap = up ? key_less<NW>(b, a) : key_less<NW>(a, b);
+                if (swap) {
+#pragma unroll
+                    for (int l = 0; l < NW; ++l) { s_key[(size_t)l * CAPD + i] = b[l]; s_key[(size_t)l * CAPD + j] = a[l]; }
+                    const u32 c = s_cnt[i]; s_cnt[i] = s_cnt[j]; s_cnt[j] = c;
+                    if (EXT) { const u32 s = s_src[i]; s_src[i] = s_src[j]; s_src[j] = s; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // write in sorted order; occurrence offsets = exclusive scan of the counts in sorted order
+    u32 carry = 0;
+    for (u32 base = 0; base < n2; base += THREADS) {
+        const u32 i = base + tid;
+        const u32 c = i < D ? s_cnt[i] : 0;
+        u32 dst = 0;
+        if (EXT) {
+            u32 inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            u32 off = carry, tot = 0;
+            for (int w = 0; w < THREADS / 32; ++w) { if (w < warp) off += s_warp[w]; tot += s_warp[w]; }
+            dst = off + inc - c;
+            carry += tot;
+            __syncthreads();
+        }
+        if (i < D) {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) P.out_words[(fk + i) * NW + l] = s_key[(size_t)l * CAPD + i];
+            P.out_cnt[fk + i] = c;
+            if (EXT) {
+                P.out_occ_off[fk + i] = fo + dst;
+                const u64 src = so + s_src[i], dd = fo + dst;
+                for (u32 t = 0; t < c; ++t) { P.out_pos[dd + t] = P.st_pos[src + t]; P.out_rid[dd + t] = P.st_rid[src + t]; }
+            }
+        }
+    }
+  }
 }
 
 // ---- per-source segment tables of the bins a rank owns (multi-rank) ---------------------------------
@@ -534,22 +631,37 @@ cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nran
     return cudaGetLastError();
 }
 
+constexpr int GS_CAP = 512, GS_THREADS = 128;      // gather: the usual bins, one CTA each
+constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers (up to the bin capacity)
+
 template <int NW, bool EXT>
 static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t s)
 {
-    const size_t smem = sizeof(BinSmem<NW, EXT>);
-    cudaError_t e = cudaFuncSetAttribute(k_bin_sort_count<NW, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int GL_CAP = NW == 1 ? 8192 : (NW == 2 ? 4096 : 2048);   // power of two >= bin capacity
+    static_assert(BinCfg<NW>::CAP <= GL_CAP, "gather capacity");
+    const size_t smem = sizeof(BinSmem<NW>);
+    cudaError_t e = cudaFuncSetAttribute(k_bin_count<NW, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_sort_count<NW, EXT>, BN_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_count<NW, EXT>, BN_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const u32 grid = (u32)std::min<u64>((u64)sm_count * per_sm, std::max<u32>(P.nbins, 1u));
-    k_bin_sort_count<NW, EXT><<<grid, BN_THREADS, smem, s>>>(P);
+    k_bin_count<NW, EXT><<<grid, BN_THREADS, smem, s>>>(P);
+    k_bin_offsets<<<1, 1024, 0, s>>>(P.bin_rec, P.nbins, P.fin, P.cursor, (u32)GS_CAP, P.big_list, P.big_count);
+    // gather + sort: a small-footprint launch for the usual bins, a large one for bins with many kept k-mers
+    const size_t per_entry = (size_t)8 * NW + 8;
+    const size_t smem_s = per_entry * GS_CAP, smem_l = per_entry * GL_CAP;
+    e = cudaFuncSetAttribute(k_bin_gather<NW, EXT, GS_CAP, GS_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+    if (e != cudaSuccess) return e;
+    k_bin_gather<NW, EXT, GS_CAP, GS_THREADS, false><<<P.nbins, GS_THREADS, smem_s, s>>>(P);
+    e = cudaFuncSetAttribute(k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+    if (e != cudaSuccess) return e;
+    k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true><<<sm_count, GL_THREADS, smem_l, s>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_sort_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
+cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
 {
     if (P.nbins == 0) return cudaSuccess;
     if (nwords == 1) return ext ? launch_bins_t<1, true>(P, sm_count, s) : launch_bins_t<1, false>(P, sm_count, s);

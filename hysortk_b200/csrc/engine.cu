@@ -154,6 +154,7 @@ struct hsk_ctx {
     DevBuf d_keys[2][MAX_WORDS], d_val[2], d_rscratch, d_cscratch, d_tsum, d_tbase;
     // result arena
     DevBuf d_owords, d_ocnt, d_oocc_off, d_opos, d_orid, d_hist, d_cursor;
+    DevBuf d_swords, d_scnt, d_spos, d_srid;   // staging (bins in completion order)
     HostBuf h_cursor, h_owords, h_ocnt, h_oocc_off, h_opos, h_orid, h_hist;
     u64 n_kept = 0, n_occ = 0;
     bool have_result = false;
@@ -261,7 +262,7 @@ void hsk_destroy(hsk_ctx *c)
     if (c->comm) g_nccl.CommDestroy(c->comm);
     DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_bucket, &c->d_len, &c->d_words,
                     &c->d_ext, &c->d_alltot, &c->d_rlen, &c->d_rwords, &c->d_rext, &c->d_seg, &c->d_lb, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
-                    &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
+                    &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
     for (int h = 0; h < 2; ++h) for (int w = 0; w < MAX_WORDS; ++w) c->d_keys[h][w].release();
@@ -475,13 +476,16 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     u64 *d_start = d_kmers + 2 * (size_t)T, *d_wstart = d_start + T + 1;
     u64 *hm = c->h_meta.as<u64>();
 
-    // ---- small device state of this call: [cursor 2][owned total 1][ticket, ovf_count (u32 x2)]
+    // ---- small device state of this call:
+    //      [cursor 2][owned total 1][ticket, ovf_count (u32 x2)][stage cursor 2][big_count (u32)]
     CK(c->d_cursor.ensure(64));
     CK(c->h_cursor.ensure(64));
     CK(cudaMemsetAsync(c->d_cursor.p, 0, 64, s));
     u64 *d_cursor = c->d_cursor.as<u64>();
     u64 *d_owned = d_cursor + 2;
     u32 *d_ticket = reinterpret_cast<u32 *>(d_cursor + 3), *d_ovfc = d_ticket + 1;
+    u64 *d_stagecur = d_cursor + 4;
+    u32 *d_bigc = reinterpret_cast<u32 *>(d_cursor + 6);
 
     BinParams BP;
     memset(&BP, 0, sizeof(BP));
@@ -553,32 +557,39 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     }
     c->stats.n_kmers_owned = owned;
 
-    // ---- result arena + look-back state
+    // ---- result arena, staging area, per-bin records
     const u64 arena = owned / (u64)c->cfg.lower + 8;
     CK(c->d_owords.ensure(arena * NW * 8));
     CK(c->d_ocnt.ensure(arena * 4));
+    CK(c->d_swords.ensure(arena * NW * 8));
+    CK(c->d_scnt.ensure(arena * 4));
     if (ext) {
         CK(c->d_oocc_off.ensure((arena + 1) * 8));
         CK(c->d_opos.ensure((owned + 8) * 4));
         CK(c->d_orid.ensure((owned + 8) * 4));
+        CK(c->d_spos.ensure((owned + 8) * 4));
+        CK(c->d_srid.ensure((owned + 8) * 4));
     }
     const size_t hist_bins = (size_t)c->cfg.upper + 1;
     CK(c->d_hist.ensure(hist_bins * 8));
     CK(cudaMemsetAsync(c->d_hist.p, 0, hist_bins * 8, s));
-    CK(c->d_lb.ensure(((size_t)2 * TG + 2) * 8 + ((size_t)TG + 2) * 4));
-    CK(cudaMemsetAsync(c->d_lb.p, 0, ((size_t)2 * TG + 2) * 8, s));
+    CK(c->d_lb.ensure(((size_t)6 * TG + 8) * 8 + ((size_t)2 * TG + 8) * 4));
+    BP.st_words = c->d_swords.as<u64>(); BP.st_cnt = c->d_scnt.as<u32>();
+    BP.st_pos = c->d_spos.as<u32>(); BP.st_rid = c->d_srid.as<int>();
+    BP.stage_cursor = d_stagecur;
+    BP.bin_rec = c->d_lb.as<u64>(); BP.fin = BP.bin_rec + (size_t)4 * TG;
     BP.out_words = c->d_owords.as<u64>(); BP.out_cnt = c->d_ocnt.as<u32>();
     BP.out_occ_off = c->d_oocc_off.as<u64>(); BP.out_pos = c->d_opos.as<u32>(); BP.out_rid = c->d_orid.as<int>();
     BP.histogram = c->d_hist.as<u64>(); BP.cursor = d_cursor;
-    BP.lb_kept = c->d_lb.as<u64>(); BP.lb_occ = BP.lb_kept + TG + 1;
     BP.ticket = d_ticket; BP.ovf_count = d_ovfc;
-    BP.ovf_list = reinterpret_cast<u32 *>(BP.lb_occ + TG + 1);
+    BP.ovf_list = reinterpret_cast<u32 *>(BP.fin + (size_t)2 * TG + 8);
+    BP.big_list = BP.ovf_list + TG + 4; BP.big_count = d_bigc;
 
     // ---- stages 4+5 on chip
     c->begin(c->ev_bins);
-    CK(launch_bin_sort_count(BP, NW, ext, c->sm_count, s));
+    CK(launch_bin_count(BP, NW, ext, c->sm_count, s));
     c->end(c->ev_bins);
-    c->stats.n_launches += 1;
+    c->stats.n_launches += 4;
     c->stats.n_batches = 1;
     CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

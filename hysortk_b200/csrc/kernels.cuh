@@ -62,16 +62,23 @@ struct BinParams {
     const u64 *seg_start[BN_MAX_SRC];    // nbins+1: first supermer of every bin inside the source's stream
     const u64 *seg_wstart[BN_MAX_SRC];   // nbins+1: first word
     const u64 *bin_kmers;                // nbins: k-mers per bin over all sources
+    // staging area (bins in completion order, unsorted inside a bin)
+    u64 *st_words; u32 *st_cnt; u32 *st_pos; int *st_rid;
+    u64 *stage_cursor;                   // [0] entries, [1] occurrences claimed so far (zeroed)
+    u64 *bin_rec;                        // nbins x {stage entry base, kept, stage occurrence base, occurrences}
+    u64 *fin;                            // nbins x {final entry base, final occurrence base}
+    // final arena (bins in index order, ascending k-mers inside a bin)
     u64 *out_words; u32 *out_cnt; u64 *out_occ_off; u32 *out_pos; int *out_rid;
     u64 *histogram;
-    u64 *cursor;                         // [0] entries, [1] occurrences: written by the last bin
-    u64 *lb_kept, *lb_occ;               // nbins look-back words each, zeroed
+    u64 *cursor;                         // [0] entries, [1] occurrences in the arena: advanced by k_bin_offsets
     u32 *ticket;                         // zeroed
     u32 *ovf_list, *ovf_count;           // bins left to the HBM path
+    u32 *big_list, *big_count;           // bins with more kept k-mers than the small gather handles
 };
 
 int bin_capacity(int nwords, bool ext);  // k-mers per bin the on-chip path can hold
-cudaError_t launch_bin_sort_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
+// k_bin_count + k_bin_offsets + k_bin_gather (x2)
+cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
 // multi-rank: segment tables of the owned bins inside the per-source streams + send/recv sizes (meta)
 cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start,
                             const u64 *local_wstart, u64 *seg_start, u64 *seg_wstart, u64 *meta, u64 *bin_kmers,
