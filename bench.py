@@ -313,10 +313,10 @@ def main_ours(args):
     real_bytes = st["supermer_bytes"] + n_kept * (8 * ctx.nwords + 4)
     ms_bins = st["ms_bins"]
     achieved = alg_bytes / (ms_bins * 1e-3) / 1e9 if ms_bins > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_bin_sort_count (expand + sort + count of one bin per CTA, in shared memory)",
+    roofline = {"bound": "hbm", "kernel": "k_bin_count (expand + count one bin per CTA in shared memory) + k_bin_offsets + k_bin_gather",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_bins,
-                "launches_per_step": 1,
+                "launches_per_step": 4,
                 "note": "algorithmic bytes = SURVEY 8(d) formula for stages 4+5 (HBM-resident expand, 8-bit LSD sort, count); "
                         "the kernel keeps the k-mers on chip, so a fraction above 1 is expected: bytes it really has to move "
                         "per launch are in hbm_bytes_needed",

@@ -68,6 +68,7 @@ struct BinSmem {
     u32 hist[BN_HCAP];
     u64 src_i0[BN_MAX_SRC], src_w0[BN_MAX_SRC];
     u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1], src_wbase[BN_MAX_SRC + 1];
+    u64 src_wdone[BN_MAX_SRC];                              // words of the source consumed by earlier chunks
     u32 wa[BN_THREADS / 32], wb[BN_THREADS / 32];
     u64 stage_kept, stage_occ;
     u32 bin, nk, S, bail;
@@ -126,10 +127,101 @@ __device__ __forceinline__ u64 fingerprint(const u64 (&w)[NW])
 
 __device__ __forceinline__ u32 half16(u32 word, u32 slot) { return (word >> (16 * (slot & 1))) & 0xFFFFu; }
 
+// rolling expansion state of one thread: position (supermer j, offset o) and the forward / reverse words
+template <int NW>
+struct Roll {
+    u64 fwd[NW], rc[NW];
+    const u32 *wp;
+    u32 j, o, nj;
+    u64 extv;
+    bool fresh;
+};
+
+// canonical k-mer at the current position, then advance by one k-mer
+template <int NW, bool EXT>
+__device__ __forceinline__ void next_kmer(Roll<NW> &r, const BinSmem<NW> &sm, const BinParams &P, int k, int padbits,
+                                          u32 c0, u64 (&key)[NW], u64 &val)
+{
+    if (r.fresh) {
+        const u32 jl = r.j - c0;
+        const int s = sm.ssrc[jl];
+        r.wp = P.words[s] + sm.src_w0[s] + sm.src_wdone[s] + (sm.woff[jl] - sm.src_wbase[s]);
+        r.nj = (u32)sm.koff[jl + 1] - (u32)sm.koff[jl];
+        if (EXT) r.extv = P.ext[s][sm.src_i0[s] + (r.j - sm.src_sbase[s])];
+        const u32 nws = sm.woff[jl + 1] - sm.woff[jl];
+        const u32 wi = r.o >> 4, sh = 2 * (r.o & 15);
+        u32 x[2 * NW + 1];
+#pragma unroll
+        for (int t = 0; t < 2 * NW + 1; ++t) x[t] = (wi + t < nws) ? __ldg(r.wp + wi + t) : 0u;
+#pragma unroll
+        for (int l = 0; l < NW; ++l) {
+            u32 hi = __funnelshift_l(x[2 * l + 1], x[2 * l], sh);
+            u32 lo = __funnelshift_l(x[2 * l + 2], x[2 * l + 1], sh);
+            r.fwd[l] = ((u64)hi << 32) | lo;
+        }
+        if (padbits) r.fwd[NW - 1] &= ~0ull << padbits;
+        kmer_twin<NW>(r.fwd, k, r.rc);
+        r.fresh = false;
+    } else {
+        // roll: drop the first base, append base (o + k - 1) of the supermer
+        const u32 bo = r.o + (u32)k - 1;
+        const u64 c = (__ldg(r.wp + (bo >> 4)) >> (30 - 2 * (bo & 15))) & 3u;
+#pragma unroll
+        for (int l = 0; l < NW; ++l) {
+            r.fwd[l] <<= 2;
+            if (l + 1 < NW) r.fwd[l] |= r.fwd[l + 1] >> 62;
+        }
+        r.fwd[NW - 1] |= c << padbits;
+#pragma unroll
+        for (int l = NW - 1; l >= 0; --l) {
+            r.rc[l] >>= 2;
+            if (l > 0) r.rc[l] |= r.rc[l - 1] << 62;
+        }
+        r.rc[0] |= (3 - c) << 62;
+        if (padbits) r.rc[NW - 1] &= ~0ull << padbits;
+    }
+    const bool use_rc = key_less<NW>(r.rc, r.fwd);
+#pragma unroll
+    for (int l = 0; l < NW; ++l) key[l] = use_rc ? r.rc[l] : r.fwd[l];
+    if (EXT) val = r.extv + ((u64)r.o << 32);
+    ++r.o;
+    if (r.o >= r.nj) { ++r.j; r.o = 0; r.fresh = true; }
+}
+
+// claim or find the slot of a k-mer and bump its counter; returns the slot and the counter word before the bump.
+// A full table (more distinct k-mers than slots) sets the bail flag.
+template <int NW>
+__device__ __forceinline__ u32 table_insert(BinSmem<NW> &sm, const u64 (&key)[NW], u32 &prev)
+{
+    using Cfg = BinCfg<NW>;
+    const u64 f = fingerprint<NW>(key);
+    u32 slot = (u32)((f * 0x9E3779B97F4A7C15ull) >> (64 - Cfg::TS_BITS));
+    for (int probes = 0;; ++probes) {
+        const u64 old = atomicCAS(&sm.fp[slot], BN_EMPTY, f);
+        if (old == BN_EMPTY) {
+            if (NW > 1) {
+#pragma unroll
+                for (int l = 0; l < NW; ++l) sm.kw[l][slot] = key[l];
+            }
+            break;
+        }
+        if (old == f) break;
+        if (probes >= Cfg::TS) { atomicOr(&sm.bail, 16u); prev = 0; return slot; }
+        slot = (slot + 1) & (Cfg::TS - 1);
+    }
+    prev = atomicAdd(&sm.cnt2[slot >> 1], 1u << (16 * (slot & 1)));
+    return slot;
+}
+
+// One CTA per bin.  K <= 32 without EXTENSION needs no per-occurrence state after the insertion, so a bin of
+// any size up to 65535 occurrences (16-bit counters / offsets) is handled, supermers in chunks of BN_SCAP, as
+// long as its distinct k-mers fit the table.  With EXTENSION or K > 32 every thread keeps its occurrences in
+// registers for the second pass, which limits a bin to BinCfg::CAP occurrences and BN_SCAP supermers.
 template <int NW, bool EXT>
 __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinParams P)
 {
     using Cfg = BinCfg<NW>;
+    constexpr bool FREE = (NW == 1) && !EXT;
     extern __shared__ __align__(16) unsigned char smraw[];
     BinSmem<NW> &sm = *reinterpret_cast<BinSmem<NW> *>(smraw);
     const int tid = threadIdx.x;
@@ -153,6 +245,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             sm.src_i0[tid] = i0;
             sm.src_n[tid] = (u32)min(i1 - i0, (u64)0xFFFFFFFFu);
             sm.src_w0[tid] = P.seg_wstart[tid][lb];
+            sm.src_wdone[tid] = 0;
         }
         __syncthreads();
         if (tid == 0) {
@@ -162,25 +255,34 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             const u64 nk = P.bin_kmers[lb];
             sm.nk = (u32)min(nk, (u64)0xFFFFFFFFu);
             sm.S = (u32)min(s, (u64)0xFFFFFFFFu);
-            if (nk > (u64)Cfg::CAP || s > (u64)BN_SCAP) sm.bail = 1;
+            if (FREE) { if (nk > 65535ull || s > 65535ull) sm.bail = 1; }
+            else { if (nk > (u64)Cfg::CAP || s > (u64)BN_SCAP) sm.bail = 1; }
         }
         __syncthreads();
         const u32 nk = sm.nk, S = sm.S;
 
-        if (!sm.bail) {
-            // ---- supermer table: k-mer and word offsets of every supermer of the bin
+        u64 kreg[FREE || NW == 1 ? 1 : Cfg::KPT][NW];   // full keys again for the K > 32 verification
+        u64 vreg[EXT ? Cfg::KPT : 1];
+        u16 slot_of[FREE ? 1 : Cfg::KPT], occ_idx[EXT ? Cfg::KPT : 1];
+        u32 a = 0, e = 0;   // my occurrences [a, e) of the (single) chunk when !FREE
+        u32 seen = 0;       // occurrences inserted so far (all chunks)
+
+        for (u32 c0 = 0; c0 < S && !sm.bail; c0 += BN_SCAP) {
+            const u32 Sc = min((u32)BN_SCAP, S - c0);
+            // ---- supermer table of the chunk: k-mer and word offsets of every supermer
             u32 n4[BN_SPT], w4[BN_SPT], tn = 0, tw = 0;
 #pragma unroll
             for (int i = 0; i < BN_SPT; ++i) {
-                const u32 j = tid * BN_SPT + i;
+                const u32 jl = tid * BN_SPT + i;
                 n4[i] = 0; w4[i] = 0;
-                if (j < S) {
+                if (jl < Sc) {
+                    const u32 j = c0 + jl;
                     int s = 0;
                     while (j >= sm.src_sbase[s + 1]) ++s;
                     const u32 len = P.len[s][sm.src_i0[s] + (j - sm.src_sbase[s])];
                     n4[i] = len - (u32)k + 1;
                     w4[i] = (len + 15) >> 4;
-                    sm.ssrc[j] = (u8)s;
+                    sm.ssrc[jl] = (u8)s;
                 }
                 tn += n4[i]; tw += w4[i];
             }
@@ -188,108 +290,68 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             block_scan2(tn, tw, sm.wa, sm.wb, en, ew, totn, totw);
 #pragma unroll
             for (int i = 0; i < BN_SPT; ++i) {
-                const u32 j = tid * BN_SPT + i;
-                if (j < S) { sm.koff[j] = (u16)en; sm.woff[j] = ew; }
+                const u32 jl = tid * BN_SPT + i;
+                if (jl < Sc) { sm.koff[jl] = (u16)en; sm.woff[jl] = ew; }
                 en += n4[i]; ew += w4[i];
             }
             if (tid == 0) {
-                sm.koff[S] = (u16)totn; sm.woff[S] = totw;
-                if (totn != nk) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
+                sm.koff[Sc] = (u16)totn; sm.woff[Sc] = totw;
+                if (seen + totn > nk) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
             }
             __syncthreads();
-            if (tid < P.nsrc) sm.src_wbase[tid] = sm.woff[min(sm.src_sbase[tid], S)];
+            // part of every source that lies in this chunk: [ls, le) in chunk-local supermer indices
+            if (tid < P.nsrc) {
+                const u32 ls = min(max(sm.src_sbase[tid], c0) - c0, Sc);
+                sm.src_wbase[tid] = sm.woff[ls];
+            }
             __syncthreads();
-        }
+            if (sm.bail) break;
 
-        u64 kreg[NW > 1 ? Cfg::KPT : 1][NW];   // full keys are only needed again for the K > 32 verification
-        u64 vreg[EXT ? Cfg::KPT : 1];
-        u16 slot_of[Cfg::KPT], occ_idx[EXT ? Cfg::KPT : 1];
-        const u32 q = (nk + BN_THREADS - 1) / BN_THREADS;   // k-mers per thread, <= KPT
-        const u32 a = tid * q, e = min(nk, a + q);
-
-        if (!sm.bail && a < e) {
-            // ---- expansion + insertion: my q consecutive k-mers, rolling inside a supermer
-            u32 j = 0;
-            for (u32 step = BN_SCAP / 2; step >= 1; step >>= 1)
-                if (j + step < S && sm.koff[j + step] <= a) j += step;
-            u32 o = a - sm.koff[j];
-            u64 fwd[NW], rc[NW];
-            const u32 *wp = nullptr;
-            u32 nj = 0;
-            u64 extv = 0;
-            bool fresh = true;
-#pragma unroll
-            for (int i = 0; i < Cfg::KPT; ++i) {
-                if (a + i < e) {
-                    if (fresh) {
-                        const int s = sm.ssrc[j];
-                        wp = P.words[s] + sm.src_w0[s] + (sm.woff[j] - sm.src_wbase[s]);
-                        nj = (u32)sm.koff[j + 1] - (u32)sm.koff[j];
-                        if (EXT) extv = P.ext[s][sm.src_i0[s] + (j - sm.src_sbase[s])];
-                        const u32 nws = sm.woff[j + 1] - sm.woff[j];
-                        const u32 wi = o >> 4, sh = 2 * (o & 15);
-                        u32 x[2 * NW + 1];
-#pragma unroll
-                        for (int t = 0; t < 2 * NW + 1; ++t) x[t] = (wi + t < nws) ? __ldg(wp + wi + t) : 0u;
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) {
-                            u32 hi = __funnelshift_l(x[2 * l + 1], x[2 * l], sh);
-                            u32 lo = __funnelshift_l(x[2 * l + 2], x[2 * l + 1], sh);
-                            fwd[l] = ((u64)hi << 32) | lo;
-                        }
-                        if (padbits) fwd[NW - 1] &= ~0ull << padbits;
-                        kmer_twin<NW>(fwd, k, rc);
-                        fresh = false;
-                    } else {
-                        // roll: drop the first base, append base (o + k - 1) of the supermer
-                        const u32 bo = o + (u32)k - 1;
-                        const u64 c = (__ldg(wp + (bo >> 4)) >> (30 - 2 * (bo & 15))) & 3u;
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) {
-                            fwd[l] <<= 2;
-                            if (l + 1 < NW) fwd[l] |= fwd[l + 1] >> 62;
-                        }
-                        fwd[NW - 1] |= c << padbits;
-#pragma unroll
-                        for (int l = NW - 1; l >= 0; --l) {
-                            rc[l] >>= 2;
-                            if (l > 0) rc[l] |= rc[l - 1] << 62;
-                        }
-                        rc[0] |= (3 - c) << 62;
-                        if (padbits) rc[NW - 1] &= ~0ull << padbits;
+            const u32 nkc = totn;
+            const u32 q = (nkc + BN_THREADS - 1) / BN_THREADS;   // occurrences per thread in this chunk
+            a = tid * q; e = min(nkc, a + q);
+            if (a < e) {
+                Roll<NW> r;
+                u32 jl = 0;
+                for (u32 step = BN_SCAP / 2; step >= 1; step >>= 1)
+                    if (jl + step < Sc && sm.koff[jl + step] <= a) jl += step;
+                r.j = c0 + jl; r.o = a - sm.koff[jl]; r.fresh = true; r.wp = nullptr; r.nj = 0; r.extv = 0;
+                if (FREE) {
+                    for (u32 i = a; i < e; ++i) {
+                        u64 key[NW], val;
+                        next_kmer<NW, EXT>(r, sm, P, k, padbits, c0, key, val);
+                        u32 prev;
+                        table_insert<NW>(sm, key, prev);
                     }
-                    const bool use_rc = key_less<NW>(rc, fwd);
-                    u64 key[NW];
+                } else {
 #pragma unroll
-                    for (int l = 0; l < NW; ++l) key[l] = use_rc ? rc[l] : fwd[l];
-                    if (NW > 1) {
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) kreg[i][l] = key[l];
-                    }
-                    if (EXT) vreg[i] = extv + ((u64)o << 32);
-                    // insert: claim or find the slot of this k-mer, bump its counter
-                    const u64 f = fingerprint<NW>(key);
-                    u32 slot = (u32)((f * 0x9E3779B97F4A7C15ull) >> (64 - Cfg::TS_BITS));
-                    while (true) {
-                        const u64 old = atomicCAS(&sm.fp[slot], BN_EMPTY, f);
-                        if (old == BN_EMPTY) {
+                    for (int i = 0; i < Cfg::KPT; ++i) {
+                        if (a + i < e) {
+                            u64 key[NW], val = 0;
+                            next_kmer<NW, EXT>(r, sm, P, k, padbits, c0, key, val);
                             if (NW > 1) {
 #pragma unroll
-                                for (int l = 0; l < NW; ++l) sm.kw[l][slot] = key[l];
+                                for (int l = 0; l < NW; ++l) kreg[i][l] = key[l];
                             }
-                            break;
+                            if (EXT) vreg[i] = val;
+                            u32 prev;
+                            const u32 slot = table_insert<NW>(sm, key, prev);
+                            slot_of[i] = (u16)slot;
+                            if (EXT) occ_idx[i] = (u16)half16(prev, slot);
                         }
-                        if (old == f) break;
-                        slot = (slot + 1) & (Cfg::TS - 1);
                     }
-                    const u32 prev = atomicAdd(&sm.cnt2[slot >> 1], 1u << (16 * (slot & 1)));
-                    slot_of[i] = (u16)slot;
-                    if (EXT) occ_idx[i] = (u16)half16(prev, slot);
-                    ++o;
-                    if (o >= nj) { ++j; o = 0; fresh = true; }
                 }
             }
+            seen += nkc;
+            __syncthreads();   // the chunk's table may be overwritten by the next chunk
+            if (tid < P.nsrc) {
+                const u32 ls = min(max(sm.src_sbase[tid], c0) - c0, Sc);
+                const u32 le = min(max(sm.src_sbase[tid + 1], c0) - c0, Sc);
+                sm.src_wdone[tid] += sm.woff[le] - sm.woff[ls];
+            }
+            __syncthreads();
         }
+        if (!sm.bail && seen != nk && tid == 0) sm.bail = 2;
         __syncthreads();
 
         if (NW > 1) {

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -293,7 +294,11 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
         CK(cudaStreamSynchronize(c->stream));
         mx = c->h_cursor.as<u64>()[5];
     }
-    const u64 target = (u64)bin_capacity(c->nwords, c->cfg.ext != 0) / 2;
+    // average occurrences per bin: K <= 32 without EXTENSION takes bins of any size on chip (limited by distinct
+    // k-mers), the other configurations keep a margin below the hard capacity
+    const u64 cap = (u64)bin_capacity(c->nwords, c->cfg.ext != 0);
+    u64 target = (c->nwords == 1 && !c->cfg.ext) ? 8192 : cap * 2 / 5;
+    if (const char *ev = getenv("HSK_TARGET_BIN")) { u64 v = strtoull(ev, nullptr, 10); if (v >= 64) target = v; }
     u64 tg = (mx * 4 + target - 1) / target;
     tg = std::max<u64>(64, (tg + 63) / 64 * 64);
     tg = std::min<u64>(tg, MAX_BINS / (u64)c->cfg.nranks);
@@ -602,19 +607,14 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         CK(cudaMemcpy(ovf.data(), BP.ovf_list, (size_t)novf * 4, cudaMemcpyDeviceToHost));
         std::sort(ovf.begin(), ovf.end());
         std::vector<OvfSeg> segs;
-        for (u32 lb : ovf) {
-            for (int src = 0; src < G; ++src) {
-                u64 st2[2], ws, km;
-                CK(cudaMemcpy(st2, BP.seg_start[src] + lb, 16, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(&ws, BP.seg_wstart[src] + lb, 8, cudaMemcpyDeviceToHost));
-                const u64 *kp = (G == 1) ? d_kmers + lb : c->d_alltot.as<u64>() + ((size_t)src * 2) * T + b_lo + lb;
-                CK(cudaMemcpy(&km, kp, 8, cudaMemcpyDeviceToHost));
-                // segment offsets are relative to the stream the bin kernel was given for this source
-                const bool local = (src == me);
-                u64 i0 = st2[0], w0 = ws;
-                (void)local;
-                segs.push_back({src, i0, st2[1] - st2[0], w0, km});
-            }
+        // tables of all bins in one copy per source (only when something overflowed)
+        std::vector<u64> hs((size_t)TG + 1), hw((size_t)TG + 1), hk((size_t)TG);
+        for (int src = 0; src < G; ++src) {
+            CK(cudaMemcpy(hs.data(), BP.seg_start[src], ((size_t)TG + 1) * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(hw.data(), BP.seg_wstart[src], ((size_t)TG + 1) * 8, cudaMemcpyDeviceToHost));
+            const u64 *kp = (G == 1) ? d_kmers : c->d_alltot.as<u64>() + ((size_t)src * 2) * T + b_lo;
+            CK(cudaMemcpy(hk.data(), kp, (size_t)TG * 8, cudaMemcpyDeviceToHost));
+            for (u32 lb : ovf) segs.push_back({src, hs[lb], hs[lb + 1] - hs[lb], hw[lb], hk[lb]});
         }
         if (run_hbm_path(c, segs)) return 1;
         CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 16, cudaMemcpyDeviceToHost, s));

@@ -138,10 +138,15 @@ def test_against_oracle(k, m, ext, lower, upper, read_len):
         # idempotent and independent of batching / bucket count
         c2, _ = gpu_counts(ctx, rs.packed, rs.readlens, readid_base=3)
         po.assert_equal(c2, exp, "second call on the same context")
-    with capi.Context(k, m, lower, upper, ext, buckets_per_rank=37, batch_kmers=50_000) as ctx:
+    # three huge bins: nothing fits on chip, everything takes the HBM path (expand -> radix sort -> count) in batches
+    with capi.Context(k, m, lower, upper, ext, buckets_per_rank=3, batch_kmers=100_000) as ctx:
         c3, raw3 = gpu_counts(ctx, rs.packed, rs.readlens, readid_base=3)
-        po.assert_equal(c3, exp, "small batches")
-        assert raw3["stats"]["n_batches"] > 3
+        po.assert_equal(c3, exp, "HBM path, small batches")
+        assert raw3["stats"]["n_overflow_bins"] == 3 and raw3["stats"]["n_batches"] >= 4
+    # mid-sized bins: several supermer chunks per bin on chip (K <= 32 without EXT), overflow otherwise
+    with capi.Context(k, m, lower, upper, ext, buckets_per_rank=37) as ctx:
+        c4, raw4 = gpu_counts(ctx, rs.packed, rs.readlens, readid_base=3)
+        po.assert_equal(c4, exp, "37 bins")
 
 
 def test_bucket_balance():
