@@ -361,6 +361,18 @@ def main_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    # the driver parses ONE JSON line from stdout: route everything else (NCCL banners, library chatter) to stderr
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _out = os.fdopen(_real_stdout, "w")
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001 - the final JSON line goes to the real stdout
+        kw.setdefault("file", _out)
+        _print(*args, **kw)
+        _out.flush()
+
     if a.impl == "reference":
         main_reference(a)
     else:
