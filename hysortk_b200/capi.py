@@ -57,10 +57,8 @@ class DeviceResult(C.Structure):
 
 
 class Supermers(C.Structure):
-    _fields_ = [("n_buckets", C.c_uint64), ("bucket_count", C.POINTER(C.c_uint64)),
-                ("bucket_words", C.POINTER(C.c_uint64)), ("bucket_kmers", C.POINTER(C.c_uint64)),
-                ("n_supermers", C.c_uint64), ("n_words", C.c_uint64), ("len", C.POINTER(C.c_uint16)),
-                ("words", C.POINTER(C.c_uint32)), ("ext", C.POINTER(C.c_uint64))]
+    _fields_ = [("n_bins", C.c_uint64), ("bin_slots", C.POINTER(C.c_uint64)), ("bin_kmers", C.POINTER(C.c_uint64)),
+                ("n_slots", C.c_uint64), ("slot_words", C.c_uint32), ("slots", C.POINTER(C.c_uint32))]
 
 
 _LIB = None
@@ -197,11 +195,13 @@ class Context:
         s = Supermers()
         _check(self.lib.hsk_debug_extract(self.handle, packed.ctypes.data, packed.nbytes, readlens.ctypes.data,
                                           len(readlens), readid_base, C.byref(s)))
-        T = int(s.n_buckets)
-        return dict(n_buckets=T, bucket_count=_arr(s.bucket_count, T, np.uint64),
-                    bucket_words=_arr(s.bucket_words, T, np.uint64), bucket_kmers=_arr(s.bucket_kmers, T, np.uint64),
-                    len=_arr(s.len, int(s.n_supermers), np.uint16), words=_arr(s.words, int(s.n_words), np.uint32),
-                    ext=_arr(s.ext, int(s.n_supermers), np.uint64) if self.ext else None)
+        T, S, SW = int(s.n_bins), int(s.n_slots), int(s.slot_words)
+        slots = _arr(s.slots, S * SW, np.uint32).reshape(S, SW)
+        pw = SW - (2 if self.ext else 0)
+        return dict(n_buckets=T, bucket_count=_arr(s.bin_slots, T, np.uint64), bucket_kmers=_arr(s.bin_kmers, T, np.uint64),
+                    slot_words=SW, slots=slots, len=(slots[:, pw - 1] & np.uint32(0xFF)).astype(np.int64) if S else np.zeros(0, np.int64),
+                    payload=slots[:, :pw].copy() if S else np.zeros((0, pw), np.uint32),
+                    ext=((slots[:, SW - 2].astype(np.uint64) << np.uint64(32)) | slots[:, SW - 1].astype(np.uint64)) if (self.ext and S) else None)
 
     def debug_sort(self, key_ptrs: list[int], tmp_ptrs: list[int], n: int, k: int, val_ptr: int = 0,
                    val_tmp_ptr: int = 0) -> None:

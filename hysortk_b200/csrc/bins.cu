@@ -62,13 +62,10 @@ struct BinSmem {
     u64 fp[BinCfg<NW>::TS];                                 // CAS key: the k-mer (NW == 1) or its fingerprint
     u64 kw[NW > 1 ? NW : 1][NW > 1 ? BinCfg<NW>::TS : 1];   // full key words (NW > 1)
     u32 cnt2[BinCfg<NW>::TS / 2];                           // two 16-bit counters per word
-    u32 woff[BN_SCAP + 1];
-    u16 koff[BN_SCAP + 2];
-    u8 ssrc[BN_SCAP];
+    u16 koff[BN_SCAP + 2];                                  // k-mer offset of every slot of the chunk
     u32 hist[BN_HCAP];
-    u64 src_i0[BN_MAX_SRC], src_w0[BN_MAX_SRC];
-    u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1], src_wbase[BN_MAX_SRC + 1];
-    u64 src_wdone[BN_MAX_SRC];                              // words of the source consumed by earlier chunks
+    u64 src_i0[BN_MAX_SRC];
+    u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1];
     u32 wa[BN_THREADS / 32], wb[BN_THREADS / 32];
     u64 stage_kept, stage_occ;
     u32 bin, nk, S, bail;
@@ -127,65 +124,68 @@ __device__ __forceinline__ u64 fingerprint(const u64 (&w)[NW])
 
 __device__ __forceinline__ u32 half16(u32 word, u32 slot) { return (word >> (16 * (slot & 1))) & 0xFFFFu; }
 
-// rolling expansion state of one thread: position (supermer j, offset o) and the forward / reverse words
-template <int NW>
-struct Roll {
-    u64 fwd[NW], rc[NW];
-    const u32 *wp;
-    u32 j, o, nj;
-    u64 extv;
-    bool fresh;
+// expansion state of one thread: the slot it is in (SW words in registers, shifted so that the current
+// k-mer starts at the top), the k-mers left in the slot, and the position of the current k-mer
+template <int SW>
+struct Walk {
+    u32 w[SW];
+    u32 j;        // slot index inside the bin
+    u32 left;     // k-mers of this slot not yet produced (0: load the next slot)
+    u32 pos, rid; // EXTENSION: PosInRead of the current k-mer, ReadId
 };
 
-// canonical k-mer at the current position, then advance by one k-mer
-template <int NW, bool EXT>
-__device__ __forceinline__ void next_kmer(Roll<NW> &r, const BinSmem<NW> &sm, const BinParams &P, int k, int padbits,
-                                          u32 c0, u64 (&key)[NW], u64 &val)
+template <int SW, int PW>
+__device__ __forceinline__ void shift_bases(u32 (&w)[SW], u32 nb)
 {
-    if (r.fresh) {
-        const u32 jl = r.j - c0;
-        const int s = sm.ssrc[jl];
-        r.wp = P.words[s] + sm.src_w0[s] + sm.src_wdone[s] + (sm.woff[jl] - sm.src_wbase[s]);
-        r.nj = (u32)sm.koff[jl + 1] - (u32)sm.koff[jl];
-        if (EXT) r.extv = P.ext[s][sm.src_i0[s] + (r.j - sm.src_sbase[s])];
-        const u32 nws = sm.woff[jl + 1] - sm.woff[jl];
-        const u32 wi = r.o >> 4, sh = 2 * (r.o & 15);
-        u32 x[2 * NW + 1];
+    // left shift of the payload words by nb bases (nb < 16)
+    const u32 sh = 2 * nb;
 #pragma unroll
-        for (int t = 0; t < 2 * NW + 1; ++t) x[t] = (wi + t < nws) ? __ldg(r.wp + wi + t) : 0u;
+    for (int x = 0; x < PW - 1; ++x) w[x] = __funnelshift_l(w[x + 1], w[x], sh);
+    w[PW - 1] <<= sh;
+}
+
+// address of slot j of the bin (j counts over the per-source segments in rank order)
+template <int NW>
+__device__ __forceinline__ const u32 *slot_ptr(const BinSmem<NW> &sm, const BinParams &P, u32 j, int sw)
+{
+    int s = 0;
+    while (j >= sm.src_sbase[s + 1]) ++s;
+    return P.slots[s] + (sm.src_i0[s] + (j - sm.src_sbase[s])) * (u64)sw;
+}
+
+// canonical k-mer at the current position, then advance by one k-mer
+template <int NW, int SW, bool EXT>
+__device__ __forceinline__ void next_kmer(Walk<SW> &r, const BinSmem<NW> &sm, const BinParams &P, int k, int padbits,
+                                          u32 skip, u64 (&key)[NW], u64 &val)
+{
+    constexpr int PW = SW - (EXT ? 2 : 0);
+    if (r.left == 0) {
+        const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr<NW>(sm, P, r.j, SW));
 #pragma unroll
-        for (int l = 0; l < NW; ++l) {
-            u32 hi = __funnelshift_l(x[2 * l + 1], x[2 * l], sh);
-            u32 lo = __funnelshift_l(x[2 * l + 2], x[2 * l + 1], sh);
-            r.fwd[l] = ((u64)hi << 32) | lo;
+        for (int x = 0; x < SW / 4; ++x) {
+            const uint4 v = __ldg(sp + x);
+            r.w[4 * x] = v.x; r.w[4 * x + 1] = v.y; r.w[4 * x + 2] = v.z; r.w[4 * x + 3] = v.w;
         }
-        if (padbits) r.fwd[NW - 1] &= ~0ull << padbits;
-        kmer_twin<NW>(r.fwd, k, r.rc);
-        r.fresh = false;
-    } else {
-        // roll: drop the first base, append base (o + k - 1) of the supermer
-        const u32 bo = r.o + (u32)k - 1;
-        const u64 c = (__ldg(r.wp + (bo >> 4)) >> (30 - 2 * (bo & 15))) & 3u;
-#pragma unroll
-        for (int l = 0; l < NW; ++l) {
-            r.fwd[l] <<= 2;
-            if (l + 1 < NW) r.fwd[l] |= r.fwd[l + 1] >> 62;
+        r.left = (r.w[PW - 1] & 0xFFu) - (u32)k + 1 - skip;
+        if (EXT) { r.pos = r.w[SW - 2] + skip; r.rid = r.w[SW - 1]; }
+        // start inside the slot: drop `skip` bases (only the first slot of a thread's range)
+        for (u32 t = skip; t > 0;) {
+            const u32 step = min(t, 15u);
+            shift_bases<SW, PW>(r.w, step);
+            t -= step;
         }
-        r.fwd[NW - 1] |= c << padbits;
-#pragma unroll
-        for (int l = NW - 1; l >= 0; --l) {
-            r.rc[l] >>= 2;
-            if (l > 0) r.rc[l] |= r.rc[l - 1] << 62;
-        }
-        r.rc[0] |= (3 - c) << 62;
-        if (padbits) r.rc[NW - 1] &= ~0ull << padbits;
     }
-    const bool use_rc = key_less<NW>(r.rc, r.fwd);
+    u64 fwd[NW], rc[NW];
 #pragma unroll
-    for (int l = 0; l < NW; ++l) key[l] = use_rc ? r.rc[l] : r.fwd[l];
-    if (EXT) val = r.extv + ((u64)r.o << 32);
-    ++r.o;
-    if (r.o >= r.nj) { ++r.j; r.o = 0; r.fresh = true; }
+    for (int l = 0; l < NW; ++l) fwd[l] = ((u64)r.w[2 * l] << 32) | r.w[2 * l + 1];
+    if (padbits) fwd[NW - 1] &= ~0ull << padbits;
+    kmer_twin<NW>(fwd, k, rc);
+    const bool use_rc = key_less<NW>(rc, fwd);
+#pragma unroll
+    for (int l = 0; l < NW; ++l) key[l] = use_rc ? rc[l] : fwd[l];
+    if (EXT) { val = ((u64)r.pos << 32) | r.rid; ++r.pos; }
+    shift_bases<SW, PW>(r.w, 1);
+    if (--r.left == 0) ++r.j;
 }
 
 // claim or find the slot of a k-mer and bump its counter; returns the slot and the counter word before the bump.
@@ -214,14 +214,16 @@ __device__ __forceinline__ u32 table_insert(BinSmem<NW> &sm, const u64 (&key)[NW
 }
 
 // One CTA per bin.  K <= 32 without EXTENSION needs no per-occurrence state after the insertion, so a bin of
-// any size up to 65535 occurrences (16-bit counters / offsets) is handled, supermers in chunks of BN_SCAP, as
+// any size up to 65535 occurrences (16-bit counters / offsets) is handled, slots in chunks of BN_SCAP, as
 // long as its distinct k-mers fit the table.  With EXTENSION or K > 32 every thread keeps its occurrences in
-// registers for the second pass, which limits a bin to BinCfg::CAP occurrences and BN_SCAP supermers.
+// registers for the second pass, which limits a bin to BinCfg::CAP occurrences and BN_SCAP slots.
 template <int NW, bool EXT>
 __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinParams P)
 {
     using Cfg = BinCfg<NW>;
     constexpr bool FREE = (NW == 1) && !EXT;
+    constexpr int SW = (NW == 1 ? 4 : 8) + (EXT ? 4 : 0);
+    constexpr int PW = SW - (EXT ? 2 : 0);
     extern __shared__ __align__(16) unsigned char smraw[];
     BinSmem<NW> &sm = *reinterpret_cast<BinSmem<NW> *>(smraw);
     const int tid = threadIdx.x;
@@ -239,20 +241,18 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
         const u32 lb = sm.bin;
         if (lb >= P.nbins) break;
 
-        // ---- bin descriptor: one segment of supermers per source rank
+        // ---- bin descriptor: one segment of slots per source rank
         if (tid < P.nsrc) {
             const u64 i0 = P.seg_start[tid][lb], i1 = P.seg_start[tid][lb + 1];
             sm.src_i0[tid] = i0;
             sm.src_n[tid] = (u32)min(i1 - i0, (u64)0xFFFFFFFFu);
-            sm.src_w0[tid] = P.seg_wstart[tid][lb];
-            sm.src_wdone[tid] = 0;
         }
         __syncthreads();
         if (tid == 0) {
             u64 s = 0;
             for (int i = 0; i < P.nsrc; ++i) { sm.src_sbase[i] = (u32)min(s, (u64)0xFFFFFFFFu); s += sm.src_n[i]; }
             sm.src_sbase[P.nsrc] = (u32)min(s, (u64)0xFFFFFFFFu);
-            const u64 nk = P.bin_kmers[lb];
+            const u64 nk = P.bin_kmers[lb] & ((1ull << 40) - 1);
             sm.nk = (u32)min(nk, (u64)0xFFFFFFFFu);
             sm.S = (u32)min(s, (u64)0xFFFFFFFFu);
             if (FREE) { if (nk > 65535ull || s > 65535ull) sm.bail = 1; }
@@ -269,40 +269,26 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
 
         for (u32 c0 = 0; c0 < S && !sm.bail; c0 += BN_SCAP) {
             const u32 Sc = min((u32)BN_SCAP, S - c0);
-            // ---- supermer table of the chunk: k-mer and word offsets of every supermer
-            u32 n4[BN_SPT], w4[BN_SPT], tn = 0, tw = 0;
+            // ---- k-mer offsets of the chunk's slots (block scan of len - K + 1)
+            u32 n4[BN_SPT], tn = 0;
 #pragma unroll
             for (int i = 0; i < BN_SPT; ++i) {
                 const u32 jl = tid * BN_SPT + i;
-                n4[i] = 0; w4[i] = 0;
-                if (jl < Sc) {
-                    const u32 j = c0 + jl;
-                    int s = 0;
-                    while (j >= sm.src_sbase[s + 1]) ++s;
-                    const u32 len = P.len[s][sm.src_i0[s] + (j - sm.src_sbase[s])];
-                    n4[i] = len - (u32)k + 1;
-                    w4[i] = (len + 15) >> 4;
-                    sm.ssrc[jl] = (u8)s;
-                }
-                tn += n4[i]; tw += w4[i];
+                n4[i] = 0;
+                if (jl < Sc) n4[i] = (__ldg(slot_ptr<NW>(sm, P, c0 + jl, SW) + (PW - 1)) & 0xFFu) - (u32)k + 1;
+                tn += n4[i];
             }
-            u32 en, ew, totn, totw;
-            block_scan2(tn, tw, sm.wa, sm.wb, en, ew, totn, totw);
+            u32 en, dummy_e, totn, dummy_t;
+            block_scan2(tn, 0u, sm.wa, sm.wb, en, dummy_e, totn, dummy_t);
 #pragma unroll
             for (int i = 0; i < BN_SPT; ++i) {
                 const u32 jl = tid * BN_SPT + i;
-                if (jl < Sc) { sm.koff[jl] = (u16)en; sm.woff[jl] = ew; }
-                en += n4[i]; ew += w4[i];
+                if (jl < Sc) sm.koff[jl] = (u16)en;
+                en += n4[i];
             }
             if (tid == 0) {
-                sm.koff[Sc] = (u16)totn; sm.woff[Sc] = totw;
+                sm.koff[Sc] = (u16)totn;
                 if (seen + totn > nk) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
-            }
-            __syncthreads();
-            // part of every source that lies in this chunk: [ls, le) in chunk-local supermer indices
-            if (tid < P.nsrc) {
-                const u32 ls = min(max(sm.src_sbase[tid], c0) - c0, Sc);
-                sm.src_wbase[tid] = sm.woff[ls];
             }
             __syncthreads();
             if (sm.bail) break;
@@ -311,15 +297,17 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             const u32 q = (nkc + BN_THREADS - 1) / BN_THREADS;   // occurrences per thread in this chunk
             a = tid * q; e = min(nkc, a + q);
             if (a < e) {
-                Roll<NW> r;
+                Walk<SW> r;
                 u32 jl = 0;
                 for (u32 step = BN_SCAP / 2; step >= 1; step >>= 1)
                     if (jl + step < Sc && sm.koff[jl + step] <= a) jl += step;
-                r.j = c0 + jl; r.o = a - sm.koff[jl]; r.fresh = true; r.wp = nullptr; r.nj = 0; r.extv = 0;
+                r.j = c0 + jl; r.left = 0; r.pos = 0; r.rid = 0;
+                u32 skip = a - sm.koff[jl];
                 if (FREE) {
                     for (u32 i = a; i < e; ++i) {
                         u64 key[NW], val;
-                        next_kmer<NW, EXT>(r, sm, P, k, padbits, c0, key, val);
+                        next_kmer<NW, SW, EXT>(r, sm, P, k, padbits, skip, key, val);
+                        skip = 0;
                         u32 prev;
                         table_insert<NW>(sm, key, prev);
                     }
@@ -328,7 +316,8 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
                     for (int i = 0; i < Cfg::KPT; ++i) {
                         if (a + i < e) {
                             u64 key[NW], val = 0;
-                            next_kmer<NW, EXT>(r, sm, P, k, padbits, c0, key, val);
+                            next_kmer<NW, SW, EXT>(r, sm, P, k, padbits, skip, key, val);
+                            skip = 0;
                             if (NW > 1) {
 #pragma unroll
                                 for (int l = 0; l < NW; ++l) kreg[i][l] = key[l];
@@ -343,13 +332,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
                 }
             }
             seen += nkc;
-            __syncthreads();   // the chunk's table may be overwritten by the next chunk
-            if (tid < P.nsrc) {
-                const u32 ls = min(max(sm.src_sbase[tid], c0) - c0, Sc);
-                const u32 le = min(max(sm.src_sbase[tid + 1], c0) - c0, Sc);
-                sm.src_wdone[tid] += sm.woff[le] - sm.woff[ls];
-            }
-            __syncthreads();
+            __syncthreads();   // koff may be overwritten by the next chunk
         }
         if (!sm.bail && seen != nk && tid == 0) sm.bail = 2;
         __syncthreads();
@@ -609,63 +592,54 @@ __global__ void __launch_bounds__(THREADS) k_bin_gather(BinParams P)
 }
 
 // ---- per-source segment tables of the bins a rank owns (multi-rank) ---------------------------------
-// alltot[src][0][b] = k-mers, alltot[src][1][b] = (supermers << 32 | words) of bin b as extracted by rank src
-// (all-gathered).  Block src scans its row over the owned bins [b_lo, b_lo + tg): exclusive prefixes of
-// supermers / words = where the bin starts inside the stream received from src.  meta[2*src..] = totals
-// received from src; meta[2*G + 2*p..] = (bin_start, word_start)[p * tg] of the LOCAL streams = the
-// boundaries of what this rank sends to rank p.
+// alltot[src][b] = (slots << 40 | k-mers) of bin b as extracted by rank src (all-gathered).  Block src scans
+// its row over the owned bins [b_lo, b_lo + tg): exclusive prefix of the slot counts = where the bin starts
+// inside the stream received from src.  meta[src] = slots received from src; meta[G + p] = bin_start[p * tg]
+// of the LOCAL stream = the boundaries of what this rank sends to rank p (p = 0..G).
 __global__ void __launch_bounds__(1024) k_seg_scan(const u64 *__restrict__ alltot, u32 T, u32 b_lo, u32 tg, int nranks,
-                                                    const u64 *__restrict__ local_start, const u64 *__restrict__ local_wstart,
-                                                    u64 *__restrict__ seg_start, u64 *__restrict__ seg_wstart,
+                                                    const u64 *__restrict__ local_start, u64 *__restrict__ seg_start,
                                                     u64 *__restrict__ meta)
 {
-    __shared__ u64 s_c[32], s_w[32];
-    __shared__ u64 carry_c, carry_w;
+    __shared__ u64 s_c[32];
+    __shared__ u64 carry_c;
     const int src = blockIdx.x;
-    const u64 *cw = alltot + ((size_t)src * 2 + 1) * T + b_lo;
-    u64 *os = seg_start + (size_t)src * (tg + 1), *ow = seg_wstart + (size_t)src * (tg + 1);
-    if (threadIdx.x == 0) { carry_c = 0; carry_w = 0; }
+    const u64 *row = alltot + (size_t)src * T + b_lo;
+    u64 *os = seg_start + (size_t)src * (tg + 1);
+    if (threadIdx.x == 0) carry_c = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u32 base = 0; base < tg; base += 1024) {
         const u32 b = base + threadIdx.x;
-        const u64 v = b < tg ? cw[b] : 0;
-        const u64 c = v >> 32, w = v & 0xFFFFFFFFull;
-        u64 ic = c, iw = w;
+        const u64 c = b < tg ? (row[b] >> 40) : 0;
+        u64 ic = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             u64 x = __shfl_up_sync(0xFFFFFFFFu, ic, d);
-            u64 y = __shfl_up_sync(0xFFFFFFFFu, iw, d);
-            if (lane >= d) { ic += x; iw += y; }
+            if (lane >= d) ic += x;
         }
-        if (lane == 31) { s_c[warp] = ic; s_w[warp] = iw; }
+        if (lane == 31) s_c[warp] = ic;
         __syncthreads();
         if (warp == 0) {
-            u64 x = s_c[lane], y = s_w[lane], ix = x, iy = y;
+            u64 x = s_c[lane], ix = x;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 u64 p = __shfl_up_sync(0xFFFFFFFFu, ix, d);
-                u64 q = __shfl_up_sync(0xFFFFFFFFu, iy, d);
-                if (lane >= d) { ix += p; iy += q; }
+                if (lane >= d) ix += p;
             }
-            s_c[lane] = ix - x; s_w[lane] = iy - y;
+            s_c[lane] = ix - x;
         }
         __syncthreads();
-        const u64 ec = carry_c + s_c[warp] + ic - c, ew = carry_w + s_w[warp] + iw - w;
-        if (b < tg) { os[b] = ec; ow[b] = ew; }
+        const u64 ec = carry_c + s_c[warp] + ic - c;
+        if (b < tg) os[b] = ec;
         __syncthreads();
-        if (threadIdx.x == 1023) { carry_c = ec + c; carry_w = ew + w; }
+        if (threadIdx.x == 1023) carry_c = ec + c;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        os[tg] = carry_c; ow[tg] = carry_w;
-        meta[2 * src] = carry_c; meta[2 * src + 1] = carry_w;
-        meta[2 * nranks + 2 * src] = local_start[(size_t)src * tg];
-        meta[2 * nranks + 2 * src + 1] = local_wstart[(size_t)src * tg];
-        if (src == 0) {
-            meta[2 * nranks + 2 * nranks] = local_start[(size_t)nranks * tg];
-            meta[2 * nranks + 2 * nranks + 1] = local_wstart[(size_t)nranks * tg];
-        }
+        os[tg] = carry_c;
+        meta[src] = carry_c;
+        meta[nranks + src] = local_start[(size_t)src * tg];
+        if (src == 0) meta[nranks + nranks] = local_start[(size_t)nranks * tg];
     }
 }
 
@@ -676,7 +650,7 @@ __global__ void __launch_bounds__(256) k_sum_kmers(const u64 *__restrict__ allto
     const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     u64 s = 0;
     if (b < tg) {
-        for (int src = 0; src < nranks; ++src) s += alltot[((size_t)src * 2) * T + b_lo + b];
+        for (int src = 0; src < nranks; ++src) s += alltot[(size_t)src * T + b_lo + b] & ((1ull << 40) - 1);
         bin_kmers[b] = s;
     }
 #pragma unroll
@@ -684,11 +658,10 @@ __global__ void __launch_bounds__(256) k_sum_kmers(const u64 *__restrict__ allto
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(owned_total, s);
 }
 
-cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start,
-                            const u64 *local_wstart, u64 *seg_start, u64 *seg_wstart, u64 *meta, u64 *bin_kmers,
-                            u64 *owned_total, cudaStream_t s)
+cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start, u64 *seg_start,
+                            u64 *meta, u64 *bin_kmers, u64 *owned_total, cudaStream_t s)
 {
-    k_seg_scan<<<nranks, 1024, 0, s>>>(alltot, T, b_lo, tg, nranks, local_start, local_wstart, seg_start, seg_wstart, meta);
+    k_seg_scan<<<nranks, 1024, 0, s>>>(alltot, T, b_lo, tg, nranks, local_start, seg_start, meta);
     k_sum_kmers<<<(tg + 255) / 256, 256, 0, s>>>(alltot, T, b_lo, tg, nranks, bin_kmers, owned_total);
     return cudaGetLastError();
 }

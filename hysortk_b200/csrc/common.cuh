@@ -121,6 +121,18 @@ constexpr int EX_WORDS = EX_TS / 16 + 4;       // 260 big-endian 32-bit words of
 constexpr u32 EX_INVALID = 0xFFFFFFFFu;
 constexpr u32 MAX_BINS = 1u << 26;
 
+// ---- supermer slots ---------------------------------------------------------------------------
+// A supermer is stored in one fixed-size slot of SW 32-bit words (16-byte multiples, so a slot is
+// written and read with 128-bit accesses and addressed by its index alone):
+//   words 0 .. PW-1   bases, 16 per word from the top bits; the last payload word holds 12 bases in its
+//                     upper 24 bits and the supermer length (bases) in its low 8 bits
+//   words PW, PW+1    PosInRead of the first base, ReadId (EXTENSION only)
+// K <= 32: SW = 4 (60 bases), with EXTENSION SW = 8 (92 bases); K > 32: SW = 8 (124 bases), with
+// EXTENSION SW = 12 (156 bases).  Runs longer than a slot are split into pieces that overlap by K-1.
+__host__ __device__ __forceinline__ int slot_words(int nwords, bool ext) { return (nwords == 1 ? 4 : 8) + (ext ? 4 : 0); }
+__host__ __device__ __forceinline__ int slot_payload_words(int nwords, bool ext) { return slot_words(nwords, ext) - (ext ? 2 : 0); }
+__host__ __device__ __forceinline__ int slot_max_bases(int nwords, bool ext) { return 16 * (slot_payload_words(nwords, ext) - 1) + 12; }
+
 // ---- radix geometry --------------------------------------------------------------------------
 constexpr int RS_THREADS = 384;
 constexpr int RS_IPT = 16;

@@ -146,11 +146,11 @@ struct hsk_ctx {
     // extraction
     DevBuf d_bucket, d_run_list, d_tile_hdr;   // d_bucket: see run_extract
     HostBuf h_bucket;
-    DevBuf d_len, d_words, d_ext;
+    DevBuf d_slots;
     // exchange
-    DevBuf d_alltot, d_rlen, d_rwords, d_rext, d_seg, d_lb;
+    DevBuf d_alltot, d_rslots, d_seg, d_lb;
     HostBuf h_alltot, h_meta;
-    std::vector<u64> rbase_idx, rbase_w;
+    std::vector<u64> rbase_idx;
     // batch buffers
     DevBuf d_keys[2][MAX_WORDS], d_val[2], d_rscratch, d_cscratch, d_tsum, d_tbase;
     // result arena
@@ -261,8 +261,8 @@ void hsk_destroy(hsk_ctx *c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_bucket, &c->d_len, &c->d_words,
-                    &c->d_ext, &c->d_alltot, &c->d_rlen, &c->d_rwords, &c->d_rext, &c->d_seg, &c->d_lb, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
+    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_bucket, &c->d_slots,
+                    &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
@@ -307,15 +307,17 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
     return 0;
 }
 
-// Device layout of d_bucket (u64 units): [bin_k T][bin_cw T][start T+1][wstart T+1][cursor T][run_cursor][kmers_total]
-// Host (h_meta): S, W, run cursor, local k-mer total.  With full_d2h the four per-bin arrays are also copied to
-// h_bucket (debug entry point).  d_len/d_words/d_ext receive the bin-major supermer streams.
+// Device layout of d_bucket (u64 units): [bin_tot T][start T+1][run_cursor][kmers_total][cursor T (u32)]
+// bin_tot = slots << 40 | k-mers.  Host (h_meta): S, run cursor, local k-mer total.  With full_d2h bin_tot and
+// start are also copied to h_bucket (debug entry point).  d_slots receives the bin-major supermer slots.
 static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
                        const u32 *d_read_len, u64 nreads, int readid_base, bool full_d2h)
 {
     if (choose_bins(c, nbytes)) return 1;
     const u32 T = c->tt;
     cudaStream_t s = c->stream;
+    const bool ext = c->cfg.ext != 0;
+    const int SW = slot_words(c->nwords, ext);
     ExtractParams P;
     P.packed = d_packed; P.nbytes = nbytes; P.nbytes_padded = nbytes_padded;
     P.read_off = d_read_off; P.read_len = d_read_len; P.nreads = nreads;
@@ -323,15 +325,16 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     u32 nctas = (u32)std::min<u64>(std::max<u64>(P.ntiles, 1), (u64)c->sm_count * 4);
     P.tiles_per_cta = (P.ntiles + nctas - 1) / nctas;
     P.k = c->cfg.k; P.m = c->m_eff; P.nbins = T; P.readid_base = readid_base;
+    P.slot_nmax = (u32)(slot_max_bases(c->nwords, ext) - c->cfg.k + 1);
 
-    const size_t host_u64 = 2 * (size_t)T + 2 * ((size_t)T + 1);
-    const size_t dev_u64 = host_u64 + (size_t)T + 2;
+    const size_t host_u64 = (size_t)T + ((size_t)T + 1);
+    const size_t dev_u64 = host_u64 + 2 + ((size_t)T + 1) / 2 + 1;
     CK(c->d_bucket.ensure(dev_u64 * 8));
     CK(c->h_meta.ensure(128 * 8));
     CK(c->d_tile_hdr.ensure((P.ntiles + 1) * sizeof(ulonglong2)));
-    u64 *d_kmers = c->d_bucket.as<u64>();
-    u64 *d_cw = d_kmers + T, *d_start = d_cw + T, *d_wstart = d_start + T + 1, *d_cur = d_wstart + T + 1, *d_runcur = d_cur + T,
-        *d_ktot = d_runcur + 1;
+    u64 *d_tot = c->d_bucket.as<u64>();
+    u64 *d_start = d_tot + T, *d_runcur = d_start + T + 1, *d_ktot = d_runcur + 1;
+    u32 *d_cur = reinterpret_cast<u32 *>(d_ktot + 1);
     u64 *hm = c->h_meta.as<u64>();
 
     const u64 nslots = nbytes * 4;
@@ -339,12 +342,10 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     c->begin(c->ev_extract);
     for (int attempt = 0;; ++attempt) {
         CK(c->d_run_list.ensure(run_cap * 8));
-        CK(cudaMemsetAsync(d_kmers, 0, dev_u64 * 8, s));
-        CK(launch_supermer_count(P, nctas, d_cw, d_kmers, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur,
-                                 run_cap, s));
-        CK(launch_bin_scan(d_cw, d_kmers, T, d_start, d_wstart, d_ktot, s));
+        CK(cudaMemsetAsync(d_tot, 0, dev_u64 * 8, s));
+        CK(launch_supermer_count(P, nctas, d_tot, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur, run_cap, s));
+        CK(launch_bin_scan(d_tot, T, d_start, d_ktot, s));
         CK(cudaMemcpyAsync(hm + 0, d_start + T, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(hm + 1, d_wstart + T, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(hm + 2, d_runcur, 16, cudaMemcpyDeviceToHost, s));   // run cursor, k-mer total
         CK(cudaStreamSynchronize(s));
         c->stats.n_launches += 2;
@@ -352,16 +353,14 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
         if (attempt) return fail("internal: run list overflow after resize");
         run_cap = nslots + 1024;   // pathological input (runs shorter than 3 k-mers on average): worst-case list
     }
-    const u64 S = hm[0], W = hm[1];
-    CK(c->d_len.ensure((S + 8) * sizeof(u16)));
-    CK(c->d_words.ensure((W + 8) * sizeof(u32)));
-    if (c->cfg.ext) CK(c->d_ext.ensure((S + 8) * sizeof(u64)));
-    CK(launch_supermer_scatter(P, nctas, c->cfg.ext != 0, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_cur, d_start,
-                               d_wstart, c->d_len.as<u16>(), c->d_words.as<u32>(), c->d_ext.as<u64>(), s));
+    const u64 S = hm[0];
+    CK(c->d_slots.ensure((S + 4) * (size_t)SW * 4));
+    CK(launch_supermer_scatter(P, nctas, c->nwords, ext, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_cur, d_start,
+                               c->d_slots.as<u32>(), s));
     c->end(c->ev_extract);
     c->stats.n_launches += 1;
     c->stats.n_supermers = S;
-    c->stats.supermer_bytes = S * (2 + (c->cfg.ext ? 8 : 0)) + W * 4;
+    c->stats.supermer_bytes = S * (u64)SW * 4;
     c->stats.n_kmers_local = hm[3];
     if (full_d2h) {
         CK(c->h_bucket.ensure((host_u64 + 1) * 8));
@@ -372,7 +371,7 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
 }
 
 // ---- HBM path for the bins the on-chip path left over (skewed bins): expand -> radix sort -> count ------
-struct OvfSeg { int src; u64 i0, nsup, w0, kmers; };
+struct OvfSeg { int src; u64 i0, nslots, kmers; };
 
 static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
 {
@@ -388,7 +387,7 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
         u64 n = 0, max_sup = 0;
         while (last < segs.size() && (n == 0 || n + segs[last].kmers <= cap)) {
             n += segs[last].kmers;
-            max_sup = std::max(max_sup, segs[last].nsup);
+            max_sup = std::max(max_sup, segs[last].nslots);
             ++last;
         }
         if (n > (1ull << 29) - 1)
@@ -400,8 +399,8 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
         CK(c->d_rscratch.ensure(radix_scratch_bytes(n)));
         CK(c->d_cscratch.ensure(count_scratch_bytes(n)));
         const u64 seg_tiles = (max_sup + XP_TILE - 1) / XP_TILE + 1;
-        CK(c->d_tsum.ensure(seg_tiles * sizeof(uint2)));
-        CK(c->d_tbase.ensure(seg_tiles * sizeof(ulonglong2)));
+        CK(c->d_tsum.ensure(seg_tiles * sizeof(u32)));
+        CK(c->d_tbase.ensure(seg_tiles * sizeof(u64)));
         Planes A, B;
         for (int w = 0; w < MAX_WORDS; ++w) {
             A.p[w] = w < NW ? c->d_keys[0][w].as<u64>() : nullptr;
@@ -413,15 +412,14 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
         u64 out_base = 0;
         for (size_t i = first; i < last; ++i) {
             const OvfSeg &g = segs[i];
-            if (g.nsup == 0) continue;
+            if (g.nslots == 0) continue;
             const bool local = (g.src == me);
+            const int SW = slot_words(NW, ext);
             ExpandSegment seg;
-            seg.len = (local ? c->d_len.as<u16>() : c->d_rlen.as<u16>() + c->rbase_idx[g.src]) + g.i0;
-            seg.words = (local ? c->d_words.as<u32>() : c->d_rwords.as<u32>() + c->rbase_w[g.src]) + g.w0;
-            seg.ext = ext ? ((local ? c->d_ext.as<u64>() : c->d_rext.as<u64>() + c->rbase_idx[g.src]) + g.i0) : nullptr;
-            seg.nsup = g.nsup;
+            seg.slots = (local ? c->d_slots.as<u32>() : c->d_rslots.as<u32>() + c->rbase_idx[g.src] * (u64)SW) + g.i0 * (u64)SW;
+            seg.nslots = g.nslots;
             seg.out_base = out_base;
-            CK(launch_expand(seg, c->cfg.k, NW, ext, c->d_tsum.as<uint2>(), c->d_tbase.as<ulonglong2>(), A, VA, s));
+            CK(launch_expand(seg, c->cfg.k, NW, ext, c->d_tsum.as<u32>(), c->d_tbase.as<u64>(), A, VA, s));
             c->stats.n_launches += 3;
             out_base += g.kmers;
         }
@@ -477,9 +475,10 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     if (run_extract(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base, false)) return 1;
     const u32 T = c->tt, TG = c->tg;
     const u32 b_lo = (u32)me * TG;
-    u64 *d_kmers = c->d_bucket.as<u64>();
-    u64 *d_start = d_kmers + 2 * (size_t)T, *d_wstart = d_start + T + 1;
+    u64 *d_tot = c->d_bucket.as<u64>();
+    u64 *d_start = d_tot + T;
     u64 *hm = c->h_meta.as<u64>();
+    const int SW = slot_words(NW, ext);
 
     // ---- small device state of this call:
     //      [cursor 2][owned total 1][ticket, ovf_count (u32 x2)][stage cursor 2][big_count (u32)]
@@ -496,67 +495,54 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     memset(&BP, 0, sizeof(BP));
     BP.k = c->cfg.k; BP.lower = (u32)c->cfg.lower; BP.upper = (u32)c->cfg.upper;
     BP.nbins = TG; BP.nsrc = G;
-    c->rbase_idx.assign(G, 0); c->rbase_w.assign(G, 0);
+    c->rbase_idx.assign(G, 0);
     u64 owned = 0;
 
     if (G == 1) {
-        BP.len[0] = c->d_len.as<u16>(); BP.words[0] = c->d_words.as<u32>(); BP.ext[0] = c->d_ext.as<u64>();
-        BP.seg_start[0] = d_start; BP.seg_wstart[0] = d_wstart;
-        BP.bin_kmers = d_kmers;
+        BP.slots[0] = c->d_slots.as<u32>();
+        BP.seg_start[0] = d_start;
+        BP.bin_kmers = d_tot;
         owned = c->stats.n_kmers_local;
     } else {
         // ---- stage 3: supermer all-to-all.  Bin totals of every rank -> segment tables and transfer sizes
-        const size_t meta_n = 2 * (size_t)G + 2 * ((size_t)G + 1);
-        CK(c->d_alltot.ensure((size_t)G * 2 * T * 8));
-        CK(c->d_seg.ensure(((size_t)2 * G * (TG + 1) + TG + meta_n) * 8));
-        u64 *d_seg_start = c->d_seg.as<u64>(), *d_seg_wstart = d_seg_start + (size_t)G * (TG + 1);
-        u64 *d_binkm = d_seg_wstart + (size_t)G * (TG + 1), *d_meta = d_binkm + TG;
+        const size_t meta_n = (size_t)G + ((size_t)G + 1);
+        CK(c->d_alltot.ensure((size_t)G * T * 8));
+        CK(c->d_seg.ensure(((size_t)G * (TG + 1) + TG + meta_n) * 8));
+        u64 *d_seg_start = c->d_seg.as<u64>();
+        u64 *d_binkm = d_seg_start + (size_t)G * (TG + 1), *d_meta = d_binkm + TG;
         c->begin(c->ev_exchange);
-        NK(g_nccl.AllGather(c->d_bucket.p, c->d_alltot.p, (size_t)2 * T, ncclUint64, c->comm, s));
-        CK(launch_seg_scan(c->d_alltot.as<u64>(), T, b_lo, TG, G, d_start, d_wstart, d_seg_start, d_seg_wstart, d_meta, d_binkm,
-                           d_owned, s));
+        NK(g_nccl.AllGather(d_tot, c->d_alltot.p, (size_t)T, ncclUint64, c->comm, s));
+        CK(launch_seg_scan(c->d_alltot.as<u64>(), T, b_lo, TG, G, d_start, d_seg_start, d_meta, d_binkm, d_owned, s));
         c->stats.n_launches += 2;
         CK(cudaMemcpyAsync(hm + 8, d_meta, meta_n * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(hm + 7, d_owned, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         owned = hm[7];
-        const u64 *rtot = hm + 8, *bounds = hm + 8 + 2 * (size_t)G;
-        u64 ri = 0, rw = 0;
+        const u64 *rtot = hm + 8, *bounds = hm + 8 + (size_t)G;
+        u64 ri = 0;
         for (int src = 0; src < G; ++src) {
             if (src == me) continue;
-            c->rbase_idx[src] = ri; c->rbase_w[src] = rw;
-            ri += rtot[2 * src]; rw += rtot[2 * src + 1];
+            c->rbase_idx[src] = ri;
+            ri += rtot[src];
         }
-        CK(c->d_rlen.ensure((ri + 8) * sizeof(u16)));
-        CK(c->d_rwords.ensure((rw + 8) * sizeof(u32)));
-        if (ext) CK(c->d_rext.ensure((ri + 8) * sizeof(u64)));
+        CK(c->d_rslots.ensure((ri + 4) * (size_t)SW * 4));
         NK(g_nccl.GroupStart());
         for (int peer = 0; peer < G; ++peer) {
             if (peer == me) continue;
-            const u64 si = bounds[2 * peer], sn = bounds[2 * (peer + 1)] - si;
-            const u64 sw = bounds[2 * peer + 1], swn = bounds[2 * (peer + 1) + 1] - sw;
-            const u64 rn = rtot[2 * peer], rwn = rtot[2 * peer + 1];
-            if (sn) NK(g_nccl.Send(c->d_len.as<u16>() + si, sn * 2, ncclUint8, peer, c->comm, s));
-            if (rn) NK(g_nccl.Recv(c->d_rlen.as<u16>() + c->rbase_idx[peer], rn * 2, ncclUint8, peer, c->comm, s));
-            if (swn) NK(g_nccl.Send(c->d_words.as<u32>() + sw, swn, ncclUint32, peer, c->comm, s));
-            if (rwn) NK(g_nccl.Recv(c->d_rwords.as<u32>() + c->rbase_w[peer], rwn, ncclUint32, peer, c->comm, s));
-            if (ext) {
-                if (sn) NK(g_nccl.Send(c->d_ext.as<u64>() + si, sn, ncclUint64, peer, c->comm, s));
-                if (rn) NK(g_nccl.Recv(c->d_rext.as<u64>() + c->rbase_idx[peer], rn, ncclUint64, peer, c->comm, s));
-            }
-            c->stats.bytes_sent += sn * (2 + (ext ? 8 : 0)) + swn * 4;
-            c->stats.bytes_received += rn * (2 + (ext ? 8 : 0)) + rwn * 4;
+            const u64 si = bounds[peer], sn = bounds[peer + 1] - si;
+            const u64 rn = rtot[peer];
+            if (sn) NK(g_nccl.Send(c->d_slots.as<u32>() + si * SW, sn * SW, ncclUint32, peer, c->comm, s));
+            if (rn) NK(g_nccl.Recv(c->d_rslots.as<u32>() + c->rbase_idx[peer] * SW, rn * SW, ncclUint32, peer, c->comm, s));
+            c->stats.bytes_sent += sn * SW * 4;
+            c->stats.bytes_received += rn * SW * 4;
         }
         NK(g_nccl.GroupEnd());
         c->end(c->ev_exchange);
         for (int src = 0; src < G; ++src) {
             const bool local = (src == me);
-            BP.len[src] = local ? c->d_len.as<u16>() : c->d_rlen.as<u16>() + c->rbase_idx[src];
-            BP.words[src] = local ? c->d_words.as<u32>() : c->d_rwords.as<u32>() + c->rbase_w[src];
-            BP.ext[src] = ext ? (local ? c->d_ext.as<u64>() : c->d_rext.as<u64>() + c->rbase_idx[src]) : nullptr;
+            BP.slots[src] = local ? c->d_slots.as<u32>() : c->d_rslots.as<u32>() + c->rbase_idx[src] * (u64)SW;
             // the local stream is addressed with its own (absolute) bin starts, the received ones with the scanned tables
             BP.seg_start[src] = local ? d_start + b_lo : d_seg_start + (size_t)src * (TG + 1);
-            BP.seg_wstart[src] = local ? d_wstart + b_lo : d_seg_wstart + (size_t)src * (TG + 1);
         }
         BP.bin_kmers = d_binkm;
     }
@@ -608,13 +594,12 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         std::sort(ovf.begin(), ovf.end());
         std::vector<OvfSeg> segs;
         // tables of all bins in one copy per source (only when something overflowed)
-        std::vector<u64> hs((size_t)TG + 1), hw((size_t)TG + 1), hk((size_t)TG);
+        std::vector<u64> hs((size_t)TG + 1), hk((size_t)TG);
         for (int src = 0; src < G; ++src) {
             CK(cudaMemcpy(hs.data(), BP.seg_start[src], ((size_t)TG + 1) * 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(hw.data(), BP.seg_wstart[src], ((size_t)TG + 1) * 8, cudaMemcpyDeviceToHost));
-            const u64 *kp = (G == 1) ? d_kmers : c->d_alltot.as<u64>() + ((size_t)src * 2) * T + b_lo;
+            const u64 *kp = (G == 1) ? d_tot : c->d_alltot.as<u64>() + (size_t)src * T + b_lo;
             CK(cudaMemcpy(hk.data(), kp, (size_t)TG * 8, cudaMemcpyDeviceToHost));
-            for (u32 lb : ovf) segs.push_back({src, hs[lb], hs[lb + 1] - hs[lb], hw[lb], hk[lb]});
+            for (u32 lb : ovf) segs.push_back({src, hs[lb], hs[lb + 1] - hs[lb], hk[lb] & ((1ull << 40) - 1)});
         }
         if (run_hbm_path(c, segs)) return 1;
         CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 16, cudaMemcpyDeviceToHost, s));
@@ -832,26 +817,20 @@ int hsk_debug_extract(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const 
     if (run_extract(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(), nreads,
                     readid_base, true)) return 1;
     const u32 T = c->tt;
+    const int SW = slot_words(c->nwords, c->cfg.ext != 0);
     const u64 *hb = c->h_bucket.as<u64>();
-    const u64 S = hb[2 * (size_t)T + T], W = hb[2 * (size_t)T + (T + 1) + T];
+    const u64 S = hb[(size_t)T + T];
     c->h_dbg.resize(2 * (size_t)T);
-    for (u32 b = 0; b < T; ++b) { c->h_dbg[b] = hb[T + b] >> 32; c->h_dbg[T + b] = hb[T + b] & 0xFFFFFFFFull; }
-    CK(c->h_ocnt.ensure((S + 1) * 2));
-    CK(c->h_owords.ensure((W + 1) * 4));
-    if (c->cfg.ext) CK(c->h_oocc_off.ensure((S + 1) * 8));
-    if (S) CK(cudaMemcpyAsync(c->h_ocnt.p, c->d_len.p, S * 2, cudaMemcpyDeviceToHost, c->stream));
-    if (W) CK(cudaMemcpyAsync(c->h_owords.p, c->d_words.p, W * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (c->cfg.ext && S) CK(cudaMemcpyAsync(c->h_oocc_off.p, c->d_ext.p, S * 8, cudaMemcpyDeviceToHost, c->stream));
+    for (u32 b = 0; b < T; ++b) { c->h_dbg[b] = hb[b] >> 40; c->h_dbg[T + b] = hb[b] & ((1ull << 40) - 1); }
+    CK(c->h_owords.ensure((S + 1) * (size_t)SW * 4));
+    if (S) CK(cudaMemcpyAsync(c->h_owords.p, c->d_slots.p, S * (size_t)SW * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    out->n_buckets = T;
-    out->bucket_kmers = reinterpret_cast<const uint64_t *>(hb);
-    out->bucket_count = reinterpret_cast<const uint64_t *>(c->h_dbg.data());
-    out->bucket_words = reinterpret_cast<const uint64_t *>(c->h_dbg.data() + T);
-    out->n_supermers = S;
-    out->n_words = W;
-    out->len = c->h_ocnt.as<u16>();
-    out->words = c->h_owords.as<u32>();
-    out->ext = c->cfg.ext ? c->h_oocc_off.as<uint64_t>() : nullptr;
+    out->n_bins = T;
+    out->bin_slots = reinterpret_cast<const uint64_t *>(c->h_dbg.data());
+    out->bin_kmers = reinterpret_cast<const uint64_t *>(c->h_dbg.data() + T);
+    out->n_slots = S;
+    out->slot_words = (uint32_t)SW;
+    out->slots = c->h_owords.as<uint32_t>();
     c->have_result = false;
     return 0;
 }

@@ -20,11 +20,12 @@
 //        run list (start, bin) of the tile for pass B
 //   k_bin_scan: exclusive prefix of the per-bin totals -> bin starts in the supermer streams
 //   pass B (k_supermer_scatter), per tile: re-stage the bytes, read the run list, and for every
-//     valid run claim (index, word offset) in its bin with one 64-bit atomic and write the length,
-//     optional (pos, rid) and the re-packed bases.  No hashing is repeated.
+//     valid run claim its slot(s) in the bin with one atomic and write the re-packed bases, length and
+//     optional (pos, rid).  No hashing is repeated.
 //
-// A supermer is a run of consecutive k-mers of one read with the same bin, stored as
-// len (u16 bases) + ceil(len/16) 32-bit words, 16 bases per word from the top bits.  Bins are
+// A supermer is a run of consecutive k-mers of one read with the same bin, stored in fixed-size slots
+// (common.cuh: 16 bytes for K <= 32: 60 bases + length; longer runs are split into overlapping pieces),
+// so that the scatter is one atomic + one 128-bit store per supermer.  Bins are
 // fine-grained (a few thousand k-mers each) so that a bin can later be expanded, sorted and counted
 // entirely inside one CTA's shared memory.  Where the reference splits supermers (250-base cap,
 // kmerops.cpp:1120) and how it hashes are free choices: only the multiset of k-mers per bin matters,
@@ -213,10 +214,10 @@ __device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &
 }
 
 // ---- pass A: per-bin totals + the run list of every tile ------------------------------------------
-// bin_cw[b] = (supermers << 32) | words, bin_k[b] = k-mers.  Run list entry = (start << 32) | bin for
-// valid runs only; tile_hdr[tile] = (first entry, number of entries).
-__global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, u64 *__restrict__ bin_cw,
-                                                                u64 *__restrict__ bin_k, u64 *__restrict__ run_list,
+// bin_tot[b] = (slots << 40) | k-mers.  Run list entry = (n << 48 | start << 32 | bin) for valid runs
+// only; tile_hdr[tile] = (first entry, number of entries).
+__global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, u64 *__restrict__ bin_tot,
+                                                                u64 *__restrict__ run_list,
                                                                 ulonglong2 *__restrict__ tile_hdr,
                                                                 u64 *__restrict__ run_cursor, u64 run_capacity)
 {
@@ -245,9 +246,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, 
             if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_nvalid, (u32)__popc(bal));
             wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
             if (valid) {
-                const u32 len = n + P.k - 1;
-                atomicAdd(&bin_cw[b], (1ull << 32) | (u64)((len + 15) >> 4));
-                atomicAdd(&bin_k[b], (u64)n);
+                const u32 pieces = (n + P.slot_nmax - 1) / P.slot_nmax;
+                atomicAdd(&bin_tot[b], ((u64)pieces << 40) | (u64)n);
                 // reuse pm[] as the tile's staging area for (start, bin)
                 const u32 slot = wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
                 sm.pm[slot] = b;
@@ -268,77 +268,71 @@ __global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, 
     }
 }
 
-// ---- bin scan: exclusive prefix over bins of (supermers, words) -> bin starts.  One block. ---------
-__global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_cw, const u64 *__restrict__ bin_k, u32 nbins,
-                                                    u64 *__restrict__ bin_start, u64 *__restrict__ word_start,
+// ---- bin scan: exclusive prefix over bins of the slot counts -> bin starts; k-mer total.  One block. ---
+__global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_tot, u32 nbins, u64 *__restrict__ bin_start,
                                                     u64 *__restrict__ kmers_total)
 {
-    __shared__ u64 s_c[32], s_w[32];
-    __shared__ u64 carry_c, carry_w;
+    __shared__ u64 s_c[32];
+    __shared__ u64 carry_c;
     u64 ksum = 0;
-    if (threadIdx.x == 0) { carry_c = 0; carry_w = 0; }
+    if (threadIdx.x == 0) carry_c = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PER = 4;
     for (u32 base = 0; base < nbins; base += 1024 * PER) {
-        u64 c[PER], w[PER], tc = 0, tw = 0;
+        u64 c[PER], tc = 0;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             u32 b = base + threadIdx.x * PER + i;
-            u64 v = b < nbins ? bin_cw[b] : 0;
-            if (b < nbins) ksum += bin_k[b];
-            c[i] = v >> 32; w[i] = v & 0xFFFFFFFFull;
-            tc += c[i]; tw += w[i];
+            u64 v = b < nbins ? bin_tot[b] : 0;
+            ksum += v & ((1ull << 40) - 1);
+            c[i] = v >> 40;
+            tc += c[i];
         }
-        u64 ic = tc, iw = tw;
+        u64 ic = tc;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             u64 a = __shfl_up_sync(0xFFFFFFFFu, ic, d);
-            u64 e = __shfl_up_sync(0xFFFFFFFFu, iw, d);
-            if (lane >= d) { ic += a; iw += e; }
+            if (lane >= d) ic += a;
         }
-        if (lane == 31) { s_c[warp] = ic; s_w[warp] = iw; }
+        if (lane == 31) s_c[warp] = ic;
         __syncthreads();
         if (warp == 0) {
-            u64 a = s_c[lane], e = s_w[lane];
-            u64 ia = a, ie = e;
+            u64 a = s_c[lane], ia = a;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 u64 x = __shfl_up_sync(0xFFFFFFFFu, ia, d);
-                u64 y = __shfl_up_sync(0xFFFFFFFFu, ie, d);
-                if (lane >= d) { ia += x; ie += y; }
+                if (lane >= d) ia += x;
             }
-            s_c[lane] = ia - a; s_w[lane] = ie - e;
+            s_c[lane] = ia - a;
         }
         __syncthreads();
         u64 ec = carry_c + s_c[warp] + ic - tc;
-        u64 ew = carry_w + s_w[warp] + iw - tw;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             u32 b = base + threadIdx.x * PER + i;
-            if (b < nbins) { bin_start[b] = ec; word_start[b] = ew; }
-            ec += c[i]; ew += w[i];
+            if (b < nbins) bin_start[b] = ec;
+            ec += c[i];
         }
         __syncthreads();
-        if (threadIdx.x == 1023) { carry_c = ec; carry_w = ew; }
+        if (threadIdx.x == 1023) carry_c = ec;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { bin_start[nbins] = carry_c; word_start[nbins] = carry_w; }
+    if (threadIdx.x == 0) bin_start[nbins] = carry_c;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) ksum += __shfl_xor_sync(0xFFFFFFFFu, ksum, d);
     if (lane == 0 && ksum) atomicAdd(kmers_total, ksum);
 }
 
-// ---- pass B ---------------------------------------------------------------------------------------
-template <bool EXT>
+// ---- pass B: one slot per piece of every valid run ----------------------------------------------------
+template <int SW, bool EXT>
 __global__ void __launch_bounds__(EX_THREADS) k_supermer_scatter(ExtractParams P, const u64 *__restrict__ run_list,
                                                                   const ulonglong2 *__restrict__ tile_hdr,
-                                                                  u64 *__restrict__ bin_cursor,
+                                                                  u32 *__restrict__ bin_cursor,
                                                                   const u64 *__restrict__ bin_start,
-                                                                  const u64 *__restrict__ word_start,
-                                                                  u16 *__restrict__ out_len, u32 *__restrict__ out_words,
-                                                                  u64 *__restrict__ out_ext)
+                                                                  u32 *__restrict__ out_slots)
 {
+    constexpr int PW = SW - (EXT ? 2 : 0);
     __shared__ u32 wbe[EX_WORDS];
     __shared__ u64 s_rlo, s_rhi;
     const int tid = threadIdx.x;
@@ -370,57 +364,62 @@ __global__ void __launch_bounds__(EX_THREADS) k_supermer_scatter(ExtractParams P
             const u64 e = __ldg(run_list + hdr.x + j);
             const u32 b = (u32)e;
             const u32 start = (u32)(e >> 32) & 0xFFFFu, n = (u32)(e >> 48);
-            const u32 len = n + P.k - 1;
-            const u32 nw = (len + 15) >> 4;
-            const u64 old = atomicAdd(&bin_cursor[b], (1ull << 32) | (u64)nw);
-            const u64 gi = __ldg(bin_start + b) + (old >> 32);
-            const u64 gw = __ldg(word_start + b) + (old & 0xFFFFFFFFull);
-            out_len[gi] = (u16)len;
+            const u32 pieces = (n + P.slot_nmax - 1) / P.slot_nmax;
+            u64 gs = __ldg(bin_start + b) + atomicAdd(&bin_cursor[b], pieces);
+            u32 pos0 = 0, rid = 0;
             if (EXT) {
                 const u64 p = slot0 + start;
                 const u64 r = find_read(P.read_off, s_rlo, s_rhi, p >> 2);
-                const u64 pos = p - __ldg(P.read_off + r) * 4;
-                const u32 rid = (u32)((long long)r + (long long)P.readid_base);
-                out_ext[gi] = (pos << 32) | (u64)rid;
+                pos0 = (u32)(p - __ldg(P.read_off + r) * 4);
+                rid = (u32)((long long)r + (long long)P.readid_base);
             }
-            for (u32 x = 0; x < nw; ++x) {
-                const u32 q = start + 16 * x;
-                u32 wv = __funnelshift_l(wbe[(q >> 4) + 1], wbe[q >> 4], 2 * (q & 15));
-                const u32 rem = len - 16 * x;
-                if (rem < 16) wv &= ~0u << (32 - 2 * rem);
-                out_words[gw + x] = wv;
+            for (u32 pc = 0; pc < pieces; ++pc, ++gs) {
+                const u32 ps = start + pc * P.slot_nmax;
+                const u32 np = min(P.slot_nmax, n - pc * P.slot_nmax);
+                const u32 len = np + P.k - 1;
+                u32 w[SW];
+#pragma unroll
+                for (int x = 0; x < PW; ++x) {
+                    const u32 q = ps + 16 * x;
+                    u32 wv = __funnelshift_l(wbe[(q >> 4) + 1], wbe[q >> 4], 2 * (q & 15));
+                    const int rem = (int)len - 16 * x;
+                    if (rem <= 0) wv = 0; else if (rem < 16) wv &= ~0u << (32 - 2 * rem);
+                    w[x] = wv;
+                }
+                w[PW - 1] = (w[PW - 1] & 0xFFFFFF00u) | len;
+                if (EXT) { w[SW - 2] = pos0 + pc * P.slot_nmax; w[SW - 1] = rid; }
+                uint4 *dst = reinterpret_cast<uint4 *>(out_slots + gs * SW);
+#pragma unroll
+                for (int x = 0; x < SW / 4; ++x) dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
             }
         }
         __syncthreads();
     }
 }
 
-cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_cw, u64 *bin_k, u64 *run_list,
-                                  ulonglong2 *tile_hdr, u64 *run_cursor, u64 run_capacity, cudaStream_t s)
+cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_tot, u64 *run_list, ulonglong2 *tile_hdr,
+                                  u64 *run_cursor, u64 run_capacity, cudaStream_t s)
 {
     cudaError_t e = cudaFuncSetAttribute(k_supermer_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExtractSmem));
     if (e != cudaSuccess) return e;
-    k_supermer_count<<<nctas, EX_THREADS, sizeof(ExtractSmem), s>>>(P, bin_cw, bin_k, run_list, tile_hdr, run_cursor, run_capacity);
+    k_supermer_count<<<nctas, EX_THREADS, sizeof(ExtractSmem), s>>>(P, bin_tot, run_list, tile_hdr, run_cursor, run_capacity);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_scan(const u64 *bin_cw, const u64 *bin_k, u32 nbins, u64 *bin_start, u64 *word_start, u64 *kmers_total,
-                            cudaStream_t s)
+cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *kmers_total, cudaStream_t s)
 {
-    k_bin_scan<<<1, 1024, 0, s>>>(bin_cw, bin_k, nbins, bin_start, word_start, kmers_total);
+    k_bin_scan<<<1, 1024, 0, s>>>(bin_tot, nbins, bin_start, kmers_total);
     return cudaGetLastError();
 }
 
-cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const u64 *run_list,
-                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, const u64 *bin_start,
-                                    const u64 *word_start, u16 *out_len, u32 *out_words, u64 *out_ext, cudaStream_t s)
+cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, int nwords, bool ext, const u64 *run_list,
+                                    const ulonglong2 *tile_hdr, u32 *bin_cursor, const u64 *bin_start, u32 *out_slots,
+                                    cudaStream_t s)
 {
-    if (ext)
-        k_supermer_scatter<true><<<nctas, EX_THREADS, 0, s>>>(P, run_list, tile_hdr, bin_cursor, bin_start, word_start, out_len,
-                                                              out_words, out_ext);
-    else
-        k_supermer_scatter<false><<<nctas, EX_THREADS, 0, s>>>(P, run_list, tile_hdr, bin_cursor, bin_start, word_start, out_len,
-                                                               out_words, out_ext);
+#define HSK_SC(SW_, EXT_) k_supermer_scatter<SW_, EXT_><<<nctas, EX_THREADS, 0, s>>>(P, run_list, tile_hdr, bin_cursor, bin_start, out_slots)
+    if (nwords == 1) { if (ext) HSK_SC(8, true); else HSK_SC(4, false); }
+    else { if (ext) HSK_SC(12, true); else HSK_SC(8, false); }
+#undef HSK_SC
     return cudaGetLastError();
 }
 

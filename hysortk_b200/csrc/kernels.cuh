@@ -15,35 +15,33 @@ struct ExtractParams {
     u64 ntiles, tiles_per_cta;
     int k, m;                // m already clamped to <= 32
     u32 nbins;               // all ranks' bins
+    u32 slot_nmax;           // k-mers per supermer slot: slot_max_bases - k + 1
     int readid_base;
 };
 
-// pass A: bin_cw[b] += (1 << 32 | words), bin_k[b] += k-mers per supermer; run list + tile headers for pass B
-cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_cw, u64 *bin_k, u64 *run_list,
-                                  ulonglong2 *tile_hdr, u64 *run_cursor, u64 run_capacity, cudaStream_t s);
-// bin_start / word_start: nbins+1 exclusive prefixes of the supermer / word counts
-cudaError_t launch_bin_scan(const u64 *bin_cw, const u64 *bin_k, u32 nbins, u64 *bin_start, u64 *word_start, u64 *kmers_total,
-                            cudaStream_t s);
-// pass B: bin_cursor (zeroed, nbins) hands out (index << 32 | word offset) inside every bin
-cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, bool ext, const u64 *run_list,
-                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, const u64 *bin_start,
-                                    const u64 *word_start, u16 *out_len, u32 *out_words, u64 *out_ext, cudaStream_t s);
+// pass A: bin_tot[b] += (slots << 40 | k-mers) per run; run list + tile headers for pass B
+cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_tot, u64 *run_list, ulonglong2 *tile_hdr,
+                                  u64 *run_cursor, u64 run_capacity, cudaStream_t s);
+// bin_start: nbins+1 exclusive prefix of the slot counts; *kmers_total += all k-mers
+cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *kmers_total, cudaStream_t s);
+// pass B: bin_cursor (zeroed, nbins) hands out slot indices inside every bin
+cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, int nwords, bool ext, const u64 *run_list,
+                                    const ulonglong2 *tile_hdr, u32 *bin_cursor, const u64 *bin_start, u32 *out_slots,
+                                    cudaStream_t s);
 
-// ---- stage 4: expand.cu ----------------------------------------------------------------------------
+// ---- stage 4 (HBM path): expand.cu -------------------------------------------------------------------
 constexpr int XP_THREADS = 256;
-constexpr int XP_SPT = 4;                          // supermers per thread in the scans
-constexpr int XP_TILE = XP_THREADS * XP_SPT;       // 1024 supermers per tile
+constexpr int XP_SPT = 4;                          // slots per thread in the scans
+constexpr int XP_TILE = XP_THREADS * XP_SPT;       // 1024 slots per tile
 
 struct ExpandSegment {
-    const u16 *len;          // nsup lengths
-    const u32 *words;        // packed bases of the segment
-    const u64 *ext;          // (pos << 32) | rid per supermer, or null
-    u64 nsup;
+    const u32 *slots;        // nslots supermer slots of sw words
+    u64 nslots;
     u64 out_base;            // first output k-mer index of the segment inside the batch
 };
 
-// scratch: tile_sums / tile_base hold ceil(nsup/XP_TILE) entries each
-cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext, uint2 *tile_sums, ulonglong2 *tile_base,
+// scratch: tile_sums / tile_base hold ceil(nslots/XP_TILE) entries each
+cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext, u32 *tile_sums, u64 *tile_base,
                           Planes out_keys, u64 *out_val, cudaStream_t s);
 
 // ---- stages 4+5 on chip: bins.cu ---------------------------------------------------------------------
@@ -56,12 +54,9 @@ struct BinParams {
     u32 lower, upper;
     u32 nbins;                           // owned bins, local index 0..nbins-1
     int nsrc;
-    const u16 *len[BN_MAX_SRC];          // supermer streams per source rank
-    const u32 *words[BN_MAX_SRC];
-    const u64 *ext[BN_MAX_SRC];
-    const u64 *seg_start[BN_MAX_SRC];    // nbins+1: first supermer of every bin inside the source's stream
-    const u64 *seg_wstart[BN_MAX_SRC];   // nbins+1: first word
-    const u64 *bin_kmers;                // nbins: k-mers per bin over all sources
+    const u32 *slots[BN_MAX_SRC];        // supermer slot stream per source rank
+    const u64 *seg_start[BN_MAX_SRC];    // nbins+1: first slot of every bin inside the source's stream
+    const u64 *bin_kmers;                // nbins: (slots << 40 | k-mers) per bin over all sources; low 40 bits used
     // staging area (bins in completion order, unsorted inside a bin)
     u64 *st_words; u32 *st_cnt; u32 *st_pos; int *st_rid;
     u64 *stage_cursor;                   // [0] entries, [1] occurrences claimed so far (zeroed)
@@ -80,9 +75,8 @@ int bin_capacity(int nwords, bool ext);  // k-mers per bin the on-chip path can 
 // k_bin_count + k_bin_offsets + k_bin_gather (x2)
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
 // multi-rank: segment tables of the owned bins inside the per-source streams + send/recv sizes (meta)
-cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start,
-                            const u64 *local_wstart, u64 *seg_start, u64 *seg_wstart, u64 *meta, u64 *bin_kmers,
-                            u64 *owned_total, cudaStream_t s);
+cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start, u64 *seg_start,
+                            u64 *meta, u64 *bin_kmers, u64 *owned_total, cudaStream_t s);
 
 // ---- stage 5a: radix.cu ------------------------------------------------------------------------------
 // scratch layout (u32 units): [RS_MAX_PASSES*256 bins][RS_MAX_PASSES tile counters][ntiles*256 look-back]

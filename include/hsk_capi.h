@@ -152,17 +152,18 @@ int hsk_fill_entries(hsk_ctx *ctx, void *entries, uint64_t capacity_entries);
 int hsk_debug_sort(hsk_ctx *ctx, uint64_t *const *d_keys, uint64_t *const *d_tmp, uint64_t *d_val, uint64_t *d_val_tmp,
                    uint64_t n, int32_t nwords, int32_t k);
 
-/* Extraction + bucketing only: returns the local supermer streams (host copies) so tests can check
- * that the supermers of every bucket re-expand to exactly the k-mers of the input. */
+/* Extraction + binning only: returns the local supermer slots (host copies) so tests can check that the
+ * supermers of every bin re-expand to exactly the k-mers of the input.  A slot is slot_words 32-bit words:
+ * bases 16 per word from the top bits; the last payload word carries 12 bases in its upper 24 bits and the
+ * length in bases in its low 8 bits; with ext two more words follow: PosInRead of the first base, ReadId.
+ * Payload words = slot_words - (ext ? 2 : 0). */
 typedef struct hsk_supermers {
-    uint64_t n_buckets;
-    const uint64_t *bucket_count;  /* supermers per bucket                              */
-    const uint64_t *bucket_words;  /* 32-bit words of packed bases per bucket           */
-    const uint64_t *bucket_kmers;  /* k-mers per bucket                                 */
-    uint64_t n_supermers, n_words;
-    const uint16_t *len;           /* bases per supermer, bucket-major                  */
-    const uint32_t *words;         /* packed bases: 16 per word from the top bits       */
-    const uint64_t *ext;           /* (pos << 32) | (uint32_t)rid per supermer, if ext  */
+    uint64_t n_bins;
+    const uint64_t *bin_slots;   /* slots per bin                      */
+    const uint64_t *bin_kmers;   /* k-mers per bin                     */
+    uint64_t n_slots;
+    uint32_t slot_words;
+    const uint32_t *slots;       /* n_slots * slot_words, bin-major    */
 } hsk_supermers;
 int hsk_debug_extract(hsk_ctx *ctx, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
                       int32_t readid_base, hsk_supermers *out);

@@ -16,21 +16,25 @@ def gpu_counts(ctx, rs_packed, readlens, readid_base=0):
     return c, r
 
 
+def slot_codes(sm, s):
+    """2-bit codes of the bases of slot s (payload words, 16 bases per word from the top bits)."""
+    w = sm["payload"][s].copy()
+    w[-1] &= np.uint32(0xFFFFFF00)
+    codes = np.stack([(w >> np.uint32(30 - 2 * j)) & np.uint32(3) for j in range(16)], axis=1).reshape(-1)
+    return codes[: int(sm["len"][s])].astype(np.uint8)
+
+
 def expand_supermers_cpu(sm, k):
-    """numpy re-expansion of the supermer streams returned by hsk_debug_extract: list of
-    (bucket, canonical k-mer words) for every k-mer of every supermer."""
+    """numpy re-expansion of the supermer slots returned by hsk_debug_extract: (bin, canonical k-mer words)
+    for every k-mer of every slot."""
     nw = 1 if k <= 32 else (2 if k <= 64 else 3)
-    lens = sm["len"].astype(np.int64)
-    nwords = (lens + 15) // 16
-    woff = np.concatenate([[0], np.cumsum(nwords)])
+    lens = sm["len"]
     bucket_of = np.repeat(np.arange(sm["n_buckets"]), sm["bucket_count"].astype(np.int64))
     out_b, out_w = [], []
-    words = sm["words"]
     for s in range(len(lens)):
-        w = words[woff[s]:woff[s + 1]]
-        codes = np.stack([(w >> np.uint32(30 - 2 * j)) & np.uint32(3) for j in range(16)], axis=1).reshape(-1)[: lens[s]]
-        for i in range(lens[s] - k + 1):
-            f = codes[i:i + k].astype(np.uint8)
+        codes = slot_codes(sm, s)
+        for i in range(int(lens[s]) - k + 1):
+            f = codes[i:i + k]
             r = (3 - f[::-1]).astype(np.uint8)
             c = f if tuple(f) <= tuple(r) else r
             ww = [0] * nw
@@ -47,7 +51,6 @@ def test_extract_supermers_cover_all_kmers(k, m, ext):
         sm = ctx.debug_extract(rs.packed, rs.readlens, readid_base=5)
     assert int(sm["bucket_kmers"].sum()) == rs.num_kmers(k)
     assert int(sm["bucket_count"].sum()) == len(sm["len"])
-    assert int(sm["bucket_words"].sum()) == len(sm["words"])
     b, w = expand_supermers_cpu(sm, k)
     assert len(b) == rs.num_kmers(k)
     # per bucket k-mer totals as reported
@@ -63,15 +66,11 @@ def test_extract_supermers_cover_all_kmers(k, m, ext):
     assert np.array_equal(first[inv], b)
     if ext:
         # (pos, rid) of every supermer point at its bases in the original read
-        off = rs.byte_offsets()
-        lens = sm["len"].astype(np.int64)
-        woff = np.concatenate([[0], np.cumsum((lens + 15) // 16)])
+        lens = sm["len"]
         for s in range(0, len(lens), 7):
             pos, rid = int(sm["ext"][s] >> np.uint64(32)), int(sm["ext"][s] & np.uint64(0xFFFFFFFF)) - 5
-            codes = rs.codes(rid)[pos:pos + lens[s]]
-            ww = sm["words"][woff[s]:woff[s + 1]]
-            got_codes = np.stack([(ww >> np.uint32(30 - 2 * j)) & np.uint32(3) for j in range(16)], axis=1).reshape(-1)[: lens[s]]
-            assert np.array_equal(codes, got_codes.astype(np.uint8))
+            codes = rs.codes(rid)[pos:pos + int(lens[s])]
+            assert np.array_equal(codes, slot_codes(sm, s))
 
 
 @pytest.mark.parametrize("k,n,with_val", [(31, 1, False), (31, 6143, False), (31, 6145, True), (31, 1_000_003, False),
