@@ -64,7 +64,7 @@ struct BinSmem {
     u32 cnt2[BinCfg<NW>::TS / 2];                           // two 16-bit counters per word
     u16 koff[BN_SCAP + 2];                                  // k-mer offset of every slot of the chunk
     u32 hist[BN_HCAP];
-    u64 src_i0[BN_MAX_SRC];
+    const u32 *src_ptr[BN_MAX_SRC];                         // first slot of the bin in every source stream
     u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1];
     u32 wa[BN_THREADS / 32], wb[BN_THREADS / 32];
     u64 stage_kept, stage_occ;
@@ -148,9 +148,10 @@ __device__ __forceinline__ void shift_bases(u32 (&w)[SW], u32 nb)
 template <int NW>
 __device__ __forceinline__ const u32 *slot_ptr(const BinSmem<NW> &sm, const BinParams &P, u32 j, int sw)
 {
+    if (P.nsrc == 1) return sm.src_ptr[0] + j * (u32)sw;
     int s = 0;
     while (j >= sm.src_sbase[s + 1]) ++s;
-    return P.slots[s] + (sm.src_i0[s] + (j - sm.src_sbase[s])) * (u64)sw;
+    return sm.src_ptr[s] + (j - sm.src_sbase[s]) * (u32)sw;
 }
 
 // canonical k-mer at the current position, then advance by one k-mer
@@ -188,8 +189,30 @@ __device__ __forceinline__ void next_kmer(Walk<SW> &r, const BinSmem<NW> &sm, co
     if (--r.left == 0) ++r.j;
 }
 
+// claim or find the slot of a k-mer; a full table (more distinct k-mers than slots) sets the bail flag
+template <int NW>
+__device__ __forceinline__ u32 table_probe(BinSmem<NW> &sm, const u64 (&key)[NW])
+{
+    using Cfg = BinCfg<NW>;
+    const u64 f = fingerprint<NW>(key);
+    u32 slot = (u32)((f * 0x9E3779B97F4A7C15ull) >> (64 - Cfg::TS_BITS));
+    for (int probes = 0;; ++probes) {
+        const u64 old = atomicCAS(&sm.fp[slot], BN_EMPTY, f);
+        if (old == BN_EMPTY) {
+            if (NW > 1) {
+#pragma unroll
+                for (int l = 0; l < NW; ++l) sm.kw[l][slot] = key[l];
+            }
+            break;
+        }
+        if (old == f) break;
+        if (probes >= Cfg::TS) { atomicOr(&sm.bail, 16u); break; }
+        slot = (slot + 1) & (Cfg::TS - 1);
+    }
+    return slot;
+}
+
 // claim or find the slot of a k-mer and bump its counter; returns the slot and the counter word before the bump.
-// A full table (more distinct k-mers than slots) sets the bail flag.
 template <int NW>
 __device__ __forceinline__ u32 table_insert(BinSmem<NW> &sm, const u64 (&key)[NW], u32 &prev)
 {
@@ -244,7 +267,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
         // ---- bin descriptor: one segment of slots per source rank
         if (tid < P.nsrc) {
             const u64 i0 = P.seg_start[tid][lb], i1 = P.seg_start[tid][lb + 1];
-            sm.src_i0[tid] = i0;
+            sm.src_ptr[tid] = P.slots[tid] + i0 * (u64)SW;
             sm.src_n[tid] = (u32)min(i1 - i0, (u64)0xFFFFFFFFu);
         }
         __syncthreads();
@@ -296,38 +319,48 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             const u32 nkc = totn;
             const u32 q = (nkc + BN_THREADS - 1) / BN_THREADS;   // occurrences per thread in this chunk
             a = tid * q; e = min(nkc, a + q);
-            if (a < e) {
-                Walk<SW> r;
+            const bool has = a < e;
+            Walk<SW> r;
+            r.j = 0; r.left = 0; r.pos = 0; r.rid = 0;
+            u32 skip = 0;
+            if (has) {
                 u32 jl = 0;
                 for (u32 step = BN_SCAP / 2; step >= 1; step >>= 1)
                     if (jl + step < Sc && sm.koff[jl + step] <= a) jl += step;
-                r.j = c0 + jl; r.left = 0; r.pos = 0; r.rid = 0;
-                u32 skip = a - sm.koff[jl];
-                if (FREE) {
-                    for (u32 i = a; i < e; ++i) {
+                r.j = c0 + jl;
+                skip = a - sm.koff[jl];
+            }
+            if (FREE) {
+                // every thread runs the same number of rounds so that the warp reconverges between the
+                // (divergent) probe loop and the counter update
+                for (u32 it = 0; it < q; ++it) {
+                    const bool act = has && (a + it < e);
+                    u32 slot = 0;
+                    if (act) {
                         u64 key[NW], val;
                         next_kmer<NW, SW, EXT>(r, sm, P, k, padbits, skip, key, val);
                         skip = 0;
-                        u32 prev;
-                        table_insert<NW>(sm, key, prev);
+                        slot = table_probe<NW>(sm, key);
                     }
-                } else {
+                    __syncwarp();
+                    if (act) atomicAdd(&sm.cnt2[slot >> 1], 1u << (16 * (slot & 1)));
+                }
+            } else if (has) {
 #pragma unroll
-                    for (int i = 0; i < Cfg::KPT; ++i) {
-                        if (a + i < e) {
-                            u64 key[NW], val = 0;
-                            next_kmer<NW, SW, EXT>(r, sm, P, k, padbits, skip, key, val);
-                            skip = 0;
-                            if (NW > 1) {
+                for (int i = 0; i < Cfg::KPT; ++i) {
+                    if (a + i < e) {
+                        u64 key[NW], val = 0;
+                        next_kmer<NW, SW, EXT>(r, sm, P, k, padbits, skip, key, val);
+                        skip = 0;
+                        if (NW > 1) {
 #pragma unroll
-                                for (int l = 0; l < NW; ++l) kreg[i][l] = key[l];
-                            }
-                            if (EXT) vreg[i] = val;
-                            u32 prev;
-                            const u32 slot = table_insert<NW>(sm, key, prev);
-                            slot_of[i] = (u16)slot;
-                            if (EXT) occ_idx[i] = (u16)half16(prev, slot);
+                            for (int l = 0; l < NW; ++l) kreg[i][l] = key[l];
                         }
+                        if (EXT) vreg[i] = val;
+                        u32 prev;
+                        const u32 slot = table_insert<NW>(sm, key, prev);
+                        slot_of[i] = (u16)slot;
+                        if (EXT) occ_idx[i] = (u16)half16(prev, slot);
                     }
                 }
             }
@@ -591,6 +624,176 @@ __global__ void __launch_bounds__(THREADS) k_bin_gather(BinParams P)
   }
 }
 
+// ---- the usual bins (<= 512 kept k-mers): bitonic sort held in registers -----------------------------
+// 128 threads x EPT elements (element i = tid * EPT + r).  Compare-exchange partners at distance < EPT are in
+// the same thread, at thread distance < 32 they are reached with warp shuffles, and only the last stages
+// (thread distance >= 32) go through shared memory: 3 of the 45 stages of a 512-element sort.
+constexpr int GS_THREADS = 128;
+
+template <int NW>
+struct GsSmem {
+    u64 key[NW][GS_THREADS * 4];
+    u32 cnt[GS_THREADS * 4], src[GS_THREADS * 4];
+    u32 warp[GS_THREADS / 32];
+};
+
+// block exclusive scan of one u32 per thread (GS_THREADS threads)
+__device__ __forceinline__ u32 gs_scan(u32 v, u32 *warp_tot, u32 &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    u32 off = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < GS_THREADS / 32; ++w) { if (w < warp) off += warp_tot[w]; total += warp_tot[w]; }
+    return off + inc - v;
+}
+
+template <int NW, bool EXT, int EPT>
+__device__ __forceinline__ void gather_small(const BinParams &P, GsSmem<NW> &sm, u32 lb, u32 D, u64 sk, u64 so, u64 fk, u64 fo)
+{
+    constexpr int N = GS_THREADS * EPT;
+    const int tid = threadIdx.x;
+    u64 key[EPT][NW];
+    u32 cnt[EPT], src[EPT];
+    // load my EPT consecutive entries (padding sorts last)
+    u32 mysum = 0;
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        const u32 i = tid * EPT + r;
+        if (i < D) {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) key[r][l] = P.st_words[(sk + i) * NW + l];
+            cnt[r] = P.st_cnt[sk + i];
+        } else {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) key[r][l] = ~0ull;
+            cnt[r] = 0;
+        }
+        src[r] = mysum;
+        mysum += cnt[r];
+    }
+    if (EXT) {   // occurrence start of every entry in staging order
+        u32 tot;
+        const u32 ex = gs_scan(mysum, sm.warp, tot);
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) src[r] += ex;
+    }
+
+#pragma unroll
+    for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride < EPT) {
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int pr = r ^ stride;
+                    if (pr > r) {
+                        const bool asc = (((tid * EPT + r) & size) == 0);
+                        const bool sw = asc ? key_less<NW>(key[pr], key[r]) : key_less<NW>(key[r], key[pr]);
+                        if (sw) {
+#pragma unroll
+                            for (int l = 0; l < NW; ++l) { const u64 t = key[r][l]; key[r][l] = key[pr][l]; key[pr][l] = t; }
+                            const u32 c = cnt[r]; cnt[r] = cnt[pr]; cnt[pr] = c;
+                            if (EXT) { const u32 x = src[r]; src[r] = src[pr]; src[pr] = x; }
+                        }
+                    }
+                }
+            } else {
+                const int ts = stride / EPT;   // partner thread distance
+                if (ts >= 32) {
+                    __syncthreads();
+#pragma unroll
+                    for (int r = 0; r < EPT; ++r) {
+                        const int i = tid * EPT + r;
+#pragma unroll
+                        for (int l = 0; l < NW; ++l) sm.key[l][i] = key[r][l];
+                        sm.cnt[i] = cnt[r];
+                        if (EXT) sm.src[i] = src[r];
+                    }
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int i = tid * EPT + r;
+                    u64 pk[NW];
+                    u32 pc, ps = 0;
+                    if (ts >= 32) {
+                        const int j = i ^ stride;
+#pragma unroll
+                        for (int l = 0; l < NW; ++l) pk[l] = sm.key[l][j];
+                        pc = sm.cnt[j];
+                        if (EXT) ps = sm.src[j];
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < NW; ++l) pk[l] = __shfl_xor_sync(0xFFFFFFFFu, key[r][l], ts);
+                        pc = __shfl_xor_sync(0xFFFFFFFFu, cnt[r], ts);
+                        if (EXT) ps = __shfl_xor_sync(0xFFFFFFFFu, src[r], ts);
+                    }
+                    const bool asc = ((i & size) == 0), lower = ((i & stride) == 0);
+                    const bool want_min = (lower == asc);
+                    const bool take = want_min ? key_less<NW>(pk, key[r]) : key_less<NW>(key[r], pk);
+                    if (take) {
+#pragma unroll
+                        for (int l = 0; l < NW; ++l) key[r][l] = pk[l];
+                        cnt[r] = pc;
+                        if (EXT) src[r] = ps;
+                    }
+                }
+            }
+        }
+    }
+
+    // write in sorted order; occurrence offsets = exclusive scan of the counts in sorted order
+    u32 dst[EPT], s2 = 0;
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) { dst[r] = s2; s2 += cnt[r]; }
+    if (EXT) {
+        u32 tot;
+        const u32 ex = gs_scan(s2, sm.warp, tot);
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) dst[r] += ex;
+    }
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        const u32 i = tid * EPT + r;
+        if (i < D) {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) P.out_words[(fk + i) * NW + l] = key[r][l];
+            P.out_cnt[fk + i] = cnt[r];
+            if (EXT) {
+                P.out_occ_off[fk + i] = fo + dst[r];
+                const u64 sp = so + src[r], dd = fo + dst[r];
+                for (u32 t = 0; t < cnt[r]; ++t) { P.out_pos[dd + t] = P.st_pos[sp + t]; P.out_rid[dd + t] = P.st_rid[sp + t]; }
+            }
+        }
+    }
+    (void)lb;
+}
+
+template <int NW, bool EXT>
+__global__ void __launch_bounds__(GS_THREADS) k_bin_gather_small(BinParams P)
+{
+    __shared__ GsSmem<NW> sm;
+    const u32 lb = blockIdx.x;
+    const u64 sk = P.bin_rec[4 * (size_t)lb + 0];
+    const u32 D = (u32)P.bin_rec[4 * (size_t)lb + 1];
+    const u64 so = P.bin_rec[4 * (size_t)lb + 2];
+    if (D == 0 || D > (u32)(GS_THREADS * 4)) return;
+    const u64 fk = P.fin[2 * (size_t)lb], fo = P.fin[2 * (size_t)lb + 1];
+    if (D <= GS_THREADS) gather_small<NW, EXT, 1>(P, sm, lb, D, sk, so, fk, fo);
+    else if (D <= 2 * GS_THREADS) gather_small<NW, EXT, 2>(P, sm, lb, D, sk, so, fk, fo);
+    else gather_small<NW, EXT, 4>(P, sm, lb, D, sk, so, fk, fo);
+}
+
 // ---- per-source segment tables of the bins a rank owns (multi-rank) ---------------------------------
 // alltot[src][b] = (slots << 40 | k-mers) of bin b as extracted by rank src (all-gathered).  Block src scans
 // its row over the owned bins [b_lo, b_lo + tg): exclusive prefix of the slot counts = where the bin starts
@@ -666,7 +869,7 @@ cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nran
     return cudaGetLastError();
 }
 
-constexpr int GS_CAP = 512, GS_THREADS = 128;      // gather: the usual bins, one CTA each
+constexpr int GS_CAP = GS_THREADS * 4;             // gather: the usual bins (register bitonic), one CTA each
 constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers (up to the bin capacity)
 
 template <int NW, bool EXT>
@@ -686,10 +889,8 @@ static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t 
     k_bin_offsets<<<1, 1024, 0, s>>>(P.bin_rec, P.nbins, P.fin, P.cursor, (u32)GS_CAP, P.big_list, P.big_count);
     // gather + sort: a small-footprint launch for the usual bins, a large one for bins with many kept k-mers
     const size_t per_entry = (size_t)8 * NW + 8;
-    const size_t smem_s = per_entry * GS_CAP, smem_l = per_entry * GL_CAP;
-    e = cudaFuncSetAttribute(k_bin_gather<NW, EXT, GS_CAP, GS_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
-    if (e != cudaSuccess) return e;
-    k_bin_gather<NW, EXT, GS_CAP, GS_THREADS, false><<<P.nbins, GS_THREADS, smem_s, s>>>(P);
+    const size_t smem_l = per_entry * GL_CAP;
+    k_bin_gather_small<NW, EXT><<<P.nbins, GS_THREADS, 0, s>>>(P);
     e = cudaFuncSetAttribute(k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
     if (e != cudaSuccess) return e;
     k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true><<<sm_count, GL_THREADS, smem_l, s>>>(P);

@@ -92,9 +92,8 @@ __host__ __device__ __forceinline__ u32 mmer_hash(u64 x)
     u32 lo = (u32)x, hi = (u32)(x >> 32);
     u32 h = lo * 0x9E3779B1u;
     h ^= (hi + 0x7F4A7C15u) * 0x85EBCA77u;
-    h ^= h >> 16; h *= 0x85EBCA6Bu;
-    h ^= h >> 13; h *= 0xC2B2AE35u;
-    h ^= h >> 16;
+    h ^= h >> 15; h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
     return h;
 }
 

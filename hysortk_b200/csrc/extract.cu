@@ -39,7 +39,7 @@ struct ExtractSmem {
     u32 wbe[EX_WORDS];                 // bases of the tile, 16 per word, first base in the top bits
     u32 hs[EX_TS + EX_TS / 32 + 8];    // m-mer hashes, then in-place suffix minima (1 pad word per 32)
     u32 pm[EX_TS + EX_TS / 32 + 8];    // prefix minima inside blocks of w
-    u32 st[EX_TSK];                    // per k-mer slot: bin or EX_INVALID
+    u32 st[EX_TSK];                    // per k-mer slot: minimizer hash | 1, or 0 (no k-mer starts here)
     u16 runs[EX_TSK + 8];              // compacted run starts (+ sentinel)
     u32 bm[EX_TS / 32];                // run-boundary bitmap
     u32 woff[EX_TS / 32 + 1];          // exclusive popcount prefix of bm
@@ -167,8 +167,10 @@ __device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &
         for (int j = 0; j < EX_R; ++j) {
             int q = j * EX_THREADS + tid;
             if (q < EX_TSK) {
-                u32 st = EX_INVALID;
-                if ((sm.vm[q >> 4] >> (q & 15)) & 1) st = hash_bucket(min(sm.hs[hx(q)], sm.pm[hx(q + w - 1)]), P.nbins);
+                // state of the slot: its minimizer hash (low bit forced to 1), or 0 when no k-mer starts here.
+                // Runs are maximal stretches of equal state; the bin is derived from the state once per run.
+                u32 st = 0;
+                if ((sm.vm[q >> 4] >> (q & 15)) & 1) st = min(sm.hs[hx(q)], sm.pm[hx(q + w - 1)]) | 1u;
                 sm.st[q] = st;
             }
         }
@@ -237,8 +239,9 @@ __global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, 
             u32 start = 0, b = 0, n = 0;
             if (j < nruns) {
                 start = sm.runs[j];
-                b = sm.st[start];
-                valid = (b != EX_INVALID);
+                const u32 st = sm.st[start];
+                valid = (st != 0);
+                b = hash_bucket(st, P.nbins);
                 n = sm.runs[j + 1] - start;
             }
             const u32 bal = __ballot_sync(0xFFFFFFFFu, valid);
