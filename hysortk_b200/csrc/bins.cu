@@ -61,7 +61,7 @@ template <int NW>
 struct BinSmem {
     u64 fp[BinCfg<NW>::TS];                                 // CAS key: the k-mer (NW == 1) or its fingerprint
     u64 kw[NW > 1 ? NW : 1][NW > 1 ? BinCfg<NW>::TS : 1];   // full key words (NW > 1)
-    u32 cnt2[BinCfg<NW>::TS / 2];                           // two 16-bit counters per word
+    u32 cnt[BinCfg<NW>::TS];                                // occurrences per slot; later: occurrence offset of the slot
     u16 koff[BN_SCAP + 2];                                  // k-mer offset of every slot of the chunk
     u32 hist[BN_HCAP];
     const u32 *src_ptr[BN_MAX_SRC];                         // first slot of the bin in every source stream
@@ -122,7 +122,6 @@ __device__ __forceinline__ u64 fingerprint(const u64 (&w)[NW])
     return h == BN_EMPTY ? 0x5851F42D4C957F2Dull : h;
 }
 
-__device__ __forceinline__ u32 half16(u32 word, u32 slot) { return (word >> (16 * (slot & 1))) & 0xFFFFu; }
 
 // expansion state of one thread: the slot it is in (SW words in registers, shifted so that the current
 // k-mer starts at the top), the k-mers left in the slot, and the position of the current k-mer
@@ -232,7 +231,7 @@ __device__ __forceinline__ u32 table_insert(BinSmem<NW> &sm, const u64 (&key)[NW
         if (probes >= Cfg::TS) { atomicOr(&sm.bail, 16u); prev = 0; return slot; }
         slot = (slot + 1) & (Cfg::TS - 1);
     }
-    prev = atomicAdd(&sm.cnt2[slot >> 1], 1u << (16 * (slot & 1)));
+    prev = atomicAdd(&sm.cnt[slot], 1u);
     return slot;
 }
 
@@ -259,7 +258,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
         __syncthreads();   // end of the previous bin: shared memory is free again
         if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; }
         for (int i = tid; i < Cfg::TS; i += BN_THREADS) sm.fp[i] = BN_EMPTY;
-        for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) sm.cnt2[i] = 0;
+        for (int i = tid; i < Cfg::TS; i += BN_THREADS) sm.cnt[i] = 0;
         __syncthreads();
         const u32 lb = sm.bin;
         if (lb >= P.nbins) break;
@@ -343,7 +342,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
                         slot = table_probe<NW>(sm, key);
                     }
                     __syncwarp();
-                    if (act) atomicAdd(&sm.cnt2[slot >> 1], 1u << (16 * (slot & 1)));
+                    if (act) atomicAdd(&sm.cnt[slot], 1u);
                 }
             } else if (has) {
 #pragma unroll
@@ -360,7 +359,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
                         u32 prev;
                         const u32 slot = table_insert<NW>(sm, key, prev);
                         slot_of[i] = (u16)slot;
-                        if (EXT) occ_idx[i] = (u16)half16(prev, slot);
+                        if (EXT) occ_idx[i] = (u16)prev;
                     }
                 }
             }
@@ -401,7 +400,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
 #pragma unroll
         for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
             const u32 slot = tid * Cfg::SLOTS_PT + i;
-            const u32 c = half16(sm.cnt2[slot >> 1], slot);
+            const u32 c = sm.cnt[slot];
             if (c >= P.lower && c <= P.upper) { keepmask |= 1u << i; ++kept; occ += c; }
         }
         u32 ek, eo, tk, to;
@@ -420,9 +419,8 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
 #pragma unroll
             for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
                 const u32 slot = tid * Cfg::SLOTS_PT + i;
-                const u32 word = sm.cnt2[slot >> 1];
-                const u32 c = half16(word, slot);
-                u32 mark = 0xFFFFu;   // "not kept" for the occurrence pass
+                const u32 c = sm.cnt[slot];
+                u32 mark = 0xFFFFFFFFu;   // "not kept" for the occurrence pass
                 if ((keepmask >> i) & 1) {
                     if (NW == 1) P.st_words[g] = sm.fp[slot];
                     else {
@@ -435,10 +433,7 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
                     lo += c;
                     ++g;
                 }
-                if (EXT) {   // both halves of a word belong to this thread (SLOTS_PT is even)
-                    const u32 sh = 16 * (slot & 1);
-                    sm.cnt2[slot >> 1] = (word & ~(0xFFFFu << sh)) | (mark << sh);
-                }
+                if (EXT) sm.cnt[slot] = mark;
             }
         }
         if (EXT) {
@@ -449,8 +444,8 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             for (int i = 0; i < Cfg::KPT; ++i) {
                 if (a + i < e) {
                     const u32 slot = slot_of[i];
-                    const u32 off = half16(sm.cnt2[slot >> 1], slot);
-                    if (off != 0xFFFFu) {
+                    const u32 off = sm.cnt[slot];
+                    if (off != 0xFFFFFFFFu) {
                         const u64 p = so + off + occ_idx[i];
                         P.st_pos[p] = (u32)(vreg[i] >> 32);
                         P.st_rid[p] = (int)(u32)vreg[i];

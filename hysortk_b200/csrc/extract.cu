@@ -39,7 +39,6 @@ struct ExtractSmem {
     u32 wbe[EX_WORDS];                 // bases of the tile, 16 per word, first base in the top bits
     u32 hs[EX_TS + EX_TS / 32 + 8];    // m-mer hashes, then in-place suffix minima (1 pad word per 32)
     u32 pm[EX_TS + EX_TS / 32 + 8];    // prefix minima inside blocks of w
-    u32 st[EX_TSK];                    // per k-mer slot: minimizer hash | 1, or 0 (no k-mer starts here)
     u16 runs[EX_TSK + 8];              // compacted run starts (+ sentinel)
     u32 bm[EX_TS / 32];                // run-boundary bitmap
     u32 woff[EX_TS / 32 + 1];          // exclusive popcount prefix of bm
@@ -50,6 +49,15 @@ struct ExtractSmem {
 };
 
 __device__ __forceinline__ int hx(int q) { return q + (q >> 5); }
+
+// state of a k-mer slot once the block-wise minima are in place: its minimizer hash (low bit forced to 1),
+// or 0 when no k-mer starts there.  Runs are maximal stretches of equal state; the bin is derived from the
+// state once per run.
+__device__ __forceinline__ u32 slot_state(const ExtractSmem &sm, int q, int w)
+{
+    if (!((sm.vm[q >> 4] >> (q & 15)) & 1)) return 0u;
+    return min(sm.hs[hx(q)], sm.pm[hx(q + w - 1)]) | 1u;
+}
 
 // largest r in [lo, hi] with off[r] <= byte (off is non-decreasing; caller guarantees off[lo] <= byte)
 __device__ __forceinline__ u64 find_read(const u64 *__restrict__ off, u64 lo, u64 hi, u64 byte)
@@ -162,29 +170,22 @@ __device__ __forceinline__ void tile_runs(ExtractSmem &sm, const ExtractParams &
             run = 0xFFFFFFFFu;
             for (int q = e - 1; q >= s; --q) { run = min(run, sm.hs[hx(q)]); sm.hs[hx(q)] = run; }
         }
-        __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < EX_R; ++j) {
-            int q = j * EX_THREADS + tid;
-            if (q < EX_TSK) {
-                // state of the slot: its minimizer hash (low bit forced to 1), or 0 when no k-mer starts here.
-                // Runs are maximal stretches of equal state; the bin is derived from the state once per run.
-                u32 st = 0;
-                if ((sm.vm[q >> 4] >> (q & 15)) & 1) st = min(sm.hs[hx(q)], sm.pm[hx(q + w - 1)]) | 1u;
-                sm.st[q] = st;
-            }
-        }
     }
     __syncthreads();
 
-    // ---- D: run boundaries -> bitmap -> compacted run starts
+    // ---- D: run boundaries (state change / tile edge) -> bitmap -> compacted run starts
+    {
+        const int w = P.k - P.m + 1;
 #pragma unroll 4
-    for (int j = 0; j < EX_R; ++j) {
-        int q = j * EX_THREADS + tid;
-        bool b = false;
-        if (q < EX_TSK) b = (q == 0) || (sm.st[q] != sm.st[q - 1]);
-        u32 bal = __ballot_sync(0xFFFFFFFFu, b);
-        if (lane == 0) sm.bm[j * (EX_THREADS / 32) + warp] = bal;
+        for (int j = 0; j < EX_R; ++j) {
+            const int q = j * EX_THREADS + tid;
+            const u32 st = (q < EX_TSK) ? slot_state(sm, q, w) : 0u;
+            u32 prev = __shfl_up_sync(0xFFFFFFFFu, st, 1);
+            if (lane == 0 && q > 0 && q < EX_TSK) prev = slot_state(sm, q - 1, w);
+            const bool b = (q < EX_TSK) && (q == 0 || st != prev);
+            const u32 bal = __ballot_sync(0xFFFFFFFFu, b);
+            if (lane == 0) sm.bm[j * (EX_THREADS / 32) + warp] = bal;
+        }
     }
     __syncthreads();
     if (warp == 0) {
@@ -225,48 +226,55 @@ __global__ void __launch_bounds__(EX_THREADS) k_supermer_count(ExtractParams P, 
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     ExtractSmem &sm = *reinterpret_cast<ExtractSmem *>(smraw);
-    __shared__ u32 s_nvalid;
+    __shared__ u32 s_nvalid, s_claim;
+    if (threadIdx.x == 0) { s_nvalid = 0; s_claim = 0; }
     const u64 t0 = (u64)blockIdx.x * P.tiles_per_cta;
     const u64 t1 = min(t0 + P.tiles_per_cta, P.ntiles);
     for (u64 tile = t0; tile < t1; ++tile) {
-        if (threadIdx.x == 0) s_nvalid = 0;
         tile_runs(sm, P, tile);
         const u32 nruns = sm.nruns;
-        // compact the valid runs of the tile: warp-aggregated claim inside the tile
-        for (u32 base = 0; base < nruns; base += EX_THREADS) {
-            const u32 j = base + threadIdx.x;
-            bool valid = false;
-            u32 start = 0, b = 0, n = 0;
-            if (j < nruns) {
-                start = sm.runs[j];
-                const u32 st = sm.st[start];
-                valid = (st != 0);
-                b = hash_bucket(st, P.nbins);
-                n = sm.runs[j + 1] - start;
-            }
-            const u32 bal = __ballot_sync(0xFFFFFFFFu, valid);
-            u32 wbase = 0;
-            if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_nvalid, (u32)__popc(bal));
-            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-            if (valid) {
-                const u32 pieces = (n + P.slot_nmax - 1) / P.slot_nmax;
-                atomicAdd(&bin_tot[b], ((u64)pieces << 40) | (u64)n);
-                // reuse pm[] as the tile's staging area for (start, bin)
-                const u32 slot = wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
-                sm.pm[slot] = b;
-                sm.hs[slot] = start | (n << 16);
-            }
+        const int w = P.k - P.m + 1;
+        // pass 1 over the runs: number of valid runs of the tile -> its place in the global run list
+        {
+            u32 cntv = 0;
+            for (u32 j = threadIdx.x; j < nruns; j += EX_THREADS) cntv += (slot_state(sm, sm.runs[j], w) != 0) ? 1u : 0u;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) cntv += __shfl_xor_sync(0xFFFFFFFFu, cntv, d);
+            if ((threadIdx.x & 31) == 0 && cntv) atomicAdd(&s_nvalid, cntv);
         }
         __syncthreads();
         const u32 nv = s_nvalid;
         if (threadIdx.x == 0) {
             sm.run_base = atomicAdd(run_cursor, (u64)nv);
             tile_hdr[tile] = make_ulonglong2(sm.run_base, (u64)nv);
+            s_nvalid = 0; s_claim = 0;
         }
         __syncthreads();
         const u64 rb = sm.run_base;
-        if (rb + nv <= run_capacity)   // otherwise the host sees run_cursor > capacity and retries with a larger list
-            for (u32 j = threadIdx.x; j < nv; j += EX_THREADS) run_list[rb + j] = ((u64)sm.hs[j] << 32) | sm.pm[j];
+        const bool fits = (rb + nv <= run_capacity);   // otherwise the host sees run_cursor > capacity and retries
+        // pass 2: per-bin totals and the run list entries (order inside a tile is irrelevant)
+        for (u32 base = 0; base < nruns; base += EX_THREADS) {
+            const u32 j = base + threadIdx.x;
+            bool valid = false;
+            u32 start = 0, st = 0, n = 0;
+            if (j < nruns) {
+                start = sm.runs[j];
+                st = slot_state(sm, start, w);
+                valid = (st != 0);
+                n = sm.runs[j + 1] - start;
+            }
+            const u32 bal = __ballot_sync(0xFFFFFFFFu, valid);
+            u32 wbase = 0;
+            if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_claim, (u32)__popc(bal));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (valid) {
+                const u32 b = hash_bucket(st, P.nbins);
+                const u32 pieces = (n + P.slot_nmax - 1) / P.slot_nmax;
+                atomicAdd(&bin_tot[b], ((u64)pieces << 40) | (u64)n);
+                const u32 slot = wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
+                if (fits) run_list[rb + slot] = ((u64)(start | (n << 16)) << 32) | b;
+            }
+        }
         __syncthreads();
     }
 }
