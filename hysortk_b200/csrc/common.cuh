@@ -108,16 +108,18 @@ __host__ __device__ __forceinline__ u32 hash_bucket(u32 h, u32 nb)
 }
 
 // ---- extraction geometry ---------------------------------------------------------------------
-// A tile covers EX_TSK k-mer start slots of the flat slot space (slot = 2 bits of the packed
-// buffer, padding slots included) and computes EX_TS m-mer hashes (halo for the minimizer window).
-constexpr int EX_THREADS = 256;
-constexpr int EX_R = 16;                       // consecutive slots per thread
-constexpr int EX_TS = EX_THREADS * EX_R;       // 4096 hash slots per tile
-constexpr int EX_HALO = 128;                   // >= K - M (window - 1), multiple of 64
-constexpr int EX_TSK = EX_TS - EX_HALO;        // 3968 k-mer slots per tile (992 bytes, 16-byte multiple)
-constexpr int EX_TILE_BYTES = EX_TSK / 4;      // 992
-constexpr int EX_WORDS = EX_TS / 16 + 4;       // 260 big-endian 32-bit words of bases staged per tile
-constexpr u32 EX_INVALID = 0xFFFFFFFFu;
+// The flat slot space (slot = 2 bits of the packed buffer, padding slots included) is cut into warp tiles:
+// every lane owns XT_R consecutive slots; the last xt_halo_lanes(w) lanes of a warp only supply m-mer hashes
+// for the minimizer windows (w = K - M + 1 hashes per k-mer) of the lanes before them.
+constexpr int XT_R = 16;                       // slots per lane (= bases per 32-bit word of packed input)
+constexpr int XT_WARPS = 8;                    // warps per CTA
+constexpr int XT_THREADS = XT_WARPS * 32;
+constexpr int XT_CTAS_PER_SM = 5;              // register budget of the extraction kernels: 40 warps per SM
+constexpr int XT_WMAX = 64;                    // widest minimizer window
+constexpr int XT_STAGE_WORDS = 40;             // words of bases a scatter warp stages: 32 + ceil((K_max - 1) / 16) + 1
+__host__ __device__ constexpr int xt_halo_lanes(int w) { return (w + 14) >> 4; }
+__host__ __device__ constexpr int xt_out_lanes(int w) { return 32 - xt_halo_lanes(w); }
+__host__ __device__ constexpr int xt_out_slots(int w) { return xt_out_lanes(w) * XT_R; }
 constexpr u32 MAX_BINS = 1u << 26;
 
 // ---- supermer slots ---------------------------------------------------------------------------

@@ -144,7 +144,7 @@ struct hsk_ctx {
     DevBuf d_packed, d_read_off, d_read_len;
     HostBuf h_read_off, h_read_len;
     // extraction
-    DevBuf d_bucket, d_run_list, d_tile_hdr;   // d_bucket: see run_extract
+    DevBuf d_bucket, d_run_list, d_tile_hdr, d_tile_read;   // d_bucket: see run_extract
     HostBuf h_bucket;
     DevBuf d_slots;
     // exchange
@@ -229,7 +229,7 @@ int hsk_create(hsk_ctx **out, const hsk_config *cfg)
     c->cfg.nccl_id = nullptr;
     c->nwords = nwords_for_k(cfg->k);
     c->m_eff = std::min(cfg->m, 32);
-    if (cfg->k - c->m_eff > EX_HALO - 1) c->m_eff = cfg->k - (EX_HALO - 1);
+    if (cfg->k - c->m_eff + 1 > XT_WMAX) c->m_eff = cfg->k + 1 - XT_WMAX;   // window of at most XT_WMAX m-mers
     c->sm_count = prop.multiProcessorCount;
     if (cfg->buckets_per_rank > 0 && (u64)cfg->buckets_per_rank * cfg->nranks > MAX_BINS) {
         delete c;
@@ -261,7 +261,7 @@ void hsk_destroy(hsk_ctx *c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_bucket, &c->d_slots,
+    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bucket, &c->d_slots,
                     &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
@@ -307,7 +307,7 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
     return 0;
 }
 
-// Device layout of d_bucket (u64 units): [bin_tot T][start T+1][run_cursor][kmers_total][cursor T (u32)]
+// Device layout of d_bucket (u64 units): [bin_tot T][start T+1][run_cursor][kmers_total][cursor T]
 // bin_tot = slots << 40 | k-mers.  Host (h_meta): S, run cursor, local k-mer total.  With full_d2h bin_tot and
 // start are also copied to h_bucket (debug entry point).  d_slots receives the bin-major supermer slots.
 static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
@@ -318,33 +318,41 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     cudaStream_t s = c->stream;
     const bool ext = c->cfg.ext != 0;
     const int SW = slot_words(c->nwords, ext);
+    const int w = c->cfg.k - c->m_eff + 1;
     ExtractParams P;
     P.packed = d_packed; P.nbytes = nbytes; P.nbytes_padded = nbytes_padded;
     P.read_off = d_read_off; P.read_len = d_read_len; P.nreads = nreads;
-    P.ntiles = (nbytes + EX_TILE_BYTES - 1) / EX_TILE_BYTES;
-    u32 nctas = (u32)std::min<u64>(std::max<u64>(P.ntiles, 1), (u64)c->sm_count * 4);
-    P.tiles_per_cta = (P.ntiles + nctas - 1) / nctas;
+    P.out_slots = (u32)xt_out_slots(w);
+    const u64 nslots = nbytes * 4;
+    P.ntiles = (nslots + P.out_slots - 1) / P.out_slots;
+    const u32 nctas = extract_grid(w, c->sm_count);
+    const u64 nwarps = (u64)nctas * XT_WARPS;
+    P.tiles_per_warp = (u32)((P.ntiles + nwarps - 1) / nwarps);
     P.k = c->cfg.k; P.m = c->m_eff; P.nbins = T; P.readid_base = readid_base;
     P.slot_nmax = (u32)(slot_max_bases(c->nwords, ext) - c->cfg.k + 1);
+    P.slot_ninv = (u32)(((1ull << 32) + P.slot_nmax - 1) / P.slot_nmax);
 
     const size_t host_u64 = (size_t)T + ((size_t)T + 1);
-    const size_t dev_u64 = host_u64 + 2 + ((size_t)T + 1) / 2 + 1;
+    const size_t dev_u64 = host_u64 + 2 + (size_t)T;
     CK(c->d_bucket.ensure(dev_u64 * 8));
     CK(c->h_meta.ensure(128 * 8));
     CK(c->d_tile_hdr.ensure((P.ntiles + 1) * sizeof(ulonglong2)));
+    CK(c->d_tile_read.ensure((P.ntiles + 2) * sizeof(u32)));
+    P.tile_read = c->d_tile_read.as<u32>();
     u64 *d_tot = c->d_bucket.as<u64>();
     u64 *d_start = d_tot + T, *d_runcur = d_start + T + 1, *d_ktot = d_runcur + 1;
-    u32 *d_cur = reinterpret_cast<u32 *>(d_ktot + 1);
+    u64 *d_cur = d_ktot + 1;
     u64 *hm = c->h_meta.as<u64>();
 
-    const u64 nslots = nbytes * 4;
     u64 run_cap = nslots / 3 + 1024;
     c->begin(c->ev_extract);
+    CK(launch_tile_reads(P, c->d_tile_read.as<u32>(), s));
+    c->stats.n_launches += 1;
     for (int attempt = 0;; ++attempt) {
         CK(c->d_run_list.ensure(run_cap * 8));
-        CK(cudaMemsetAsync(d_tot, 0, dev_u64 * 8, s));
-        CK(launch_supermer_count(P, nctas, d_tot, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur, run_cap, s));
-        CK(launch_bin_scan(d_tot, T, d_start, d_ktot, s));
+        CK(cudaMemsetAsync(d_tot, 0, (host_u64 + 2) * 8, s));
+        if (P.ntiles) CK(launch_supermer_count(P, nctas, d_tot, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur, run_cap, s));
+        CK(launch_bin_scan(d_tot, T, d_start, d_cur, d_ktot, s));
         CK(cudaMemcpyAsync(hm + 0, d_start + T, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(hm + 2, d_runcur, 16, cudaMemcpyDeviceToHost, s));   // run cursor, k-mer total
         CK(cudaStreamSynchronize(s));
@@ -355,8 +363,8 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     }
     const u64 S = hm[0];
     CK(c->d_slots.ensure((S + 4) * (size_t)SW * 4));
-    CK(launch_supermer_scatter(P, nctas, c->nwords, ext, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_cur, d_start,
-                               c->d_slots.as<u32>(), s));
+    if (P.ntiles) CK(launch_supermer_scatter(P, nctas, c->nwords, ext, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_cur,
+                                             c->d_slots.as<u32>(), s));
     c->end(c->ev_extract);
     c->stats.n_launches += 1;
     c->stats.n_supermers = S;

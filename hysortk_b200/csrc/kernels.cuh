@@ -12,22 +12,29 @@ struct ExtractParams {
     const u64 *read_off;     // nreads+1 byte offsets (read_off[nreads] = nbytes)
     const u32 *read_len;     // nreads lengths in bases
     u64 nreads;
-    u64 ntiles, tiles_per_cta;
-    int k, m;                // m already clamped to <= 32
+    u64 ntiles;              // warp tiles of out_slots k-mer start slots each
+    u32 tiles_per_warp;
+    u32 out_slots;           // xt_out_slots(k - m + 1)
+    const u32 *tile_read;    // ntiles+1: read holding the first byte of every tile (k_tile_reads)
+    int k, m;                // m already clamped (m <= 32, k - m + 1 <= XT_WMAX)
     u32 nbins;               // all ranks' bins
     u32 slot_nmax;           // k-mers per supermer slot: slot_max_bases - k + 1
+    u32 slot_ninv;           // ceil(2^32 / slot_nmax)
     int readid_base;
 };
 
+// grid of the two extraction passes (persistent warps, contiguous tile ranges)
+u32 extract_grid(int w, int sm_count);
+// tile_read[t] = read holding byte t * out_slots / 4 (t = 0..ntiles)
+cudaError_t launch_tile_reads(const ExtractParams &P, u32 *tile_read, cudaStream_t s);
 // pass A: bin_tot[b] += (slots << 40 | k-mers) per run; run list + tile headers for pass B
 cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_tot, u64 *run_list, ulonglong2 *tile_hdr,
                                   u64 *run_cursor, u64 run_capacity, cudaStream_t s);
-// bin_start: nbins+1 exclusive prefix of the slot counts; *kmers_total += all k-mers
-cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *kmers_total, cudaStream_t s);
-// pass B: bin_cursor (zeroed, nbins) hands out slot indices inside every bin
+// bin_start: nbins+1 exclusive prefix of the slot counts, bin_cursor[b] = bin_start[b]; *kmers_total += all k-mers
+cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *bin_cursor, u64 *kmers_total, cudaStream_t s);
+// pass B: bin_cursor hands out absolute slot indices
 cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, int nwords, bool ext, const u64 *run_list,
-                                    const ulonglong2 *tile_hdr, u32 *bin_cursor, const u64 *bin_start, u32 *out_slots,
-                                    cudaStream_t s);
+                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, u32 *out_slots, cudaStream_t s);
 
 // ---- stage 4 (HBM path): expand.cu -------------------------------------------------------------------
 constexpr int XP_THREADS = 256;
