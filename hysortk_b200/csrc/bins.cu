@@ -12,15 +12,19 @@
 // few values: sorting the occurrences is both unbalanced (30-copy lumps) and wasted work.  Here:
 //
 //   k_bin_count   (one CTA per bin, bins taken in index order through a ticket)
-//     1. supermer table of the bin: block scan of k-mer / word offsets
-//     2. every thread expands its share of consecutive k-mers (rolling forward / reverse words inside a
-//        supermer) and inserts each into an open-addressing table in shared memory keyed by the
-//        canonical k-mer (64-bit CAS; for K > 32 a 64-bit fingerprint of the words is the CAS key and
-//        the full words are verified afterwards — a fingerprint clash sends the bin to the HBM path,
-//        so the result stays exact).  The slot's 16-bit counter gives the count AND the index of this
-//        occurrence among its k-mer's occurrences (used to place (pos, rid) when EXTENSION).
+//     1. warps take batches of 32 consecutive supermer slots of the bin; a warp scan of the k-mers per slot and
+//        a bitmap of the slot starts map k-mer g of the batch to (slot, offset), so that in every round each
+//        lane extracts ONE k-mer directly from the staged slot words (funnel shift, reverse complement by bit
+//        reversal, canonical choice) — no per-thread walk, no divergence on supermer boundaries
+//     2. the k-mer is inserted into an open-addressing table in shared memory: for K <= 32 the cell is the
+//        k-mer itself (one 64-bit CAS, and only when a plain load did not already find it); for K > 32 a
+//        32-bit fingerprint cell guards the full key words (claim = EMPTY -> LOCK -> words -> fingerprint), and
+//        every fingerprint match is confirmed on the full words, so the table is exact.  A 32-bit counter per
+//        slot counts the occurrences
 //     3. every thread filters its slots with LOWER <= count <= UPPER, a block scan compacts the kept
 //        (k-mer, count) pairs and they are written to a staging area at an atomically claimed offset
+//     4. EXTENSION: the counters of the kept slots become cursors into the bin's occurrence area and a second
+//        walk over the bin places (pos, rid) of every occurrence of a kept k-mer
 //   k_bin_offsets  exclusive scan of the per-bin kept / occurrence totals -> final positions
 //   k_bin_gather   (one CTA per bin) sorts the bin's kept k-mers by key (bitonic sort in shared
 //                  memory over the few distinct kept keys) and writes them, with their occurrence
@@ -29,46 +33,63 @@
 // So the SORT is still there, but it runs over the distinct kept k-mers (D) instead of over every
 // occurrence (N): D/N is ~4 % at 30x coverage with 1 % errors.  The arena holds the bins in index order
 // and ascending k-mers inside each bin (the reference: per-task sorted runs in task order,
-// kmerops.cpp:883-904), deterministically.  Bins are sized by the extraction stage so that they fit
-// (CAP k-mers); the rare bin that does not (skew) is reported in an overflow list and goes through the
-// HBM path (expand.cu -> radix.cu -> count.cu).
+// kmerops.cpp:883-904), deterministically.  A bin of any number of occurrences is handled as long as its
+// distinct k-mers fit the table; bins are sized by the extraction stage so that they fill about a third of
+// it, and the rare bin that does not fit (skew) is reported in an overflow list and goes through the HBM
+// path (expand.cu -> radix.cu -> count.cu).
 #include "kernels.cuh"
 
 #include <algorithm>
 
 namespace hsk {
 
-constexpr int BN_SPT = BN_SCAP / BN_THREADS;   // supermers per thread in the table scan
-constexpr int BN_HCAP = 2048;                  // shared-memory histogram bins
+constexpr int BN_WARPS = BN_THREADS / 32;
+constexpr int BN_HCAP = 256;                   // shared-memory histogram bins (larger counts go to the global histogram)
 constexpr u64 BN_EMPTY = ~0ull;                // never a canonical k-mer: a K-mer of all T is not canonical
+constexpr u32 BN_EMPTY32 = 0xFFFFFFFFu;        // K > 32: state of a fingerprint cell
+constexpr u32 BN_LOCK32 = 0xFFFFFFFEu;         //          claimed, key words not yet written
+constexpr u32 BN_NOTKEPT = 0xFFFFFFFFu;
+constexpr int BN_CAND = 1024;                  // candidate list; a bin with more candidates scans its whole table
 
-template <int NW>
+template <int NW, bool EXT>
 struct BinCfg {
-    static constexpr int KPT = NW == 1 ? 12 : (NW == 2 ? 6 : 4);
-    static constexpr int CAP = BN_THREADS * KPT;           // 6144 / 3072 / 2048 k-mers per bin
-    static constexpr int TS_BITS = NW == 1 ? 13 : 12;      // table slots: 8192 / 4096 / 4096
+    static constexpr int SW = (NW == 1 ? 4 : 8) + (EXT ? 4 : 0);
+    static constexpr int PW = SW - (EXT ? 2 : 0);
+    // table slots: K <= 32: 8192 (two CTAs per SM), with EXTENSION 4096 (three CTAs); K > 32: one CTA per SM
+    static constexpr int TS_BITS = NW == 1 ? (EXT ? 12 : 13) : (NW == 2 && !EXT ? 13 : 12);
     static constexpr int TS = 1 << TS_BITS;
-    static constexpr int SLOTS_PT = TS / BN_THREADS;       // slots per thread in the filter: 16 / 8 / 8
+    static constexpr int SLOTS_PT = TS / BN_THREADS;
+    static constexpr int CTAS = NW == 1 ? (EXT ? 3 : 2) : 1;
+    // most k-mers one slot can hold (smallest K of the word count) = rounds of 32 k-mers a batch of 32 slots can need
+    static constexpr int NMAX = 16 * (PW - 1) + 12 - (NW == 1 ? 3 : (NW == 2 ? 33 : 65)) + 1;
+    static constexpr int HEADW = (NMAX + 31) / 32 * 32;
+    static constexpr int TARGET = NW == 1 ? (EXT ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
 };
 
-int bin_capacity(int nwords, bool ext)
+int bin_target_kmers(int nwords, bool ext)
 {
-    (void)ext;
-    return BN_THREADS * (nwords == 1 ? 12 : (nwords == 2 ? 6 : 4));
+    if (nwords == 1) return ext ? BinCfg<1, true>::TARGET : BinCfg<1, false>::TARGET;
+    if (nwords == 2) return ext ? BinCfg<2, true>::TARGET : BinCfg<2, false>::TARGET;
+    return BinCfg<3, false>::TARGET;
 }
 
-template <int NW>
+template <int NW, bool EXT>
 struct BinSmem {
-    u64 fp[BinCfg<NW>::TS];                                 // CAS key: the k-mer (NW == 1) or its fingerprint
-    u64 kw[NW > 1 ? NW : 1][NW > 1 ? BinCfg<NW>::TS : 1];   // full key words (NW > 1)
-    u32 cnt[BinCfg<NW>::TS];                                // occurrences per slot; later: occurrence offset of the slot
-    u16 koff[BN_SCAP + 2];                                  // k-mer offset of every slot of the chunk
+    using Cfg = BinCfg<NW, EXT>;
+    alignas(16) u64 fp[NW == 1 ? Cfg::TS : 1];                          // K <= 32: the k-mer itself is the CAS key
+    u64 kw[NW > 1 ? NW : 1][NW > 1 ? Cfg::TS : 1];          // K > 32: full key words ...
+    alignas(16) u32 fp32[NW > 1 ? Cfg::TS : 1];                         //         ... guarded by a 32-bit fingerprint cell
+    alignas(16) u32 cnt[Cfg::TS];                                       // occurrences per slot; EXT pass 2: next occurrence offset
+    alignas(16) uint4 stg[BN_WARPS][32 * Cfg::SW / 4 + 2];              // the warp's batch of 32 supermer slots (+ pad)
+    u16 scan[BN_WARPS][32];                                 // first k-mer of every slot of the batch
+    u32 heads[BN_WARPS][Cfg::HEADW];                        // bit g set: k-mer g of the batch starts a slot
     u32 hist[BN_HCAP];
+    u16 cand[BN_CAND];                                      // slots whose counter reached LOWER
     const u32 *src_ptr[BN_MAX_SRC];                         // first slot of the bin in every source stream
     u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1];
-    u32 wa[BN_THREADS / 32], wb[BN_THREADS / 32];
+    u32 wa[BN_WARPS], wb[BN_WARPS];
     u64 stage_kept, stage_occ;
-    u32 bin, nk, S, bail;
+    u32 bin, nk, S, bail, next_batch, seen, ncand;
 };
 
 // block-wide exclusive scan of two u32 values (BN_THREADS threads); returns exclusive prefixes and totals
@@ -107,147 +128,187 @@ __device__ __forceinline__ bool key_less(const u64 (&a)[NW], const u64 (&b)[NW])
     return false;
 }
 
-// CAS key of a k-mer: the k-mer itself when it is one word, else a 64-bit fingerprint of its words
+// home slot and (K > 32) fingerprint of a k-mer
 template <int NW>
-__device__ __forceinline__ u64 fingerprint(const u64 (&w)[NW])
+__device__ __forceinline__ u64 key_mix(const u64 (&w)[NW])
 {
-    if (NW == 1) return w[0];
     u64 h = w[0] * 0x9E3779B97F4A7C15ull;
 #pragma unroll
     for (int l = 1; l < NW; ++l) {
         h ^= h >> 29;
         h = (h + w[l]) * 0xBF58476D1CE4E5B9ull;
     }
-    h ^= h >> 32;
-    return h == BN_EMPTY ? 0x5851F42D4C957F2Dull : h;
-}
-
-
-// expansion state of one thread: the slot it is in (SW words in registers, shifted so that the current
-// k-mer starts at the top), the k-mers left in the slot, and the position of the current k-mer
-template <int SW>
-struct Walk {
-    u32 w[SW];
-    u32 j;        // slot index inside the bin
-    u32 left;     // k-mers of this slot not yet produced (0: load the next slot)
-    u32 pos, rid; // EXTENSION: PosInRead of the current k-mer, ReadId
-};
-
-template <int SW, int PW>
-__device__ __forceinline__ void shift_bases(u32 (&w)[SW], u32 nb)
-{
-    // left shift of the payload words by nb bases (nb < 16)
-    const u32 sh = 2 * nb;
-#pragma unroll
-    for (int x = 0; x < PW - 1; ++x) w[x] = __funnelshift_l(w[x + 1], w[x], sh);
-    w[PW - 1] <<= sh;
+    return h;
 }
 
 // address of slot j of the bin (j counts over the per-source segments in rank order)
-template <int NW>
-__device__ __forceinline__ const u32 *slot_ptr(const BinSmem<NW> &sm, const BinParams &P, u32 j, int sw)
+template <typename SM>
+__device__ __forceinline__ const u32 *slot_ptr(const SM &sm, const BinParams &P, u32 j, int sw)
 {
-    if (P.nsrc == 1) return sm.src_ptr[0] + j * (u32)sw;
+    if (P.nsrc == 1) return sm.src_ptr[0] + (size_t)j * (u32)sw;
     int s = 0;
     while (j >= sm.src_sbase[s + 1]) ++s;
-    return sm.src_ptr[s] + (j - sm.src_sbase[s]) * (u32)sw;
+    return sm.src_ptr[s] + (size_t)(j - sm.src_sbase[s]) * (u32)sw;
 }
 
-// canonical k-mer at the current position, then advance by one k-mer
-template <int NW, int SW, bool EXT>
-__device__ __forceinline__ void next_kmer(Walk<SW> &r, const BinSmem<NW> &sm, const BinParams &P, int k, int padbits,
-                                          u32 skip, u64 (&key)[NW], u64 &val)
+// Find the slot of a k-mer in the table; INSERT claims an empty slot when the k-mer is new.  Returns TS when the
+// table is full (INSERT) / the k-mer is absent (lookup).
+//   K <= 32: the cell holds the k-mer; one 64-bit CAS claims it.
+//   K > 32:  the cell holds a 32-bit fingerprint; a claim goes EMPTY -> LOCK (CAS), key words written, fence,
+//            fingerprint published, so whoever reads a fingerprint also sees the words and compares them in full:
+//            equal fingerprints of different k-mers just probe on.  Exact, no second pass.
+template <int NW, bool EXT, bool INSERT>
+__device__ __forceinline__ u32 table_find(BinSmem<NW, EXT> &sm, const u64 (&key)[NW])
 {
-    constexpr int PW = SW - (EXT ? 2 : 0);
-    if (r.left == 0) {
-        const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr<NW>(sm, P, r.j, SW));
-#pragma unroll
-        for (int x = 0; x < SW / 4; ++x) {
-            const uint4 v = __ldg(sp + x);
-            r.w[4 * x] = v.x; r.w[4 * x + 1] = v.y; r.w[4 * x + 2] = v.z; r.w[4 * x + 3] = v.w;
-        }
-        r.left = (r.w[PW - 1] & 0xFFu) - (u32)k + 1 - skip;
-        if (EXT) { r.pos = r.w[SW - 2] + skip; r.rid = r.w[SW - 1]; }
-        // start inside the slot: drop `skip` bases (only the first slot of a thread's range)
-        for (u32 t = skip; t > 0;) {
-            const u32 step = min(t, 15u);
-            shift_bases<SW, PW>(r.w, step);
-            t -= step;
-        }
-    }
-    u64 fwd[NW], rc[NW];
-#pragma unroll
-    for (int l = 0; l < NW; ++l) fwd[l] = ((u64)r.w[2 * l] << 32) | r.w[2 * l + 1];
-    if (padbits) fwd[NW - 1] &= ~0ull << padbits;
-    kmer_twin<NW>(fwd, k, rc);
-    const bool use_rc = key_less<NW>(rc, fwd);
-#pragma unroll
-    for (int l = 0; l < NW; ++l) key[l] = use_rc ? rc[l] : fwd[l];
-    if (EXT) { val = ((u64)r.pos << 32) | r.rid; ++r.pos; }
-    shift_bases<SW, PW>(r.w, 1);
-    if (--r.left == 0) ++r.j;
-}
-
-// claim or find the slot of a k-mer; a full table (more distinct k-mers than slots) sets the bail flag
-template <int NW>
-__device__ __forceinline__ u32 table_probe(BinSmem<NW> &sm, const u64 (&key)[NW])
-{
-    using Cfg = BinCfg<NW>;
-    const u64 f = fingerprint<NW>(key);
-    u32 slot = (u32)((f * 0x9E3779B97F4A7C15ull) >> (64 - Cfg::TS_BITS));
-    for (int probes = 0;; ++probes) {
-        const u64 old = atomicCAS(&sm.fp[slot], BN_EMPTY, f);
-        if (old == BN_EMPTY) {
-            if (NW > 1) {
-#pragma unroll
-                for (int l = 0; l < NW; ++l) sm.kw[l][slot] = key[l];
+    using Cfg = BinCfg<NW, EXT>;
+    const u64 hmix = key_mix<NW>(key);
+    u32 slot = (u32)(hmix >> (64 - Cfg::TS_BITS));
+    if (NW == 1) {
+        const u64 f = key[0];
+        for (int probes = 0; probes < Cfg::TS; ++probes) {
+            u64 old = *reinterpret_cast<volatile u64 *>(&sm.fp[slot]);
+            if (old == f) return slot;
+            if (old == BN_EMPTY) {
+                if (!INSERT) return (u32)Cfg::TS;
+                old = atomicCAS(&sm.fp[slot], BN_EMPTY, f);
+                if (old == BN_EMPTY || old == f) return slot;
             }
-            break;
+            slot = (slot + 1) & (Cfg::TS - 1);
         }
-        if (old == f) break;
-        if (probes >= Cfg::TS) { atomicOr(&sm.bail, 16u); break; }
-        slot = (slot + 1) & (Cfg::TS - 1);
-    }
-    return slot;
-}
-
-// claim or find the slot of a k-mer and bump its counter; returns the slot and the counter word before the bump.
-template <int NW>
-__device__ __forceinline__ u32 table_insert(BinSmem<NW> &sm, const u64 (&key)[NW], u32 &prev)
-{
-    using Cfg = BinCfg<NW>;
-    const u64 f = fingerprint<NW>(key);
-    u32 slot = (u32)((f * 0x9E3779B97F4A7C15ull) >> (64 - Cfg::TS_BITS));
-    for (int probes = 0;; ++probes) {
-        const u64 old = atomicCAS(&sm.fp[slot], BN_EMPTY, f);
-        if (old == BN_EMPTY) {
-            if (NW > 1) {
+    } else {
+        const u32 f = (u32)hmix & 0x7FFFFFFFu;
+        for (int probes = 0; probes < Cfg::TS; ++probes) {
+            volatile u32 *cell = &sm.fp32[slot];
+            u32 old = *cell;
+            if (old == BN_EMPTY32) {
+                if (!INSERT) return (u32)Cfg::TS;
+                old = atomicCAS(&sm.fp32[slot], BN_EMPTY32, BN_LOCK32);
+                if (old == BN_EMPTY32) {
 #pragma unroll
-                for (int l = 0; l < NW; ++l) sm.kw[l][slot] = key[l];
+                    for (int l = 0; l < NW; ++l) sm.kw[l][slot] = key[l];
+                    __threadfence_block();
+                    *cell = f;
+                    return slot;
+                }
             }
-            break;
+            while (old == BN_LOCK32) old = *cell;
+            if (old == f) {
+                bool same = true;
+#pragma unroll
+                for (int l = 0; l < NW; ++l) same = same && (*reinterpret_cast<volatile u64 *>(&sm.kw[l][slot]) == key[l]);
+                if (same) return slot;
+            }
+            slot = (slot + 1) & (Cfg::TS - 1);
         }
-        if (old == f) break;
-        if (probes >= Cfg::TS) { atomicOr(&sm.bail, 16u); prev = 0; return slot; }
-        slot = (slot + 1) & (Cfg::TS - 1);
     }
-    prev = atomicAdd(&sm.cnt[slot], 1u);
-    return slot;
+    return (u32)Cfg::TS;
 }
 
-// One CTA per bin.  K <= 32 without EXTENSION needs no per-occurrence state after the insertion, so a bin of
-// any size up to 65535 occurrences (16-bit counters / offsets) is handled, slots in chunks of BN_SCAP, as
-// long as its distinct k-mers fit the table.  With EXTENSION or K > 32 every thread keeps its occurrences in
-// registers for the second pass, which limits a bin to BinCfg::CAP occurrences and BN_SCAP slots.
+// One pass over the k-mers of the bin.  Warps take batches of 32 consecutive slots (ticket in shared memory): the
+// lanes stage one slot each, a warp scan of the k-mers per slot and a bitmap of the slot starts map k-mer g of
+// the batch to (slot, offset) without a search, and round r gives k-mer 32r + lane to every lane — all lanes
+// work on every round but the last, whatever the supermer lengths are.
+//   PASS2 == false: insert + count.   PASS2 == true (EXTENSION): place (pos, rid) of the occurrences of kept k-mers.
+template <int NW, bool EXT, bool PASS2>
+__device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &P, int k, int padbits, u32 S)
+{
+    using Cfg = BinCfg<NW, EXT>;
+    constexpr int SW = Cfg::SW, PW = Cfg::PW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 *stg = reinterpret_cast<u32 *>(sm.stg[warp]);
+    u16 *scan = sm.scan[warp];
+    u32 *heads = sm.heads[warp];
+    u32 seen = 0;
+    while (true) {
+        u32 bt = 0;
+        if (lane == 0) bt = atomicAdd(&sm.next_batch, 1u);
+        bt = __shfl_sync(0xFFFFFFFFu, bt, 0);
+        const u32 j0 = bt * 32u;
+        if (j0 >= S) break;
+        u32 n = 0;
+        if (j0 + lane < S) {
+            const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j0 + lane, SW));
+#pragma unroll
+            for (int x = 0; x < SW / 4; ++x) {
+                const uint4 v = __ldg(sp + x);
+                sm.stg[warp][lane * (SW / 4) + x] = v;
+                if (x == (PW - 1) / 4) {
+                    const u32 lw = ((PW - 1) % 4 == 3) ? v.w : ((PW - 1) % 4 == 1 ? v.y : ((PW - 1) % 4 == 2 ? v.z : v.x));
+                    n = (lw & 0xFFu) - (u32)k + 1;
+                }
+            }
+        }
+        u32 inc = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const u32 T = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const u32 ex = inc - n;
+        const u32 rounds = (T + 31) >> 5;
+        scan[lane] = (u16)ex;
+        for (u32 r = lane; r < rounds && r < (u32)Cfg::HEADW; r += 32) heads[r] = 0;
+        __syncwarp();
+        if (n) atomicOr(&heads[ex >> 5], 1u << (ex & 31));
+        __syncwarp();
+        u32 base = 0;   // slots started before this round
+        for (u32 r = 0; r < rounds; ++r) {
+            const u32 word = heads[r];
+            const u32 g = 32 * r + lane;
+            const u32 s = base + __popc(word & (0xFFFFFFFFu >> (31 - lane))) - 1;
+            base += __popc(word);
+            const bool act = g < T;
+            const u32 o = act ? g - scan[s] : 0u;
+            const u32 *w = stg + s * SW;
+            const u32 wi = o >> 4, sh = 2 * (o & 15);
+            u64 key[NW];
+#pragma unroll
+            for (int l = 0; l < NW; ++l) {
+                const u32 a = w[wi + 2 * l], b = w[wi + 2 * l + 1], c = w[wi + 2 * l + 2];
+                key[l] = ((u64)__funnelshift_l(b, a, sh) << 32) | __funnelshift_l(c, b, sh);
+            }
+            if (padbits) key[NW - 1] &= ~0ull << padbits;
+            kmer_canonical<NW>(key, k);
+            if (!PASS2) {
+                u32 slot = (u32)Cfg::TS;
+                if (act) slot = table_find<NW, EXT, true>(sm, key);
+                __syncwarp();   // the probe loop diverges; everything after it runs once per warp
+                if (act) {
+                    if (slot < (u32)Cfg::TS) {
+                        // the occurrence that lifts a counter to LOWER makes its slot a candidate for the output
+                        if (atomicAdd(&sm.cnt[slot], 1u) + 1 == P.lower) {
+                            const u32 ci = atomicAdd(&sm.ncand, 1u);
+                            if (ci < (u32)BN_CAND) sm.cand[ci] = (u16)slot;
+                        }
+                    } else atomicOr(&sm.bail, 16u);
+                }
+            } else {
+                u32 slot = (u32)Cfg::TS;
+                if (act) slot = table_find<NW, EXT, false>(sm, key);
+                __syncwarp();
+                if (slot < (u32)Cfg::TS && *reinterpret_cast<volatile u32 *>(&sm.cnt[slot]) != BN_NOTKEPT) {
+                    const u64 p = sm.stage_occ + atomicAdd(&sm.cnt[slot], 1u);
+                    P.st_pos[p] = w[SW - 2] + o;
+                    P.st_rid[p] = (int)w[SW - 1];
+                }
+            }
+        }
+        seen += T;
+        __syncwarp();   // the staging area is reused by the next batch
+    }
+    if (!PASS2 && lane == 0 && seen) atomicAdd(&sm.seen, seen);
+}
+
+// One CTA per bin, bins taken in index order through a ticket; a bin of any size is handled as long as its distinct
+// k-mers fit the table (anything else is listed for the HBM path).
 template <int NW, bool EXT>
-__global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinParams P)
+__global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count(BinParams P)
 {
-    using Cfg = BinCfg<NW>;
-    constexpr bool FREE = (NW == 1) && !EXT;
-    constexpr int SW = (NW == 1 ? 4 : 8) + (EXT ? 4 : 0);
-    constexpr int PW = SW - (EXT ? 2 : 0);
+    using Cfg = BinCfg<NW, EXT>;
+    constexpr int SW = Cfg::SW;
     extern __shared__ __align__(16) unsigned char smraw[];
-    BinSmem<NW> &sm = *reinterpret_cast<BinSmem<NW> *>(smraw);
+    BinSmem<NW, EXT> &sm = *reinterpret_cast<BinSmem<NW, EXT> *>(smraw);
     const int tid = threadIdx.x;
     const int k = P.k;
     const int padbits = 2 * (32 * NW - k);
@@ -256,9 +317,13 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
 
     while (true) {
         __syncthreads();   // end of the previous bin: shared memory is free again
-        if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; }
-        for (int i = tid; i < Cfg::TS; i += BN_THREADS) sm.fp[i] = BN_EMPTY;
-        for (int i = tid; i < Cfg::TS; i += BN_THREADS) sm.cnt[i] = 0;
+        if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; }
+        {
+            const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
+            if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
+            else { for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp32)[i] = ones; }
+            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
+        }
         __syncthreads();
         const u32 lb = sm.bin;
         if (lb >= P.nbins) break;
@@ -277,113 +342,16 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             const u64 nk = P.bin_kmers[lb] & ((1ull << 40) - 1);
             sm.nk = (u32)min(nk, (u64)0xFFFFFFFFu);
             sm.S = (u32)min(s, (u64)0xFFFFFFFFu);
-            if (FREE) { if (nk > 65535ull || s > 65535ull) sm.bail = 1; }
-            else { if (nk > (u64)Cfg::CAP || s > (u64)BN_SCAP) sm.bail = 1; }
+            if (nk >= 0xFFFFFFFFull || s >= 0xFFFFFFFFull) sm.bail = 1;   // 32-bit counters
         }
         __syncthreads();
         const u32 nk = sm.nk, S = sm.S;
 
-        u64 kreg[FREE || NW == 1 ? 1 : Cfg::KPT][NW];   // full keys again for the K > 32 verification
-        u64 vreg[EXT ? Cfg::KPT : 1];
-        u16 slot_of[FREE ? 1 : Cfg::KPT], occ_idx[EXT ? Cfg::KPT : 1];
-        u32 a = 0, e = 0;   // my occurrences [a, e) of the (single) chunk when !FREE
-        u32 seen = 0;       // occurrences inserted so far (all chunks)
-
-        for (u32 c0 = 0; c0 < S && !sm.bail; c0 += BN_SCAP) {
-            const u32 Sc = min((u32)BN_SCAP, S - c0);
-            // ---- k-mer offsets of the chunk's slots (block scan of len - K + 1)
-            u32 n4[BN_SPT], tn = 0;
-#pragma unroll
-            for (int i = 0; i < BN_SPT; ++i) {
-                const u32 jl = tid * BN_SPT + i;
-                n4[i] = 0;
-                if (jl < Sc) n4[i] = (__ldg(slot_ptr<NW>(sm, P, c0 + jl, SW) + (PW - 1)) & 0xFFu) - (u32)k + 1;
-                tn += n4[i];
-            }
-            u32 en, dummy_e, totn, dummy_t;
-            block_scan2(tn, 0u, sm.wa, sm.wb, en, dummy_e, totn, dummy_t);
-#pragma unroll
-            for (int i = 0; i < BN_SPT; ++i) {
-                const u32 jl = tid * BN_SPT + i;
-                if (jl < Sc) sm.koff[jl] = (u16)en;
-                en += n4[i];
-            }
-            if (tid == 0) {
-                sm.koff[Sc] = (u16)totn;
-                if (seen + totn > nk) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
-            }
-            __syncthreads();
-            if (sm.bail) break;
-
-            const u32 nkc = totn;
-            const u32 q = (nkc + BN_THREADS - 1) / BN_THREADS;   // occurrences per thread in this chunk
-            a = tid * q; e = min(nkc, a + q);
-            const bool has = a < e;
-            Walk<SW> r;
-            r.j = 0; r.left = 0; r.pos = 0; r.rid = 0;
-            u32 skip = 0;
-            if (has) {
-                u32 jl = 0;
-                for (u32 step = BN_SCAP / 2; step >= 1; step >>= 1)
-                    if (jl + step < Sc && sm.koff[jl + step] <= a) jl += step;
-                r.j = c0 + jl;
-                skip = a - sm.koff[jl];
-            }
-            if (FREE) {
-                // every thread runs the same number of rounds so that the warp reconverges between the
-                // (divergent) probe loop and the counter update
-                for (u32 it = 0; it < q; ++it) {
-                    const bool act = has && (a + it < e);
-                    u32 slot = 0;
-                    if (act) {
-                        u64 key[NW], val;
-                        next_kmer<NW, SW, EXT>(r, sm, P, k, padbits, skip, key, val);
-                        skip = 0;
-                        slot = table_probe<NW>(sm, key);
-                    }
-                    __syncwarp();
-                    if (act) atomicAdd(&sm.cnt[slot], 1u);
-                }
-            } else if (has) {
-#pragma unroll
-                for (int i = 0; i < Cfg::KPT; ++i) {
-                    if (a + i < e) {
-                        u64 key[NW], val = 0;
-                        next_kmer<NW, SW, EXT>(r, sm, P, k, padbits, skip, key, val);
-                        skip = 0;
-                        if (NW > 1) {
-#pragma unroll
-                            for (int l = 0; l < NW; ++l) kreg[i][l] = key[l];
-                        }
-                        if (EXT) vreg[i] = val;
-                        u32 prev;
-                        const u32 slot = table_insert<NW>(sm, key, prev);
-                        slot_of[i] = (u16)slot;
-                        if (EXT) occ_idx[i] = (u16)prev;
-                    }
-                }
-            }
-            seen += nkc;
-            __syncthreads();   // koff may be overwritten by the next chunk
-        }
-        if (!sm.bail && seen != nk && tid == 0) sm.bail = 2;
+        // ---- expand + insert + count
+        if (!sm.bail) walk_bin<NW, EXT, false>(sm, P, k, padbits, S);
         __syncthreads();
-
-        if (NW > 1) {
-            // ---- the CAS key was a fingerprint: every occurrence checks the full words of its slot
-            if (!sm.bail && a < e) {
-                bool ok = true;
-#pragma unroll
-                for (int i = 0; i < Cfg::KPT; ++i) {
-                    if (a + i < e) {
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) ok = ok && (sm.kw[l][slot_of[i]] == kreg[i][l]);
-                    }
-                }
-                if (!ok) atomicOr(&sm.bail, 8u);
-            }
-            __syncthreads();
-        }
+        if (!sm.bail && sm.seen != nk && tid == 0) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
+        __syncthreads();
 
         if (sm.bail) {
             // bin goes to the HBM path
@@ -395,13 +363,19 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             continue;
         }
 
-        // ---- filter my slots, compact the kept (k-mer, count) pairs into the staging area
+        // ---- filter, compact the kept (k-mer, count) pairs into the staging area.  Usually the candidate list
+        //      (slots that reached LOWER) names the few slots to look at; a bin with more candidates than the
+        //      list holds (LOWER == 1, mostly) scans its whole table.
+        const u32 ncand = sm.ncand;
+        const bool listed = ncand <= (u32)BN_CAND;
+        const u32 per_thread = listed ? (ncand + BN_THREADS - 1) / BN_THREADS : (u32)Cfg::SLOTS_PT;
         u32 kept = 0, occ = 0, keepmask = 0;
-#pragma unroll
-        for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
-            const u32 slot = tid * Cfg::SLOTS_PT + i;
+        for (u32 i = 0; i < per_thread; ++i) {
+            u32 slot = tid * per_thread + i;
+            bool in = true;
+            if (listed) { in = slot < ncand; slot = in ? sm.cand[slot] : 0u; }
             const u32 c = sm.cnt[slot];
-            if (c >= P.lower && c <= P.upper) { keepmask |= 1u << i; ++kept; occ += c; }
+            if (in && c >= P.lower && c <= P.upper) { keepmask |= 1u << i; ++kept; occ += c; }
         }
         u32 ek, eo, tk, to;
         block_scan2(kept, occ, sm.wa, sm.wb, ek, eo, tk, to);
@@ -409,19 +383,32 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
             const u64 sk = tk ? atomicAdd(P.stage_cursor, (u64)tk) : 0;
             const u64 so = (EXT && to) ? atomicAdd(P.stage_cursor + 1, (u64)to) : 0;
             sm.stage_kept = sk; sm.stage_occ = so;
+            sm.next_batch = 0;
             P.bin_rec[4 * (size_t)lb + 0] = sk; P.bin_rec[4 * (size_t)lb + 1] = tk;
             P.bin_rec[4 * (size_t)lb + 2] = so; P.bin_rec[4 * (size_t)lb + 3] = EXT ? to : 0;
         }
         __syncthreads();
+        if (EXT && listed) {
+            // slots outside the list are not kept: the occurrence pass tells by the mark
+            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) {
+                uint4 v = reinterpret_cast<uint4 *>(sm.cnt)[i];
+                if (v.x < P.lower || v.x > P.upper) v.x = BN_NOTKEPT;
+                if (v.y < P.lower || v.y > P.upper) v.y = BN_NOTKEPT;
+                if (v.z < P.lower || v.z > P.upper) v.z = BN_NOTKEPT;
+                if (v.w < P.lower || v.w > P.upper) v.w = BN_NOTKEPT;
+                reinterpret_cast<uint4 *>(sm.cnt)[i] = v;
+            }
+            __syncthreads();
+        }
         {
             u64 g = sm.stage_kept + ek;
             u32 lo = eo;   // occurrence offset inside the bin
-#pragma unroll
-            for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
-                const u32 slot = tid * Cfg::SLOTS_PT + i;
-                const u32 c = sm.cnt[slot];
-                u32 mark = 0xFFFFFFFFu;   // "not kept" for the occurrence pass
+            for (u32 i = 0; i < per_thread; ++i) {
+                u32 slot = tid * per_thread + i;
+                if (listed) slot = slot < ncand ? sm.cand[slot] : 0u;
+                u32 mark = BN_NOTKEPT;   // "not kept" for the occurrence pass
                 if ((keepmask >> i) & 1) {
+                    const u32 c = sm.cnt[slot];
                     if (NW == 1) P.st_words[g] = sm.fp[slot];
                     else {
 #pragma unroll
@@ -433,25 +420,13 @@ __global__ void __launch_bounds__(BN_THREADS, NW == 1 ? 2 : 1) k_bin_count(BinPa
                     lo += c;
                     ++g;
                 }
-                if (EXT) sm.cnt[slot] = mark;
+                if (EXT && (!listed || ((keepmask >> i) & 1))) sm.cnt[slot] = mark;
             }
         }
         if (EXT) {
             // ---- occurrences: (pos, rid) of every occurrence of a kept k-mer, grouped per k-mer
             __syncthreads();
-            const u64 so = sm.stage_occ;
-#pragma unroll
-            for (int i = 0; i < Cfg::KPT; ++i) {
-                if (a + i < e) {
-                    const u32 slot = slot_of[i];
-                    const u32 off = sm.cnt[slot];
-                    if (off != 0xFFFFFFFFu) {
-                        const u64 p = so + off + occ_idx[i];
-                        P.st_pos[p] = (u32)(vreg[i] >> 32);
-                        P.st_rid[p] = (int)(u32)vreg[i];
-                    }
-                }
-            }
+            if (to) walk_bin<NW, EXT, true>(sm, P, k, padbits, S);
         }
     }
 
@@ -870,9 +845,8 @@ constexpr int GL_THREADS = 512;                    // gather: listed bins with m
 template <int NW, bool EXT>
 static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t s)
 {
-    constexpr int GL_CAP = NW == 1 ? 8192 : (NW == 2 ? 4096 : 2048);   // power of two >= bin capacity
-    static_assert(BinCfg<NW>::CAP <= GL_CAP, "gather capacity");
-    const size_t smem = sizeof(BinSmem<NW>);
+    constexpr int GL_CAP = BinCfg<NW, EXT>::TS;   // a bin keeps at most one entry per table slot
+    const size_t smem = sizeof(BinSmem<NW, EXT>);
     cudaError_t e = cudaFuncSetAttribute(k_bin_count<NW, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;

@@ -277,7 +277,7 @@ void hsk_destroy(hsk_ctx *c)
 
 // ---- extraction (stages 1+2) -------------------------------------------------------------------------
 // Bins per rank: fixed by the config, or sized so that a bin holds on average half of what the on-chip
-// path can take (bins.cu: bin_capacity); every rank must use the same number, so the largest input of
+// path is sized for (bins.cu: bin_target_kmers); every rank must use the same number, so the largest input of
 // any rank decides.
 
 static int choose_bins(hsk_ctx *c, u64 nbytes)
@@ -294,10 +294,8 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
         CK(cudaStreamSynchronize(c->stream));
         mx = c->h_cursor.as<u64>()[5];
     }
-    // average occurrences per bin: K <= 32 without EXTENSION takes bins of any size on chip (limited by distinct
-    // k-mers), the other configurations keep a margin below the hard capacity
-    const u64 cap = (u64)bin_capacity(c->nwords, c->cfg.ext != 0);
-    u64 target = (c->nwords == 1 && !c->cfg.ext) ? 8192 : cap * 2 / 5;
+    // average occurrences per bin: sized so that the distinct k-mers of a bin fill about a third of its table
+    u64 target = (u64)bin_target_kmers(c->nwords, c->cfg.ext != 0);
     if (const char *ev = getenv("HSK_TARGET_BIN")) { u64 v = strtoull(ev, nullptr, 10); if (v >= 64) target = v; }
     u64 tg = (mx * 4 + target - 1) / target;
     tg = std::max<u64>(64, (tg + 63) / 64 * 64);

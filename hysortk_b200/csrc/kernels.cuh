@@ -53,7 +53,6 @@ cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext,
 
 // ---- stages 4+5 on chip: bins.cu ---------------------------------------------------------------------
 constexpr int BN_THREADS = 512;
-constexpr int BN_SCAP = 2048;        // supermers per bin that the on-chip path handles
 constexpr int BN_MAX_SRC = 16;       // source ranks per bin
 
 struct BinParams {
@@ -78,7 +77,7 @@ struct BinParams {
     u32 *big_list, *big_count;           // bins with more kept k-mers than the small gather handles
 };
 
-int bin_capacity(int nwords, bool ext);  // k-mers per bin the on-chip path can hold
+int bin_target_kmers(int nwords, bool ext);  // k-mer occurrences per bin the on-chip path is sized for
 // k_bin_count + k_bin_offsets + k_bin_gather (x2)
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
 // multi-rank: segment tables of the owned bins inside the per-source streams + send/recv sizes (meta)
