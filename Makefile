@@ -40,7 +40,7 @@ CXXFLAGS=$(OPT) -std=c++17 -fPIC -fopenmp -pthread -Wall $(PARAMS) -I./include $
 NVFLAGS=-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 
 HOST_OBJ=$(OBJ)/hysortk.o $(OBJ)/dnaseq.o $(OBJ)/dnabuffer.o $(OBJ)/hashfuncs.o
-CUDA_OBJ=$(OBJ)/extract.o $(OBJ)/expand.o $(OBJ)/radix.o $(OBJ)/count.o $(OBJ)/bins.o $(OBJ)/engine.o
+CUDA_OBJ=$(OBJ)/reads.o $(OBJ)/extract.o $(OBJ)/expand.o $(OBJ)/radix.o $(OBJ)/count.o $(OBJ)/bins.o $(OBJ)/engine.o
 
 all: print lib
 

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhysortk_b200.so")
-SOURCES = ["extract.cu", "expand.cu", "radix.cu", "count.cu", "bins.cu", "engine.cu"]
+SOURCES = ["reads.cu", "extract.cu", "expand.cu", "radix.cu", "count.cu", "bins.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
 
     while (true) {
         __syncthreads();   // end of the previous bin: shared memory is free again
-        if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; }
+        if (tid == 0) { sm.bin = P.bin_lo + atomicAdd(P.ticket, 1u); sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; }
         {
             const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
             if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         }
         __syncthreads();
         const u32 lb = sm.bin;
-        if (lb >= P.nbins) break;
+        if (lb >= P.bin_hi) break;
 
         // ---- bin descriptor: one segment of slots per source rank
         if (tid < P.nsrc) {
@@ -436,20 +436,23 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
 }
 
 // ---- final positions of the bins: exclusive scan of (kept, occurrences) over the bins; one block ----
-__global__ void __launch_bounds__(1024) k_bin_offsets(const u64 *__restrict__ bin_rec, u32 nbins, u64 *__restrict__ fin,
-                                                       u64 *__restrict__ cursor, u32 big_from, u32 *__restrict__ big_list,
-                                                       u32 *__restrict__ big_count)
+__global__ void __launch_bounds__(1024) k_bin_offsets(const u64 *__restrict__ bin_rec, u32 bin_lo, u32 nbins, u64 *__restrict__ fin,
+                                                       u64 *__restrict__ cursor, u32 mid_from, u32 big_from,
+                                                       u32 *__restrict__ mid_list, u32 *__restrict__ mid_count,
+                                                       u32 *__restrict__ big_list, u32 *__restrict__ big_count,
+                                                       volatile u64 *snap)
 {
     __shared__ u64 s_a[32], s_b[32];
     __shared__ u64 carry_a, carry_b;
     if (threadIdx.x == 0) { carry_a = cursor[0]; carry_b = cursor[1]; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u32 base = 0; base < nbins; base += 1024) {
+    for (u32 base = bin_lo; base < nbins; base += 1024) {
         const u32 b = base + threadIdx.x;
         u64 x = 0, y = 0;
         if (b < nbins) { x = bin_rec[4 * (size_t)b + 1]; y = bin_rec[4 * (size_t)b + 3]; }
-        if (x > (u64)big_from) big_list[atomicAdd(big_count, 1u)] = b;   // handled by the large gather launch
+        if (x > (u64)big_from) big_list[atomicAdd(big_count, 1u)] = b;        // handled by the large gather launch
+        else if (x > (u64)mid_from) mid_list[atomicAdd(mid_count, 1u)] = b;   // by the mid gather
         u64 ix = x, iy = y;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -476,7 +479,13 @@ __global__ void __launch_bounds__(1024) k_bin_offsets(const u64 *__restrict__ bi
         if (threadIdx.x == 1023) { carry_a = ex + x; carry_b = ey + y; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { cursor[0] = carry_a; cursor[1] = carry_b; }
+    if (threadIdx.x == 0) {
+        cursor[0] = carry_a; cursor[1] = carry_b;
+        if (snap) {   // page-locked host memory: the host reads it after the event that follows this group
+            snap[0] = carry_a; snap[1] = carry_b; snap[2] = *big_count;
+            __threadfence_system();
+        }
+    }
 }
 
 // ---- per bin: sort the kept k-mers by key and move them (and their occurrences) to the arena ----------
@@ -599,11 +608,13 @@ __global__ void __launch_bounds__(THREADS) k_bin_gather(BinParams P)
 // the same thread, at thread distance < 32 they are reached with warp shuffles, and only the last stages
 // (thread distance >= 32) go through shared memory: 3 of the 45 stages of a 512-element sort.
 constexpr int GS_THREADS = 128;
+constexpr int GS_EPT = 4;                          // most entries per thread of the small gather: 512 kept k-mers
+constexpr int GM_EPT = 8;                          // the mid gather (listed bins): up to 1024
 
-template <int NW>
+template <int NW, int EPTMAX = GS_EPT>
 struct GsSmem {
-    u64 key[NW][GS_THREADS * 4];
-    u32 cnt[GS_THREADS * 4], src[GS_THREADS * 4];
+    u64 key[NW][GS_THREADS * EPTMAX];
+    u32 cnt[GS_THREADS * EPTMAX], src[GS_THREADS * EPTMAX];
     u32 warp[GS_THREADS / 32];
 };
 
@@ -627,8 +638,8 @@ __device__ __forceinline__ u32 gs_scan(u32 v, u32 *warp_tot, u32 &total)
     return off + inc - v;
 }
 
-template <int NW, bool EXT, int EPT>
-__device__ __forceinline__ void gather_small(const BinParams &P, GsSmem<NW> &sm, u32 lb, u32 D, u64 sk, u64 so, u64 fk, u64 fo)
+template <int NW, bool EXT, int EPT, typename SM>
+__device__ __forceinline__ void gather_small(const BinParams &P, SM &sm, u32 lb, u32 D, u64 sk, u64 so, u64 fk, u64 fo)
 {
     constexpr int N = GS_THREADS * EPT;
     const int tid = threadIdx.x;
@@ -753,15 +764,32 @@ template <int NW, bool EXT>
 __global__ void __launch_bounds__(GS_THREADS) k_bin_gather_small(BinParams P)
 {
     __shared__ GsSmem<NW> sm;
-    const u32 lb = blockIdx.x;
+    const u32 lb = P.bin_lo + blockIdx.x;
     const u64 sk = P.bin_rec[4 * (size_t)lb + 0];
     const u32 D = (u32)P.bin_rec[4 * (size_t)lb + 1];
     const u64 so = P.bin_rec[4 * (size_t)lb + 2];
-    if (D == 0 || D > (u32)(GS_THREADS * 4)) return;
+    if (D == 0 || D > (u32)(GS_THREADS * GS_EPT)) return;
     const u64 fk = P.fin[2 * (size_t)lb], fo = P.fin[2 * (size_t)lb + 1];
     if (D <= GS_THREADS) gather_small<NW, EXT, 1>(P, sm, lb, D, sk, so, fk, fo);
     else if (D <= 2 * GS_THREADS) gather_small<NW, EXT, 2>(P, sm, lb, D, sk, so, fk, fo);
     else gather_small<NW, EXT, 4>(P, sm, lb, D, sk, so, fk, fo);
+}
+
+// bins with 513..1024 kept k-mers (listed by k_bin_offsets): the same register sort, 8 entries per thread
+template <int NW, bool EXT>
+__global__ void __launch_bounds__(GS_THREADS) k_bin_gather_mid(BinParams P)
+{
+    __shared__ GsSmem<NW, GM_EPT> sm;
+    const u32 n = *P.mid_count;
+    for (u32 work = blockIdx.x; work < n; work += gridDim.x) {
+        const u32 lb = P.mid_list[work];
+        const u64 sk = P.bin_rec[4 * (size_t)lb + 0];
+        const u32 D = (u32)P.bin_rec[4 * (size_t)lb + 1];
+        const u64 so = P.bin_rec[4 * (size_t)lb + 2];
+        const u64 fk = P.fin[2 * (size_t)lb], fo = P.fin[2 * (size_t)lb + 1];
+        __syncthreads();
+        gather_small<NW, EXT, GM_EPT>(P, sm, lb, D, sk, so, fk, fo);
+    }
 }
 
 // ---- per-source segment tables of the bins a rank owns (multi-rank) ---------------------------------
@@ -839,13 +867,12 @@ cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nran
     return cudaGetLastError();
 }
 
-constexpr int GS_CAP = GS_THREADS * 4;             // gather: the usual bins (register bitonic), one CTA each
+constexpr int GS_CAP = GS_THREADS * GS_EPT;             // gather: the usual bins (register bitonic), one CTA each
 constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers (up to the bin capacity)
 
 template <int NW, bool EXT>
 static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t s)
 {
-    constexpr int GL_CAP = BinCfg<NW, EXT>::TS;   // a bin keeps at most one entry per table slot
     const size_t smem = sizeof(BinSmem<NW, EXT>);
     cudaError_t e = cudaFuncSetAttribute(k_bin_count<NW, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -853,14 +880,24 @@ static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t 
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_count<NW, EXT>, BN_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const u32 grid = (u32)std::min<u64>((u64)sm_count * per_sm, std::max<u32>(P.nbins, 1u));
+    const u32 nb = P.bin_hi - P.bin_lo;
+    const u32 grid = (u32)std::min<u64>((u64)sm_count * per_sm, std::max<u32>(nb, 1u));
     k_bin_count<NW, EXT><<<grid, BN_THREADS, smem, s>>>(P);
-    k_bin_offsets<<<1, 1024, 0, s>>>(P.bin_rec, P.nbins, P.fin, P.cursor, (u32)GS_CAP, P.big_list, P.big_count);
-    // gather + sort: a small-footprint launch for the usual bins, a large one for bins with many kept k-mers
-    const size_t per_entry = (size_t)8 * NW + 8;
-    const size_t smem_l = per_entry * GL_CAP;
-    k_bin_gather_small<NW, EXT><<<P.nbins, GS_THREADS, 0, s>>>(P);
-    e = cudaFuncSetAttribute(k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+    k_bin_offsets<<<1, 1024, 0, s>>>(P.bin_rec, P.bin_lo, P.bin_hi, P.fin, P.cursor, (u32)GS_CAP, (u32)(GS_THREADS * GM_EPT), P.mid_list,
+                                     P.mid_count, P.big_list, P.big_count, P.snap);
+    // gather + sort: the usual bins one CTA each, the listed mid-sized ones by a small grid; bins with even more
+    // kept k-mers are listed (big_list) for launch_bin_gather_big
+    k_bin_gather_small<NW, EXT><<<nb, GS_THREADS, 0, s>>>(P);
+    k_bin_gather_mid<NW, EXT><<<32, GS_THREADS, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <int NW, bool EXT>
+static cudaError_t launch_big_t(const BinParams &P, int sm_count, cudaStream_t s)
+{
+    constexpr int GL_CAP = BinCfg<NW, EXT>::TS;   // a bin keeps at most one entry per table slot
+    const size_t smem_l = ((size_t)8 * NW + 8) * GL_CAP;
+    cudaError_t e = cudaFuncSetAttribute(k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
     if (e != cudaSuccess) return e;
     k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true><<<sm_count, GL_THREADS, smem_l, s>>>(P);
     return cudaGetLastError();
@@ -868,10 +905,21 @@ static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t 
 
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
 {
-    if (P.nbins == 0) return cudaSuccess;
+    if (P.bin_hi <= P.bin_lo) return cudaSuccess;
     if (nwords == 1) return ext ? launch_bins_t<1, true>(P, sm_count, s) : launch_bins_t<1, false>(P, sm_count, s);
     if (nwords == 2) return ext ? launch_bins_t<2, true>(P, sm_count, s) : launch_bins_t<2, false>(P, sm_count, s);
     return ext ? launch_bins_t<3, true>(P, sm_count, s) : launch_bins_t<3, false>(P, sm_count, s);
 }
 
+} // namespace hsk
+
+namespace hsk {
+// sorts + moves the bins listed in P.big_list (more kept k-mers than the small gather takes); launched only when
+// the group's big_count is not zero
+cudaError_t launch_bin_gather_big(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
+{
+    if (nwords == 1) return ext ? launch_big_t<1, true>(P, sm_count, s) : launch_big_t<1, false>(P, sm_count, s);
+    if (nwords == 2) return ext ? launch_big_t<2, true>(P, sm_count, s) : launch_big_t<2, false>(P, sm_count, s);
+    return ext ? launch_big_t<3, true>(P, sm_count, s) : launch_big_t<3, false>(P, sm_count, s);
+}
 } // namespace hsk

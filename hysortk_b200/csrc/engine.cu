@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -93,6 +94,20 @@ static int load_nccl()
 
 namespace {
 
+// HSK_TRACE=1: host-side timeline of a call on stderr (milliseconds since the first mark)
+struct Trace {
+    bool on = false;
+    std::chrono::steady_clock::time_point t0;
+    void start() { const char *e = getenv("HSK_TRACE"); on = e && *e == '1'; if (on) t0 = std::chrono::steady_clock::now(); }
+    void mark(const char *what) const
+    {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[hsk trace] %8.3f ms  %s\n", ms, what);
+    }
+};
+Trace g_trace;
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -123,6 +138,18 @@ struct HostBuf {   // page-locked
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grow, keeping the first `used` bytes (the caller makes sure no copy into the old block is in flight)
+    cudaError_t ensure_keep(size_t bytes, size_t used)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        void *q = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if (p) { if (used) memcpy(q, p, used); cudaFreeHost(p); }
+        p = q; cap = want;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
@@ -136,13 +163,20 @@ struct hsk_ctx {
     int nwords = 1, m_eff = 0;
     u32 tg = 0, tt = 0;   // buckets per rank / total
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host <-> device copies of hsk_count, overlapped with the kernels
     bool own_stream = false;
     ncclComm_t comm = nullptr;
     int sm_count = 148;
 
     // input staging (hsk_count)
-    DevBuf d_packed, d_read_off, d_read_len;
-    HostBuf h_read_off, h_read_len;
+    DevBuf d_packed, d_read_off, d_read_len, d_len64, d_rtscratch;
+    // host pipeline of hsk_count: chunks of the packed reads in flight (tile bound + event), result streaming
+    struct InChunk { u64 tile_end; cudaEvent_t ready; };
+    std::vector<InChunk> in_chunks;
+    bool stream_result = false;          // hsk_count: results go to the host buffers group by group
+    u32 *d_in_flags = nullptr;           // hsk_count: read table checks (reads.cu), looked at after the first sync
+    DevBuf d_grp;                        // per bin group: ticket, big-bin counter
+    HostBuf h_grp;                       // per bin group: arena cursor after the group
     // extraction
     DevBuf d_bucket, d_run_list, d_tile_hdr, d_tile_read;   // d_bucket: see run_extract
     HostBuf h_bucket;
@@ -162,6 +196,7 @@ struct hsk_ctx {
     hsk_stats stats;
 
     std::vector<u64> h_dbg;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<EvPair> ev_extract, ev_exchange, ev_expand, ev_sort, ev_count, ev_pass, ev_bins;
@@ -243,6 +278,10 @@ int hsk_create(hsk_ctx **out, const hsk_config *cfg)
         if (e != cudaSuccess) { delete c; return fail("cudaStreamCreate: %s", cudaGetErrorString(e)); }
         c->own_stream = true;
     }
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail("cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    }
     if (cfg->nranks > 1) {
         ncclUniqueId id;
         memcpy(&id, cfg->nccl_id, sizeof(id));
@@ -260,14 +299,15 @@ void hsk_destroy(hsk_ctx *c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bucket, &c->d_slots,
+    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_len64, &c->d_rtscratch, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bucket, &c->d_slots,
                     &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
     for (int h = 0; h < 2; ++h) for (int w = 0; w < MAX_WORDS; ++w) c->d_keys[h][w].release();
-    HostBuf *hb[] = {&c->h_read_off, &c->h_read_len, &c->h_bucket, &c->h_alltot, &c->h_meta, &c->h_cursor, &c->h_owords, &c->h_ocnt,
+    HostBuf *hb[] = {&c->h_bucket, &c->h_alltot, &c->h_meta, &c->h_cursor, &c->h_owords, &c->h_ocnt,
                      &c->h_oocc_off, &c->h_opos, &c->h_orid, &c->h_hist};
     for (auto *b : hb) b->release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -325,6 +365,7 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     P.ntiles = (nslots + P.out_slots - 1) / P.out_slots;
     const u32 nctas = extract_grid(w, c->sm_count);
     const u64 nwarps = (u64)nctas * XT_WARPS;
+    P.tile_begin = 0; P.tile_end = P.ntiles;
     P.tiles_per_warp = (u32)((P.ntiles + nwarps - 1) / nwarps);
     P.k = c->cfg.k; P.m = c->m_eff; P.nbins = T; P.readid_base = readid_base;
     P.slot_nmax = (u32)(slot_max_bases(c->nwords, ext) - c->cfg.k + 1);
@@ -349,21 +390,46 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     for (int attempt = 0;; ++attempt) {
         CK(c->d_run_list.ensure(run_cap * 8));
         CK(cudaMemsetAsync(d_tot, 0, (host_u64 + 2) * 8, s));
-        if (P.ntiles) CK(launch_supermer_count(P, nctas, d_tot, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur, run_cap, s));
+        // pass A over the tiles whose bytes have arrived (hsk_count uploads the reads in chunks); a retry and
+        // hsk_count_device see the whole buffer at once
+        u64 tb = 0;
+        const size_t nchunks = attempt == 0 ? c->in_chunks.size() : 0;
+        for (size_t ci = 0; ci <= nchunks; ++ci) {
+            u64 te = P.ntiles;
+            if (ci < nchunks) {
+                CK(cudaStreamWaitEvent(s, c->in_chunks[ci].ready, 0));
+                te = std::min<u64>(c->in_chunks[ci].tile_end, P.ntiles);
+                if (ci + 1 == nchunks) te = P.ntiles;
+            }
+            if (te <= tb) continue;
+            P.tile_begin = tb; P.tile_end = te;
+            P.tiles_per_warp = (u32)((te - tb + nwarps - 1) / nwarps);
+            CK(launch_supermer_count(P, nctas, d_tot, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur, run_cap, s));
+            c->stats.n_launches += 1;
+            tb = te;
+        }
         CK(launch_bin_scan(d_tot, T, d_start, d_cur, d_ktot, s));
         CK(cudaMemcpyAsync(hm + 0, d_start + T, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(hm + 2, d_runcur, 16, cudaMemcpyDeviceToHost, s));   // run cursor, k-mer total
+        hm[5] = 0;
+        if (c->d_in_flags) CK(cudaMemcpyAsync(hm + 5, c->d_in_flags, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        c->stats.n_launches += 2;
+        c->stats.n_launches += 1;
+        g_trace.mark("pass A + bin scan done (host sync)");
+        if (hm[5] & 1) return fail("a read is longer than 2^32-1 bases");
+        if (hm[5] & 2) return fail("DnaBuffer size %llu does not match the read lengths", (unsigned long long)nbytes);
         if (hm[2] <= run_cap) break;
         if (attempt) return fail("internal: run list overflow after resize");
         run_cap = nslots + 1024;   // pathological input (runs shorter than 3 k-mers on average): worst-case list
     }
+    P.tile_begin = 0; P.tile_end = P.ntiles;
+    P.tiles_per_warp = (u32)((P.ntiles + nwarps - 1) / nwarps);
     const u64 S = hm[0];
     CK(c->d_slots.ensure((S + 4) * (size_t)SW * 4));
     if (P.ntiles) CK(launch_supermer_scatter(P, nctas, c->nwords, ext, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_cur,
                                              c->d_slots.as<u32>(), s));
     c->end(c->ev_extract);
+    g_trace.mark("scatter enqueued");
     c->stats.n_launches += 1;
     c->stats.n_supermers = S;
     c->stats.supermer_bytes = S * (u64)SW * 4;
@@ -468,7 +534,6 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     const int NW = c->nwords;
     const bool ext = c->cfg.ext != 0;
     if (G > BN_MAX_SRC) return fail("more than %d ranks are not supported yet", BN_MAX_SRC);
-    c->ev_used = 0;
     c->ev_extract.clear(); c->ev_exchange.clear(); c->ev_expand.clear(); c->ev_sort.clear(); c->ev_count.clear(); c->ev_pass.clear();
     c->ev_bins.clear();
     hsk_stats keep = c->stats;
@@ -500,7 +565,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     BinParams BP;
     memset(&BP, 0, sizeof(BP));
     BP.k = c->cfg.k; BP.lower = (u32)c->cfg.lower; BP.upper = (u32)c->cfg.upper;
-    BP.nbins = TG; BP.nsrc = G;
+    BP.nbins = TG; BP.bin_lo = 0; BP.bin_hi = TG; BP.nsrc = G;
     c->rbase_idx.assign(G, 0);
     u64 owned = 0;
 
@@ -570,7 +635,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     const size_t hist_bins = (size_t)c->cfg.upper + 1;
     CK(c->d_hist.ensure(hist_bins * 8));
     CK(cudaMemsetAsync(c->d_hist.p, 0, hist_bins * 8, s));
-    CK(c->d_lb.ensure(((size_t)6 * TG + 8) * 8 + ((size_t)2 * TG + 8) * 4));
+    CK(c->d_lb.ensure(((size_t)6 * TG + 8) * 8 + ((size_t)3 * TG + 16) * 4));
     BP.st_words = c->d_swords.as<u64>(); BP.st_cnt = c->d_scnt.as<u32>();
     BP.st_pos = c->d_spos.as<u32>(); BP.st_rid = c->d_srid.as<int>();
     BP.stage_cursor = d_stagecur;
@@ -580,13 +645,88 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     BP.histogram = c->d_hist.as<u64>(); BP.cursor = d_cursor;
     BP.ticket = d_ticket; BP.ovf_count = d_ovfc;
     BP.ovf_list = reinterpret_cast<u32 *>(BP.fin + (size_t)2 * TG + 8);
-    BP.big_list = BP.ovf_list + TG + 4; BP.big_count = d_bigc;
+    u32 *const big_base = BP.ovf_list + TG + 4, *const mid_base = big_base + TG + 4;
+    BP.big_list = big_base; BP.big_count = d_bigc; BP.mid_list = mid_base; BP.mid_count = d_bigc; BP.snap = nullptr;
 
-    // ---- stages 4+5 on chip
-    c->begin(c->ev_bins);
-    CK(launch_bin_count(BP, NW, ext, c->sm_count, s));
-    c->end(c->ev_bins);
-    c->stats.n_launches += 4;
+    // ---- stages 4+5 on chip, in groups of bins.  hsk_count streams every group's part of the arena to the host
+    //      while the next group is counted; hsk_count_device runs one group.
+    int NG = (c->stream_result && TG >= 2048) ? 8 : 1;
+    if (const char *ev = getenv("HSK_GROUPS")) { const int v = atoi(ev); if (v >= 1 && v <= 8 && c->stream_result) NG = v; }
+    CK(c->d_grp.ensure((size_t)NG * 16));
+    CK(c->h_grp.ensure((size_t)NG * 32));
+    CK(cudaMemsetAsync(c->d_grp.p, 0, (size_t)NG * 16, s));
+    const size_t hist_bytes = hist_bins * 8;
+    u64 sent_kept = 0, sent_occ = 0;
+    cudaEvent_t ev_grp[8], ev_d0 = nullptr, ev_d1 = nullptr;
+    if (c->stream_result) { ev_d0 = c->ev(); ev_d1 = c->ev(); CK(cudaEventRecord(ev_d0, c->copy_stream)); }
+    // copy arena entries [sent_kept, kept_end) / occurrences [sent_occ, occ_end) once `ready` has fired
+    auto send_result = [&](u64 kept_end, u64 occ_end, u64 kept_total_hint, cudaEvent_t ready) -> int {
+        const u64 want = std::max<u64>(kept_end, kept_total_hint) + 1;
+        if (want * NW * 8 > c->h_owords.cap || want * 4 > c->h_ocnt.cap || (ext && (want + 1) * 8 > c->h_oocc_off.cap)) {
+            CK(cudaStreamSynchronize(c->copy_stream));
+            CK(c->h_owords.ensure_keep(want * NW * 8, sent_kept * NW * 8));
+            CK(c->h_ocnt.ensure_keep(want * 4, sent_kept * 4));
+            if (ext) CK(c->h_oocc_off.ensure_keep((want + 1) * 8, sent_kept * 8));
+        }
+        if (ext && ((occ_end + 1) * 4 > c->h_opos.cap)) {
+            const u64 wo = occ_end + (kept_end ? (u64)((double)occ_end / (double)kept_end * (double)(want - kept_end)) : 0) + 1;
+            CK(cudaStreamSynchronize(c->copy_stream));
+            CK(c->h_opos.ensure_keep(wo * 4, sent_occ * 4));
+            CK(c->h_orid.ensure_keep(wo * 4, sent_occ * 4));
+        }
+        cudaStream_t cs = c->copy_stream;
+        CK(cudaStreamWaitEvent(cs, ready, 0));
+        const u64 nk = kept_end - sent_kept, no = occ_end - sent_occ;
+        if (nk) {
+            CK(cudaMemcpyAsync(c->h_owords.as<u64>() + sent_kept * NW, c->d_owords.as<u64>() + sent_kept * NW, nk * NW * 8, cudaMemcpyDeviceToHost, cs));
+            CK(cudaMemcpyAsync(c->h_ocnt.as<u32>() + sent_kept, c->d_ocnt.as<u32>() + sent_kept, nk * 4, cudaMemcpyDeviceToHost, cs));
+            if (ext) CK(cudaMemcpyAsync(c->h_oocc_off.as<u64>() + sent_kept, c->d_oocc_off.as<u64>() + sent_kept, nk * 8, cudaMemcpyDeviceToHost, cs));
+        }
+        if (ext && no) {
+            CK(cudaMemcpyAsync(c->h_opos.as<u32>() + sent_occ, c->d_opos.as<u32>() + sent_occ, no * 4, cudaMemcpyDeviceToHost, cs));
+            CK(cudaMemcpyAsync(c->h_orid.as<int>() + sent_occ, c->d_orid.as<int>() + sent_occ, no * 4, cudaMemcpyDeviceToHost, cs));
+        }
+        sent_kept = kept_end; sent_occ = occ_end;
+        return 0;
+    };
+    // h_grp[4g..4g+2] = arena cursor (entries, occurrences) after group g, number of its big bins.
+    // Bins with too many kept k-mers for the small gather are rare: their gather is launched only when the group
+    // reports some, one group late, and the group's copy waits for it.
+    auto group_params = [&](int g) {
+        BP.bin_lo = (u32)((u64)TG * g / NG); BP.bin_hi = (u32)((u64)TG * (g + 1) / NG);
+        BP.ticket = c->d_grp.as<u32>() + 4 * g; BP.mid_count = BP.ticket + 1; BP.big_count = BP.ticket + 2;
+        BP.mid_list = mid_base + BP.bin_lo; BP.big_list = big_base + BP.bin_lo;
+        BP.snap = c->h_grp.as<u64>() + 4 * g;
+    };
+    auto flush_group = [&](int g) -> int {
+        CK(cudaEventSynchronize(ev_grp[g]));
+        g_trace.mark("bin group done");
+        const u64 kept_end = c->h_grp.as<u64>()[4 * g], occ_end = c->h_grp.as<u64>()[4 * g + 1];
+        cudaEvent_t ready = ev_grp[g];
+        if ((u32)c->h_grp.as<u64>()[4 * g + 2]) {
+            group_params(g);
+            CK(launch_bin_gather_big(BP, NW, ext, c->sm_count, s));
+            c->stats.n_launches += 1;
+            ready = c->ev();
+            CK(cudaEventRecord(ready, s));
+        }
+        if (!c->stream_result) return 0;
+        // size the host buffers for the whole result from the groups seen so far
+        const u64 hint = (u64)((double)kept_end * (double)NG / (double)(g + 1) * 1.15) + 4096;
+        return send_result(kept_end, occ_end, hint, ready);
+    };
+    for (int g = 0; g < NG; ++g) {
+        group_params(g);
+        c->begin(c->ev_bins);
+        CK(launch_bin_count(BP, NW, ext, c->sm_count, s));
+        c->end(c->ev_bins);
+        c->stats.n_launches += 3;
+        c->stats.n_launches += 1;
+        ev_grp[g] = c->ev();
+        CK(cudaEventRecord(ev_grp[g], s));
+        if (g > 0 && flush_group(g - 1)) return 1;   // the host waits one group behind the GPU
+    }
+    if (flush_group(NG - 1)) return 1;
     c->stats.n_batches = 1;
     CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -617,6 +757,18 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     if (ext) {   // closing offset of the occurrence lists
         CK(cudaMemcpyAsync(c->d_oocc_off.as<u64>() + c->n_kept, c->h_cursor.as<u64>() + 1, 8, cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
+    }
+    if (c->stream_result) {
+        // what the HBM path appended, the histogram, and the end of the copies
+        if (send_result(c->n_kept, c->n_occ, c->n_kept, ev_t1)) return 1;
+        CK(c->h_hist.ensure(hist_bytes));
+        CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, hist_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaEventRecord(ev_d1, c->copy_stream));
+        g_trace.mark("last copies enqueued");
+        CK(cudaStreamSynchronize(c->copy_stream));
+        g_trace.mark("copies done");
+        if (ext) c->h_oocc_off.as<u64>()[c->n_kept] = c->n_occ;
+        CK(cudaEventElapsedTime(&c->stats.ms_d2h, ev_d0, ev_d1));
     }
     c->stats.ms_extract = hsk_ctx::sum_ms(c->ev_extract);
     c->stats.ms_exchange = hsk_ctx::sum_ms(c->ev_exchange);
@@ -650,6 +802,9 @@ int hsk_count_device(hsk_ctx *c, const uint8_t *d_packed, uint64_t nbytes, const
     if (!c || !out) return fail("hsk_count_device: null argument");
     if (((uintptr_t)d_packed & 15) != 0) return fail("hsk_count_device: d_packed must be 16-byte aligned");
     c->stats.ms_h2d = 0;
+    c->ev_used = 0;
+    c->in_chunks.clear();
+    c->d_in_flags = nullptr;
     if (count_device(c, d_packed, nbytes, (nbytes + 15) & ~15ull, (const u64 *)d_read_off, d_read_len, nreads, readid_base)) return 1;
     fill_device_result(c, out);
     return 0;
@@ -702,36 +857,45 @@ int hsk_fetch_result(hsk_ctx *c, hsk_result *out)
     return 0;
 }
 
-// host -> device staging of a DnaBuffer: bytes as they are, byte offsets of the reads, 32-bit lengths
+// host -> device staging of a DnaBuffer.  The 64-bit read lengths go up as they are and reads.cu turns them into
+// byte offsets + 32-bit lengths on the device; the packed bytes go up in chunks on the copy stream, every chunk
+// with an event and the number of extraction tiles it completes, so that pass A of the extraction starts on the
+// first chunk while the others are still on the bus.
 static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads)
 {
     CK(cudaSetDevice(c->cfg.device));
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->stream, cs = c->copy_stream;
     const u64 padded = ((nbytes + 15) & ~15ull) + 64;
     CK(c->d_packed.ensure(padded));
-    CK(c->d_read_off.ensure((nreads + 1) * 8));
-    CK(c->d_read_len.ensure((nreads + 1) * 4));
-    CK(c->h_read_off.ensure((nreads + 1) * 8));
-    CK(c->h_read_len.ensure((nreads + 1) * 4));
-    u64 *off = c->h_read_off.as<u64>();
-    u32 *len = c->h_read_len.as<u32>();
-    u64 acc = 0;
-    for (u64 i = 0; i < nreads; ++i) {
-        if (read_len[i] > 0xFFFFFFFFull) return fail("read %llu longer than 2^32-1 bases", (unsigned long long)i);
-        off[i] = acc; len[i] = (u32)read_len[i];
-        acc += (read_len[i] + 3) / 4;
-    }
-    off[nreads] = acc;
-    if (acc != nbytes) return fail("DnaBuffer size %llu does not match the read lengths (%llu bytes)", (unsigned long long)nbytes, (unsigned long long)acc);
+    CK(c->d_len64.ensure((nreads + 1) * 8));
+    CK(c->d_read_off.ensure((nreads + 2) * 8));
+    CK(c->d_read_len.ensure((nreads + 2) * 4));
+    const size_t rts = read_table_scratch_bytes(nreads);
+    CK(c->d_rtscratch.ensure(rts + 16));
+    c->d_in_flags = reinterpret_cast<u32 *>(c->d_rtscratch.as<u8>() + rts);
+    CK(cudaMemsetAsync(c->d_in_flags, 0, 16, s));
+    if (nreads) CK(cudaMemcpyAsync(c->d_len64.p, read_len, nreads * 8, cudaMemcpyHostToDevice, s));
+    CK(launch_read_table(c->d_len64.as<u64>(), nreads, nbytes, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(),
+                         c->d_rtscratch.as<u64>(), c->d_in_flags, s));
+    c->stats.n_launches += 3;
+
+    const u32 OL = (u32)xt_out_lanes(c->cfg.k - c->m_eff + 1);
+    c->in_chunks.clear();
     cudaEvent_t e0 = c->ev(), e1 = c->ev();
-    CK(cudaEventRecord(e0, s));
-    CK(cudaMemsetAsync(c->d_packed.as<u8>() + (nbytes & ~15ull), 0, padded - (nbytes & ~15ull), s));
-    if (nbytes) CK(cudaMemcpyAsync(c->d_packed.p, packed, nbytes, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->d_read_off.p, off, (nreads + 1) * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->d_read_len.p, len, (nreads + 1) * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaEventRecord(e1, s));
-    CK(cudaStreamSynchronize(s));
-    CK(cudaEventElapsedTime(&c->stats.ms_h2d, e0, e1));
+    CK(cudaEventRecord(e0, cs));
+    CK(cudaMemsetAsync(c->d_packed.as<u8>() + (nbytes & ~15ull), 0, padded - (nbytes & ~15ull), cs));
+    u64 chunk = std::min<u64>(std::max<u64>((nbytes / 8 + 4095) & ~4095ull, 2ull << 20), 256ull << 20);
+    for (u64 o = 0; o < nbytes; o += chunk) {
+        const u64 n = std::min<u64>(chunk, nbytes - o);
+        CK(cudaMemcpyAsync(c->d_packed.as<u8>() + o, packed + o, n, cudaMemcpyHostToDevice, cs));
+        cudaEvent_t ev = c->ev();
+        CK(cudaEventRecord(ev, cs));
+        const u64 words = (o + n) / 4;   // a tile reads 34 words from its first one
+        c->in_chunks.push_back({words >= 34 ? (words - 34) / OL + 1 : 0, ev});
+    }
+    CK(cudaEventRecord(e1, cs));
+    // ms_h2d is read after the call has synchronised
+    c->ev_h2d[0] = e0; c->ev_h2d[1] = e1;
     return 0;
 }
 
@@ -741,12 +905,36 @@ int hsk_count(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t
     if (!c || !out) return fail("hsk_count: null argument");
     if (nreads && (!read_len)) return fail("hsk_count: null read_len");
     c->ev_used = 0;
+    hsk_stats keep;
+    memset(&keep, 0, sizeof(keep));
+    c->stats = keep;
+    g_trace.start();
+    g_trace.mark("hsk_count begin");
     if (stage_input(c, packed, nbytes, read_len, nreads)) return 1;
-    const float h2d = c->stats.ms_h2d;
-    if (count_device(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(), nreads,
-                     readid_base)) return 1;
-    c->stats.ms_h2d = h2d;
-    return hsk_fetch_result(c, out);
+    g_trace.mark("input copies enqueued");
+    const u64 staged_launches = c->stats.n_launches;
+    c->stream_result = true;
+    const int rc = count_device(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(),
+                                c->d_read_len.as<u32>(), nreads, readid_base);
+    c->stream_result = false;
+    c->in_chunks.clear();
+    c->d_in_flags = nullptr;
+    if (rc) { cudaStreamSynchronize(c->copy_stream); return 1; }
+    g_trace.mark("hsk_count end");
+    c->stats.n_launches += staged_launches;
+    CK(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_h2d[0], c->ev_h2d[1]));
+    const bool ext = c->cfg.ext != 0;
+    out->nwords = c->nwords;
+    out->n_kept = c->n_kept;
+    out->n_occ = c->n_occ;
+    out->kmer_words = c->h_owords.as<uint64_t>();
+    out->cnt = c->h_ocnt.as<u32>();
+    out->occ_off = ext ? c->h_oocc_off.as<uint64_t>() : nullptr;
+    out->pos = ext ? c->h_opos.as<u32>() : nullptr;
+    out->rid = ext ? c->h_orid.as<int32_t>() : nullptr;
+    out->histogram = c->h_hist.as<uint64_t>();
+    out->stats = c->stats;
+    return 0;
 }
 
 int hsk_allreduce_histogram(hsk_ctx *c, uint64_t *hist)
@@ -821,7 +1009,9 @@ int hsk_debug_extract(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const 
     c->ev_extract.clear();
     if (stage_input(c, packed, nbytes, read_len, nreads)) return 1;
     if (run_extract(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(), nreads,
-                    readid_base, true)) return 1;
+                    readid_base, true)) { c->in_chunks.clear(); c->d_in_flags = nullptr; cudaStreamSynchronize(c->copy_stream); return 1; }
+    c->in_chunks.clear();
+    c->d_in_flags = nullptr;
     const u32 T = c->tt;
     const int SW = slot_words(c->nwords, c->cfg.ext != 0);
     const u64 *hb = c->h_bucket.as<u64>();

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(XT_THREADS, XT_CTAS_PER_SM) k_supermer_count(E
     __shared__ u16 s_pos[XT_WARPS][OUT + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 gw = (u64)blockIdx.x * XT_WARPS + warp;
-    const u64 t0 = gw * P.tiles_per_warp, t1 = min(t0 + P.tiles_per_warp, P.ntiles);
+    const u64 t0 = P.tile_begin + gw * P.tiles_per_warp, t1 = min(t0 + P.tiles_per_warp, P.tile_end);
     const u32 *packed32 = reinterpret_cast<const u32 *>(P.packed);
     const u64 nwords_readable = P.nbytes_padded >> 2;
     const int m = P.m;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_supermer_scatter(ExtractParams P
     __shared__ u32 s_w[XT_WARPS][XT_STAGE_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 gw = (u64)blockIdx.x * XT_WARPS + warp;
-    const u64 t0 = gw * P.tiles_per_warp, t1 = min(t0 + P.tiles_per_warp, P.ntiles);
+    const u64 t0 = P.tile_begin + gw * P.tiles_per_warp, t1 = min(t0 + P.tiles_per_warp, P.tile_end);
     const u32 *packed32 = reinterpret_cast<const u32 *>(P.packed);
     const u64 nwords_readable = P.nbytes_padded >> 2;
     const u32 OL = P.out_slots / XT_R;

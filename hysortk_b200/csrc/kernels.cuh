@@ -4,6 +4,13 @@
 
 namespace hsk {
 
+// ---- read table: reads.cu ---------------------------------------------------------------------------
+size_t read_table_scratch_bytes(u64 nreads);
+// read_off[nreads+1] / read_len[nreads] from 64-bit lengths; flags bit 0: a read longer than 2^32-1 bases, bit 1: the
+// lengths do not add up to nbytes
+cudaError_t launch_read_table(const u64 *len64, u64 nreads, u64 nbytes, u64 *read_off, u32 *read_len, u64 *scratch, u32 *flags,
+                              cudaStream_t s);
+
 // ---- stage 1+2: extract.cu -----------------------------------------------------------------------
 struct ExtractParams {
     const u8 *packed;        // DnaBuffer bytes on the device, 16-byte aligned
@@ -13,6 +20,7 @@ struct ExtractParams {
     const u32 *read_len;     // nreads lengths in bases
     u64 nreads;
     u64 ntiles;              // warp tiles of out_slots k-mer start slots each
+    u64 tile_begin, tile_end;   // tiles of this launch
     u32 tiles_per_warp;
     u32 out_slots;           // xt_out_slots(k - m + 1)
     const u32 *tile_read;    // ntiles+1: read holding the first byte of every tile (k_tile_reads)
@@ -59,6 +67,7 @@ struct BinParams {
     int k;
     u32 lower, upper;
     u32 nbins;                           // owned bins, local index 0..nbins-1
+    u32 bin_lo, bin_hi;                  // bins of this launch group
     int nsrc;
     const u32 *slots[BN_MAX_SRC];        // supermer slot stream per source rank
     const u64 *seg_start[BN_MAX_SRC];    // nbins+1: first slot of every bin inside the source's stream
@@ -74,12 +83,16 @@ struct BinParams {
     u64 *cursor;                         // [0] entries, [1] occurrences in the arena: advanced by k_bin_offsets
     u32 *ticket;                         // zeroed
     u32 *ovf_list, *ovf_count;           // bins left to the HBM path
-    u32 *big_list, *big_count;           // bins with more kept k-mers than the small gather handles
+    u32 *mid_list, *mid_count;           // bins with 513..1024 kept k-mers (mid gather)
+    u32 *big_list, *big_count;           // bins with more (big gather, launched only when there are some)
+    u64 *snap;                           // page-locked host memory or null: {entries, occurrences, big bins} after the group
 };
 
 int bin_target_kmers(int nwords, bool ext);  // k-mer occurrences per bin the on-chip path is sized for
-// k_bin_count + k_bin_offsets + k_bin_gather (x2)
+// k_bin_count + k_bin_offsets + k_bin_gather_small over the bins [bin_lo, bin_hi)
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
+// k_bin_gather over the group's big_list; needed only when *big_count != 0
+cudaError_t launch_bin_gather_big(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
 // multi-rank: segment tables of the owned bins inside the per-source streams + send/recv sizes (meta)
 cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start, u64 *seg_start,
                             u64 *meta, u64 *bin_kmers, u64 *owned_total, cudaStream_t s);
