@@ -44,7 +44,7 @@
 namespace hsk {
 
 constexpr int BN_WARPS = BN_THREADS / 32;
-constexpr int BN_HCAP = 256;                   // shared-memory histogram bins (larger counts go to the global histogram)
+constexpr int BN_HCAP = 128;                   // shared-memory histogram bins (larger counts go to the global histogram)
 constexpr u64 BN_EMPTY = ~0ull;                // never a canonical k-mer: a K-mer of all T is not canonical
 constexpr u32 BN_EMPTY32 = 0xFFFFFFFFu;        // K > 32: state of a fingerprint cell
 constexpr u32 BN_LOCK32 = 0xFFFFFFFEu;         //          claimed, key words not yet written
@@ -73,23 +73,48 @@ int bin_target_kmers(int nwords, bool ext)
     return BinCfg<3, false>::TARGET;
 }
 
+constexpr int BN_SORTCAP = 2 * BN_THREADS;      // kept k-mers a CTA sorts itself (two per thread); more: staging + big gather
+
+// scratch of a CTA, used by the walk (staged slots, scan, slot-start bitmap of every warp) and then by the sort of
+// the kept k-mers (exchange buffers; the compacted slot list sits at their start until it has been consumed)
+template <int NW, bool EXT>
+struct BinScratchCfg {
+    using Cfg = BinCfg<NW, EXT>;
+    static constexpr int STG_U4 = 32 * Cfg::SW / 4 + 2;                       // uint4 per warp (+ pad)
+    static constexpr size_t WALK = (size_t)BN_WARPS * (STG_U4 * 16 + 32 * 2 + Cfg::HEADW * 4);
+    static constexpr size_t SORT = (size_t)BN_SORTCAP * (8 * NW + 4);
+    static constexpr size_t BYTES = (WALK > SORT ? WALK : SORT + 15) / 16 * 16;
+};
+
 template <int NW, bool EXT>
 struct BinSmem {
     using Cfg = BinCfg<NW, EXT>;
-    alignas(16) u64 fp[NW == 1 ? Cfg::TS : 1];                          // K <= 32: the k-mer itself is the CAS key
+    using Scr = BinScratchCfg<NW, EXT>;
+    alignas(16) u64 fp[NW == 1 ? Cfg::TS : 1];              // K <= 32: the k-mer itself is the CAS key
     u64 kw[NW > 1 ? NW : 1][NW > 1 ? Cfg::TS : 1];          // K > 32: full key words ...
-    alignas(16) u32 fp32[NW > 1 ? Cfg::TS : 1];                         //         ... guarded by a 32-bit fingerprint cell
-    alignas(16) u32 cnt[Cfg::TS];                                       // occurrences per slot; EXT pass 2: next occurrence offset
-    alignas(16) uint4 stg[BN_WARPS][32 * Cfg::SW / 4 + 2];              // the warp's batch of 32 supermer slots (+ pad)
-    u16 scan[BN_WARPS][32];                                 // first k-mer of every slot of the batch
-    u32 heads[BN_WARPS][Cfg::HEADW];                        // bit g set: k-mer g of the batch starts a slot
+    alignas(16) u32 fp32[NW > 1 ? Cfg::TS : 1];             //         ... guarded by a 32-bit fingerprint cell
+    alignas(16) u32 cnt[Cfg::TS];                           // occurrences per slot; EXT pass 2: next occurrence offset
+    alignas(16) unsigned char scratch[Scr::BYTES];
     u32 hist[BN_HCAP];
     u16 cand[BN_CAND];                                      // slots whose counter reached LOWER
     const u32 *src_ptr[BN_MAX_SRC];                         // first slot of the bin in every source stream
     u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1];
     u32 wa[BN_WARPS], wb[BN_WARPS];
-    u64 stage_kept, stage_occ;
+    u64 base_k, base_o;                                     // where the bin's entries / occurrences go
+    u32 *occ_pos; int *occ_rid;                             // EXT pass 2 target arrays (arena, or staging for big bins)
     u32 bin, nk, S, bail, next_batch, seen, ncand;
+
+    // walk layout
+    __device__ uint4 *stg(int warp) { return reinterpret_cast<uint4 *>(scratch) + (size_t)warp * Scr::STG_U4; }
+    __device__ u16 *scan(int warp) { return reinterpret_cast<u16 *>(scratch + (size_t)BN_WARPS * Scr::STG_U4 * 16) + warp * 32; }
+    __device__ u32 *heads(int warp)
+    {
+        return reinterpret_cast<u32 *>(scratch + (size_t)BN_WARPS * (Scr::STG_U4 * 16 + 64)) + (size_t)warp * Cfg::HEADW;
+    }
+    // sort layout
+    __device__ u64 *xkey() { return reinterpret_cast<u64 *>(scratch); }                                   // [NW][BN_SORTCAP]
+    __device__ u32 *xpay() { return reinterpret_cast<u32 *>(scratch + (size_t)BN_SORTCAP * 8 * NW); }     // [BN_SORTCAP]
+    __device__ u16 *klist() { return reinterpret_cast<u16 *>(scratch); }                                  // [BN_SORTCAP], before the sort
 };
 
 // block-wide exclusive scan of two u32 values (BN_THREADS threads); returns exclusive prefixes and totals
@@ -215,9 +240,10 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
     using Cfg = BinCfg<NW, EXT>;
     constexpr int SW = Cfg::SW, PW = Cfg::PW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 *stg = reinterpret_cast<u32 *>(sm.stg[warp]);
-    u16 *scan = sm.scan[warp];
-    u32 *heads = sm.heads[warp];
+    uint4 *stg4 = sm.stg(warp);
+    u32 *stg = reinterpret_cast<u32 *>(stg4);
+    u16 *scan = sm.scan(warp);
+    u32 *heads = sm.heads(warp);
     u32 seen = 0;
     while (true) {
         u32 bt = 0;
@@ -231,7 +257,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
 #pragma unroll
             for (int x = 0; x < SW / 4; ++x) {
                 const uint4 v = __ldg(sp + x);
-                sm.stg[warp][lane * (SW / 4) + x] = v;
+                stg4[lane * (SW / 4) + x] = v;
                 if (x == (PW - 1) / 4) {
                     const u32 lw = ((PW - 1) % 4 == 3) ? v.w : ((PW - 1) % 4 == 1 ? v.y : ((PW - 1) % 4 == 2 ? v.z : v.x));
                     n = (lw & 0xFFu) - (u32)k + 1;
@@ -288,9 +314,9 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
                 if (act) slot = table_find<NW, EXT, false>(sm, key);
                 __syncwarp();
                 if (slot < (u32)Cfg::TS && *reinterpret_cast<volatile u32 *>(&sm.cnt[slot]) != BN_NOTKEPT) {
-                    const u64 p = sm.stage_occ + atomicAdd(&sm.cnt[slot], 1u);
-                    P.st_pos[p] = w[SW - 2] + o;
-                    P.st_rid[p] = (int)w[SW - 1];
+                    const u64 p = sm.base_o + atomicAdd(&sm.cnt[slot], 1u);
+                    sm.occ_pos[p] = w[SW - 2] + o;
+                    sm.occ_rid[p] = (int)w[SW - 1];
                 }
             }
         }
@@ -298,6 +324,179 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
         __syncwarp();   // the staging area is reused by the next batch
     }
     if (!PASS2 && lane == 0 && seen) atomicAdd(&sm.seen, seen);
+}
+
+// ---- position of a bin in the arena: decoupled look-back over the bins -------------------------------
+// Bins are taken in index order by CTAs that are all resident, so every bin before `lb` has been started and
+// publishes the number of entries it keeps (AGG) before it waits for anybody; a bin adds up the aggregates
+// behind it until it meets an inclusive prefix (INC) and then publishes its own.
+constexpr u64 LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_VAL = (1ull << 62) - 1;
+
+__device__ __forceinline__ u64 warp_sum64(u64 v)
+{
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+// exclusive prefix over the bins before lb (whole warp; same value in every lane)
+__device__ __forceinline__ u64 lookback(volatile u64 *st, u32 lb)
+{
+    const int lane = threadIdx.x & 31;
+    u64 sum = 0;
+    for (long long j = (long long)lb; j > 0; j -= 32) {
+        const long long idx = j - 1 - lane;
+        u64 v = LB_INC;   // before bin 0: inclusive 0
+        if (idx >= 0) { do { v = st[idx]; } while ((v >> 62) == 0); }
+        const u32 inc = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+        u64 val = v & LB_VAL;
+        if (inc) {
+            if (lane > __ffs(inc) - 1) val = 0;   // nothing behind the nearest inclusive prefix
+            sum += warp_sum64(val);
+            break;
+        }
+        sum += warp_sum64(val);
+    }
+    return sum;
+}
+
+// Bitonic sort of BN_THREADS * EPT elements spread over the CTA (element e = tid * EPT + r): partners inside a
+// thread are exchanged in registers, inside a warp by shuffles, further away through the exchange buffers.
+template <int NW, int EPT>
+__device__ __forceinline__ void block_sort(u64 (&key)[EPT][NW], u32 (&pay)[EPT], u32 n2, u64 *xkey, u32 *xpay)
+{
+    const u32 tid = threadIdx.x;
+    // warps whose elements all lie beyond the network only keep the barriers company.  Keys are distinct except for
+    // the padding (all ones, payload 0), so one comparison decides an exchange: "the partner is smaller" == "I keep
+    // the smaller one".
+    const bool active = tid * EPT < max(n2, 32u * EPT);
+    for (u32 size = 2; size <= n2; size <<= 1) {
+        for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
+            if (EPT == 2 && stride == 1) {
+                const bool asc = ((tid * 2) & size) == 0;
+                if (active && key_less<NW>(key[EPT - 1], key[0]) == asc) {
+#pragma unroll
+                    for (int l = 0; l < NW; ++l) { const u64 t = key[0][l]; key[0][l] = key[EPT - 1][l]; key[EPT - 1][l] = t; }
+                    const u32 t = pay[0]; pay[0] = pay[EPT - 1]; pay[EPT - 1] = t;
+                }
+                continue;
+            }
+            const u32 ts = stride / EPT;   // partner thread distance
+            if (ts >= 32) {
+                __syncthreads();
+                if (active) {
+#pragma unroll
+                    for (int r = 0; r < EPT; ++r) {
+                        const u32 e = tid * EPT + r;
+#pragma unroll
+                        for (int l = 0; l < NW; ++l) xkey[(size_t)l * BN_SORTCAP + e] = key[r][l];
+                        xpay[e] = pay[r];
+                    }
+                }
+                __syncthreads();
+            }
+            if (!active) continue;
+#pragma unroll
+            for (int r = 0; r < EPT; ++r) {
+                const u32 e = tid * EPT + r;
+                u64 pk[NW];
+                u32 pp;
+                if (ts >= 32) {
+                    const u32 j = e ^ stride;
+#pragma unroll
+                    for (int l = 0; l < NW; ++l) pk[l] = xkey[(size_t)l * BN_SORTCAP + j];
+                    pp = xpay[j];
+                } else {
+#pragma unroll
+                    for (int l = 0; l < NW; ++l) pk[l] = __shfl_xor_sync(0xFFFFFFFFu, key[r][l], ts);
+                    pp = __shfl_xor_sync(0xFFFFFFFFu, pay[r], ts);
+                }
+                const bool want_min = ((e & size) == 0) == ((e & stride) == 0);
+                if (key_less<NW>(pk, key[r]) == want_min) {
+#pragma unroll
+                    for (int l = 0; l < NW; ++l) key[r][l] = pk[l];
+                    pay[r] = pp;
+                }
+            }
+        }
+    }
+}
+
+// look-back of one bin (warp 0): arena position -> sm.base_k / sm.base_o, inclusive prefix published
+template <int NW, bool EXT>
+__device__ __forceinline__ void resolve_position(BinSmem<NW, EXT> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
+{
+    if (threadIdx.x < 32) {
+        volatile u64 *lbk = P.lb_state, *lbo = P.lb_state + P.nbins;
+        const u64 exk = lookback(lbk, lb);
+        const u64 exo = EXT ? lookback(lbo, lb) : 0;
+        if (threadIdx.x == 0) {
+            lbk[lb] = LB_INC | (exk + tk);
+            if (EXT) lbo[lb] = LB_INC | (exo + to);
+            sm.base_k = exk; sm.base_o = exo;
+            const u32 g = lb / P.group_bins;
+            if (lb + 1 == P.nbins || (lb + 1) % P.group_bins == 0) { P.grp_end[2 * g] = exk + tk; P.grp_end[2 * g + 1] = exo + to; }
+            if (lb + 1 == P.nbins) { P.cursor[0] = exk + tk; P.cursor[1] = exo + to; }
+        }
+    }
+    __syncthreads();
+}
+
+// The kept k-mers of a bin (slot list in sm.klist(), tk <= BN_THREADS * EPT): sort them, give every one its place
+// in the arena and write (k-mer, count[, occurrence offset]); EXTENSION leaves the occurrence cursors in sm.cnt.
+template <int NW, bool EXT, int EPT>
+__device__ __forceinline__ void sort_emit(BinSmem<NW, EXT> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
+{
+    const u32 tid = threadIdx.x;
+    if (tk == 0) { resolve_position<NW, EXT>(sm, P, lb, 0u, 0u); return; }
+    u64 key[EPT][NW];
+    u32 pay[EPT];   // slot << 16 | count (count <= UPPER <= 65535)
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        const u32 e = tid * EPT + r;
+        if (e < tk) {
+            const u32 slot = sm.klist()[e];
+#pragma unroll
+            for (int l = 0; l < NW; ++l) key[r][l] = NW == 1 ? sm.fp[slot] : sm.kw[l][slot];
+            pay[r] = (slot << 16) | sm.cnt[slot];
+        } else {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) key[r][l] = ~0ull;
+            pay[r] = 0;
+        }
+    }
+    u32 n2 = 2;
+    while (n2 < tk) n2 <<= 1;
+    __syncthreads();   // the slot list has been read: the scratch becomes the exchange buffer
+    block_sort<NW, EPT>(key, pay, n2, sm.xkey(), sm.xpay());
+    u32 off[EPT];
+    if (EXT) {
+        // occurrence lists follow the sorted order: offsets inside the bin, left in the slots' counters as cursors
+        u32 mine = 0;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) { off[r] = mine; mine += pay[r] & 0xFFFFu; }
+        u32 ex, d0, t0, t1;
+        block_scan2(mine, 0u, sm.wa, sm.wb, ex, d0, t0, t1);
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            off[r] += ex;
+            if (tid * EPT + r < tk) sm.cnt[pay[r] >> 16] = off[r];
+        }
+    }
+    resolve_position<NW, EXT>(sm, P, lb, tk, to);
+    const u64 bk = sm.base_k, bo = sm.base_o;
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        const u32 e = tid * EPT + r;
+        if (e < tk) {
+            const u32 c = pay[r] & 0xFFFFu;
+#pragma unroll
+            for (int l = 0; l < NW; ++l) P.out_words[(bk + e) * NW + l] = key[r][l];
+            P.out_cnt[bk + e] = c;
+            if (EXT) P.out_occ_off[bk + e] = bo + off[r];
+            if (c < (u32)BN_HCAP) atomicAdd(&sm.hist[c], 1u); else atomicAdd(&P.histogram[c], 1ull);
+        }
+    }
 }
 
 // One CTA per bin, bins taken in index order through a ticket; a bin of any size is handled as long as its distinct
@@ -317,7 +516,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
 
     while (true) {
         __syncthreads();   // end of the previous bin: shared memory is free again
-        if (tid == 0) { sm.bin = P.bin_lo + atomicAdd(P.ticket, 1u); sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; }
+        if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; }
         {
             const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
             if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
@@ -326,7 +525,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         }
         __syncthreads();
         const u32 lb = sm.bin;
-        if (lb >= P.bin_hi) break;
+        if (lb >= P.nbins) break;
 
         // ---- bin descriptor: one segment of slots per source rank
         if (tid < P.nsrc) {
@@ -352,23 +551,13 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         __syncthreads();
         if (!sm.bail && sm.seen != nk && tid == 0) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
         __syncthreads();
+        const bool bailed = sm.bail != 0;   // the bin goes to the HBM path; it still takes its (empty) place in the chain
 
-        if (sm.bail) {
-            // bin goes to the HBM path
-            if (tid == 0) {
-                P.ovf_list[atomicAdd(P.ovf_count, 1u)] = lb;
-                P.bin_rec[4 * (size_t)lb + 0] = 0; P.bin_rec[4 * (size_t)lb + 1] = 0;
-                P.bin_rec[4 * (size_t)lb + 2] = 0; P.bin_rec[4 * (size_t)lb + 3] = 0;
-            }
-            continue;
-        }
-
-        // ---- filter, compact the kept (k-mer, count) pairs into the staging area.  Usually the candidate list
-        //      (slots that reached LOWER) names the few slots to look at; a bin with more candidates than the
-        //      list holds (LOWER == 1, mostly) scans its whole table.
+        // ---- filter.  Usually the candidate list (slots that reached LOWER) names the few slots to look at; a bin
+        //      with more candidates than the list holds (LOWER == 1, mostly) scans its whole table.
         const u32 ncand = sm.ncand;
         const bool listed = ncand <= (u32)BN_CAND;
-        const u32 per_thread = listed ? (ncand + BN_THREADS - 1) / BN_THREADS : (u32)Cfg::SLOTS_PT;
+        const u32 per_thread = bailed ? 0u : (listed ? (ncand + BN_THREADS - 1) / BN_THREADS : (u32)Cfg::SLOTS_PT);
         u32 kept = 0, occ = 0, keepmask = 0;
         for (u32 i = 0; i < per_thread; ++i) {
             u32 slot = tid * per_thread + i;
@@ -379,17 +568,22 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         }
         u32 ek, eo, tk, to;
         block_scan2(kept, occ, sm.wa, sm.wb, ek, eo, tk, to);
+        if (!EXT) to = 0;
+        const bool big = tk > (u32)BN_SORTCAP;   // too many kept k-mers to sort here: staging area + big gather
         if (tid == 0) {
-            const u64 sk = tk ? atomicAdd(P.stage_cursor, (u64)tk) : 0;
-            const u64 so = (EXT && to) ? atomicAdd(P.stage_cursor + 1, (u64)to) : 0;
-            sm.stage_kept = sk; sm.stage_occ = so;
+            volatile u64 *lbs = P.lb_state;
+            lbs[lb] = LB_AGG | tk;
+            if (EXT) lbs[P.nbins + lb] = LB_AGG | to;
             sm.next_batch = 0;
-            P.bin_rec[4 * (size_t)lb + 0] = sk; P.bin_rec[4 * (size_t)lb + 1] = tk;
-            P.bin_rec[4 * (size_t)lb + 2] = so; P.bin_rec[4 * (size_t)lb + 3] = EXT ? to : 0;
+            if (bailed) P.ovf_list[atomicAdd(P.ovf_count, 1u)] = lb;
+            if (big) {
+                sm.base_k = atomicAdd(P.stage_cursor, (u64)tk);
+                sm.base_o = (EXT && to) ? atomicAdd(P.stage_cursor + 1, (u64)to) : 0;
+            }
         }
-        __syncthreads();
-        if (EXT && listed) {
-            // slots outside the list are not kept: the occurrence pass tells by the mark
+        if (EXT && !bailed && (listed || !big)) {
+            // slots that are not kept: the occurrence pass tells by the mark (kept slots get their cursor below)
+            __syncthreads();
             for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) {
                 uint4 v = reinterpret_cast<uint4 *>(sm.cnt)[i];
                 if (v.x < P.lower || v.x > P.upper) v.x = BN_NOTKEPT;
@@ -398,15 +592,31 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
                 if (v.w < P.lower || v.w > P.upper) v.w = BN_NOTKEPT;
                 reinterpret_cast<uint4 *>(sm.cnt)[i] = v;
             }
-            __syncthreads();
         }
-        {
-            u64 g = sm.stage_kept + ek;
+        __syncthreads();
+        if (!big) {
+            // compacted list of the kept slots, then sort + emit straight into the arena
+            u32 g = ek;
+            for (u32 i = 0; i < per_thread; ++i) {
+                if ((keepmask >> i) & 1) {
+                    u32 slot = tid * per_thread + i;
+                    if (listed) slot = sm.cand[slot];
+                    sm.klist()[g++] = (u16)slot;
+                }
+            }
+            __syncthreads();
+            if (tk <= (u32)BN_THREADS) sort_emit<NW, EXT, 1>(sm, P, lb, tk, to);
+            else sort_emit<NW, EXT, 2>(sm, P, lb, tk, to);
+            if (EXT && tid == 0) { sm.occ_pos = P.out_pos; sm.occ_rid = P.out_rid; }
+        } else {
+            // unsorted into the staging area; the big gather sorts and moves the bin to its place in the arena
+            const u64 sk = sm.base_k, so = sm.base_o;
+            u64 g = sk + ek;
             u32 lo = eo;   // occurrence offset inside the bin
             for (u32 i = 0; i < per_thread; ++i) {
                 u32 slot = tid * per_thread + i;
                 if (listed) slot = slot < ncand ? sm.cand[slot] : 0u;
-                u32 mark = BN_NOTKEPT;   // "not kept" for the occurrence pass
+                u32 mark = BN_NOTKEPT;
                 if ((keepmask >> i) & 1) {
                     const u32 c = sm.cnt[slot];
                     if (NW == 1) P.st_words[g] = sm.fp[slot];
@@ -422,70 +632,43 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
                 }
                 if (EXT && (!listed || ((keepmask >> i) & 1))) sm.cnt[slot] = mark;
             }
+            __syncthreads();
+            resolve_position<NW, EXT>(sm, P, lb, tk, to);   // sm.base_k / base_o: now the place in the arena
+            if (tid == 0) {
+                P.bin_rec[4 * (size_t)lb + 0] = sk; P.bin_rec[4 * (size_t)lb + 1] = tk;
+                P.bin_rec[4 * (size_t)lb + 2] = so; P.bin_rec[4 * (size_t)lb + 3] = to;
+                P.fin[2 * (size_t)lb] = sm.base_k; P.fin[2 * (size_t)lb + 1] = sm.base_o;
+                P.big_list[atomicAdd(P.big_count, 1u)] = lb;
+                atomicAdd(&P.grp_big[lb / P.group_bins], 1u);
+                sm.base_o = so;   // pass 2 writes the occurrences to the staging area
+                sm.occ_pos = P.st_pos; sm.occ_rid = P.st_rid;
+            }
         }
         if (EXT) {
             // ---- occurrences: (pos, rid) of every occurrence of a kept k-mer, grouped per k-mer
             __syncthreads();
             if (to) walk_bin<NW, EXT, true>(sm, P, k, padbits, S);
         }
+
+        // ---- the bin is in the arena: group bookkeeping for the host that streams the result out
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const u32 g = lb / P.group_bins;
+            const u32 gsize = min(P.group_bins, P.nbins - g * P.group_bins);
+            if (atomicAdd(&P.grp_done[g], 1u) + 1 == gsize && P.snap) {
+                __threadfence();
+                volatile u64 *sn = P.snap + 4 * (size_t)g;
+                sn[0] = P.grp_end[2 * g]; sn[1] = P.grp_end[2 * g + 1]; sn[2] = P.grp_big[g];
+                __threadfence_system();
+                sn[3] = 1;
+            }
+        }
     }
 
     __syncthreads();
     for (int i = tid; i < BN_HCAP; i += BN_THREADS)
         if (sm.hist[i]) atomicAdd(&P.histogram[i], (u64)sm.hist[i]);
-}
-
-// ---- final positions of the bins: exclusive scan of (kept, occurrences) over the bins; one block ----
-__global__ void __launch_bounds__(1024) k_bin_offsets(const u64 *__restrict__ bin_rec, u32 bin_lo, u32 nbins, u64 *__restrict__ fin,
-                                                       u64 *__restrict__ cursor, u32 mid_from, u32 big_from,
-                                                       u32 *__restrict__ mid_list, u32 *__restrict__ mid_count,
-                                                       u32 *__restrict__ big_list, u32 *__restrict__ big_count,
-                                                       volatile u64 *snap)
-{
-    __shared__ u64 s_a[32], s_b[32];
-    __shared__ u64 carry_a, carry_b;
-    if (threadIdx.x == 0) { carry_a = cursor[0]; carry_b = cursor[1]; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u32 base = bin_lo; base < nbins; base += 1024) {
-        const u32 b = base + threadIdx.x;
-        u64 x = 0, y = 0;
-        if (b < nbins) { x = bin_rec[4 * (size_t)b + 1]; y = bin_rec[4 * (size_t)b + 3]; }
-        if (x > (u64)big_from) big_list[atomicAdd(big_count, 1u)] = b;        // handled by the large gather launch
-        else if (x > (u64)mid_from) mid_list[atomicAdd(mid_count, 1u)] = b;   // by the mid gather
-        u64 ix = x, iy = y;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u64 p = __shfl_up_sync(0xFFFFFFFFu, ix, d);
-            u64 q = __shfl_up_sync(0xFFFFFFFFu, iy, d);
-            if (lane >= d) { ix += p; iy += q; }
-        }
-        if (lane == 31) { s_a[warp] = ix; s_b[warp] = iy; }
-        __syncthreads();
-        if (warp == 0) {
-            u64 p = s_a[lane], q = s_b[lane], ip = p, iq = q;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u64 u = __shfl_up_sync(0xFFFFFFFFu, ip, d);
-                u64 v = __shfl_up_sync(0xFFFFFFFFu, iq, d);
-                if (lane >= d) { ip += u; iq += v; }
-            }
-            s_a[lane] = ip - p; s_b[lane] = iq - q;
-        }
-        __syncthreads();
-        const u64 ex = carry_a + s_a[warp] + ix - x, ey = carry_b + s_b[warp] + iy - y;
-        if (b < nbins) { fin[2 * (size_t)b] = ex; fin[2 * (size_t)b + 1] = ey; }
-        __syncthreads();
-        if (threadIdx.x == 1023) { carry_a = ex + x; carry_b = ey + y; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        cursor[0] = carry_a; cursor[1] = carry_b;
-        if (snap) {   // page-locked host memory: the host reads it after the event that follows this group
-            snap[0] = carry_a; snap[1] = carry_b; snap[2] = *big_count;
-            __threadfence_system();
-        }
-    }
 }
 
 // ---- per bin: sort the kept k-mers by key and move them (and their occurrences) to the arena ----------
@@ -603,195 +786,6 @@ __global__ void __launch_bounds__(THREADS) k_bin_gather(BinParams P)
   }
 }
 
-// ---- the usual bins (<= 512 kept k-mers): bitonic sort held in registers -----------------------------
-// 128 threads x EPT elements (element i = tid * EPT + r).  Compare-exchange partners at distance < EPT are in
-// the same thread, at thread distance < 32 they are reached with warp shuffles, and only the last stages
-// (thread distance >= 32) go through shared memory: 3 of the 45 stages of a 512-element sort.
-constexpr int GS_THREADS = 128;
-constexpr int GS_EPT = 4;                          // most entries per thread of the small gather: 512 kept k-mers
-constexpr int GM_EPT = 8;                          // the mid gather (listed bins): up to 1024
-
-template <int NW, int EPTMAX = GS_EPT>
-struct GsSmem {
-    u64 key[NW][GS_THREADS * EPTMAX];
-    u32 cnt[GS_THREADS * EPTMAX], src[GS_THREADS * EPTMAX];
-    u32 warp[GS_THREADS / 32];
-};
-
-// block exclusive scan of one u32 per thread (GS_THREADS threads)
-__device__ __forceinline__ u32 gs_scan(u32 v, u32 *warp_tot, u32 &total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    __syncthreads();
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    u32 off = 0;
-    total = 0;
-#pragma unroll
-    for (int w = 0; w < GS_THREADS / 32; ++w) { if (w < warp) off += warp_tot[w]; total += warp_tot[w]; }
-    return off + inc - v;
-}
-
-template <int NW, bool EXT, int EPT, typename SM>
-__device__ __forceinline__ void gather_small(const BinParams &P, SM &sm, u32 lb, u32 D, u64 sk, u64 so, u64 fk, u64 fo)
-{
-    constexpr int N = GS_THREADS * EPT;
-    const int tid = threadIdx.x;
-    u64 key[EPT][NW];
-    u32 cnt[EPT], src[EPT];
-    // load my EPT consecutive entries (padding sorts last)
-    u32 mysum = 0;
-#pragma unroll
-    for (int r = 0; r < EPT; ++r) {
-        const u32 i = tid * EPT + r;
-        if (i < D) {
-#pragma unroll
-            for (int l = 0; l < NW; ++l) key[r][l] = P.st_words[(sk + i) * NW + l];
-            cnt[r] = P.st_cnt[sk + i];
-        } else {
-#pragma unroll
-            for (int l = 0; l < NW; ++l) key[r][l] = ~0ull;
-            cnt[r] = 0;
-        }
-        src[r] = mysum;
-        mysum += cnt[r];
-    }
-    if (EXT) {   // occurrence start of every entry in staging order
-        u32 tot;
-        const u32 ex = gs_scan(mysum, sm.warp, tot);
-#pragma unroll
-        for (int r = 0; r < EPT; ++r) src[r] += ex;
-    }
-
-#pragma unroll
-    for (int size = 2; size <= N; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride < EPT) {
-#pragma unroll
-                for (int r = 0; r < EPT; ++r) {
-                    const int pr = r ^ stride;
-                    if (pr > r) {
-                        const bool asc = (((tid * EPT + r) & size) == 0);
-                        const bool sw = asc ? key_less<NW>(key[pr], key[r]) : key_less<NW>(key[r], key[pr]);
-                        if (sw) {
-#pragma unroll
-                            for (int l = 0; l < NW; ++l) { const u64 t = key[r][l]; key[r][l] = key[pr][l]; key[pr][l] = t; }
-                            const u32 c = cnt[r]; cnt[r] = cnt[pr]; cnt[pr] = c;
-                            if (EXT) { const u32 x = src[r]; src[r] = src[pr]; src[pr] = x; }
-                        }
-                    }
-                }
-            } else {
-                const int ts = stride / EPT;   // partner thread distance
-                if (ts >= 32) {
-                    __syncthreads();
-#pragma unroll
-                    for (int r = 0; r < EPT; ++r) {
-                        const int i = tid * EPT + r;
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) sm.key[l][i] = key[r][l];
-                        sm.cnt[i] = cnt[r];
-                        if (EXT) sm.src[i] = src[r];
-                    }
-                    __syncthreads();
-                }
-#pragma unroll
-                for (int r = 0; r < EPT; ++r) {
-                    const int i = tid * EPT + r;
-                    u64 pk[NW];
-                    u32 pc, ps = 0;
-                    if (ts >= 32) {
-                        const int j = i ^ stride;
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) pk[l] = sm.key[l][j];
-                        pc = sm.cnt[j];
-                        if (EXT) ps = sm.src[j];
-                    } else {
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) pk[l] = __shfl_xor_sync(0xFFFFFFFFu, key[r][l], ts);
-                        pc = __shfl_xor_sync(0xFFFFFFFFu, cnt[r], ts);
-                        if (EXT) ps = __shfl_xor_sync(0xFFFFFFFFu, src[r], ts);
-                    }
-                    const bool asc = ((i & size) == 0), lower = ((i & stride) == 0);
-                    const bool want_min = (lower == asc);
-                    const bool take = want_min ? key_less<NW>(pk, key[r]) : key_less<NW>(key[r], pk);
-                    if (take) {
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) key[r][l] = pk[l];
-                        cnt[r] = pc;
-                        if (EXT) src[r] = ps;
-                    }
-                }
-            }
-        }
-    }
-
-    // write in sorted order; occurrence offsets = exclusive scan of the counts in sorted order
-    u32 dst[EPT], s2 = 0;
-#pragma unroll
-    for (int r = 0; r < EPT; ++r) { dst[r] = s2; s2 += cnt[r]; }
-    if (EXT) {
-        u32 tot;
-        const u32 ex = gs_scan(s2, sm.warp, tot);
-#pragma unroll
-        for (int r = 0; r < EPT; ++r) dst[r] += ex;
-    }
-#pragma unroll
-    for (int r = 0; r < EPT; ++r) {
-        const u32 i = tid * EPT + r;
-        if (i < D) {
-#pragma unroll
-            for (int l = 0; l < NW; ++l) P.out_words[(fk + i) * NW + l] = key[r][l];
-            P.out_cnt[fk + i] = cnt[r];
-            if (EXT) {
-                P.out_occ_off[fk + i] = fo + dst[r];
-                const u64 sp = so + src[r], dd = fo + dst[r];
-                for (u32 t = 0; t < cnt[r]; ++t) { P.out_pos[dd + t] = P.st_pos[sp + t]; P.out_rid[dd + t] = P.st_rid[sp + t]; }
-            }
-        }
-    }
-    (void)lb;
-}
-
-template <int NW, bool EXT>
-__global__ void __launch_bounds__(GS_THREADS) k_bin_gather_small(BinParams P)
-{
-    __shared__ GsSmem<NW> sm;
-    const u32 lb = P.bin_lo + blockIdx.x;
-    const u64 sk = P.bin_rec[4 * (size_t)lb + 0];
-    const u32 D = (u32)P.bin_rec[4 * (size_t)lb + 1];
-    const u64 so = P.bin_rec[4 * (size_t)lb + 2];
-    if (D == 0 || D > (u32)(GS_THREADS * GS_EPT)) return;
-    const u64 fk = P.fin[2 * (size_t)lb], fo = P.fin[2 * (size_t)lb + 1];
-    if (D <= GS_THREADS) gather_small<NW, EXT, 1>(P, sm, lb, D, sk, so, fk, fo);
-    else if (D <= 2 * GS_THREADS) gather_small<NW, EXT, 2>(P, sm, lb, D, sk, so, fk, fo);
-    else gather_small<NW, EXT, 4>(P, sm, lb, D, sk, so, fk, fo);
-}
-
-// bins with 513..1024 kept k-mers (listed by k_bin_offsets): the same register sort, 8 entries per thread
-template <int NW, bool EXT>
-__global__ void __launch_bounds__(GS_THREADS) k_bin_gather_mid(BinParams P)
-{
-    __shared__ GsSmem<NW, GM_EPT> sm;
-    const u32 n = *P.mid_count;
-    for (u32 work = blockIdx.x; work < n; work += gridDim.x) {
-        const u32 lb = P.mid_list[work];
-        const u64 sk = P.bin_rec[4 * (size_t)lb + 0];
-        const u32 D = (u32)P.bin_rec[4 * (size_t)lb + 1];
-        const u64 so = P.bin_rec[4 * (size_t)lb + 2];
-        const u64 fk = P.fin[2 * (size_t)lb], fo = P.fin[2 * (size_t)lb + 1];
-        __syncthreads();
-        gather_small<NW, EXT, GM_EPT>(P, sm, lb, D, sk, so, fk, fo);
-    }
-}
-
 // ---- per-source segment tables of the bins a rank owns (multi-rank) ---------------------------------
 // alltot[src][b] = (slots << 40 | k-mers) of bin b as extracted by rank src (all-gathered).  Block src scans
 // its row over the owned bins [b_lo, b_lo + tg): exclusive prefix of the slot counts = where the bin starts
@@ -867,8 +861,11 @@ cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nran
     return cudaGetLastError();
 }
 
-constexpr int GS_CAP = GS_THREADS * GS_EPT;             // gather: the usual bins (register bitonic), one CTA each
-constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers (up to the bin capacity)
+// 228 KB of shared memory per SM, 1 KB reserved per CTA
+static_assert(sizeof(BinSmem<1, false>) <= (233472 - 2 * 1024) / 2, "K <= 32: two CTAs per SM");
+static_assert(sizeof(BinSmem<1, true>) <= (233472 - 3 * 1024) / 3, "K <= 32 with EXTENSION: three CTAs per SM");
+static_assert(sizeof(BinSmem<2, false>) <= 232448 && sizeof(BinSmem<2, true>) <= 232448 && sizeof(BinSmem<3, true>) <= 232448, "K > 32: one CTA per SM");
+constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers than a CTA sorts itself
 
 template <int NW, bool EXT>
 static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t s)
@@ -879,16 +876,10 @@ static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t 
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_count<NW, EXT>, BN_THREADS, smem);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    const u32 nb = P.bin_hi - P.bin_lo;
-    const u32 grid = (u32)std::min<u64>((u64)sm_count * per_sm, std::max<u32>(nb, 1u));
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    // every CTA must be resident: the look-back chain waits on bins that other CTAs hold
+    const u32 grid = (u32)std::min<u64>((u64)sm_count * per_sm, std::max<u32>(P.nbins, 1u));
     k_bin_count<NW, EXT><<<grid, BN_THREADS, smem, s>>>(P);
-    k_bin_offsets<<<1, 1024, 0, s>>>(P.bin_rec, P.bin_lo, P.bin_hi, P.fin, P.cursor, (u32)GS_CAP, (u32)(GS_THREADS * GM_EPT), P.mid_list,
-                                     P.mid_count, P.big_list, P.big_count, P.snap);
-    // gather + sort: the usual bins one CTA each, the listed mid-sized ones by a small grid; bins with even more
-    // kept k-mers are listed (big_list) for launch_bin_gather_big
-    k_bin_gather_small<NW, EXT><<<nb, GS_THREADS, 0, s>>>(P);
-    k_bin_gather_mid<NW, EXT><<<32, GS_THREADS, 0, s>>>(P);
     return cudaGetLastError();
 }
 
@@ -905,7 +896,7 @@ static cudaError_t launch_big_t(const BinParams &P, int sm_count, cudaStream_t s
 
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
 {
-    if (P.bin_hi <= P.bin_lo) return cudaSuccess;
+    if (P.nbins == 0) return cudaSuccess;
     if (nwords == 1) return ext ? launch_bins_t<1, true>(P, sm_count, s) : launch_bins_t<1, false>(P, sm_count, s);
     if (nwords == 2) return ext ? launch_bins_t<2, true>(P, sm_count, s) : launch_bins_t<2, false>(P, sm_count, s);
     return ext ? launch_bins_t<3, true>(P, sm_count, s) : launch_bins_t<3, false>(P, sm_count, s);

@@ -565,7 +565,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     BinParams BP;
     memset(&BP, 0, sizeof(BP));
     BP.k = c->cfg.k; BP.lower = (u32)c->cfg.lower; BP.upper = (u32)c->cfg.upper;
-    BP.nbins = TG; BP.bin_lo = 0; BP.bin_hi = TG; BP.nsrc = G;
+    BP.nbins = TG; BP.nsrc = G;
     c->rbase_idx.assign(G, 0);
     u64 owned = 0;
 
@@ -635,31 +635,41 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     const size_t hist_bins = (size_t)c->cfg.upper + 1;
     CK(c->d_hist.ensure(hist_bins * 8));
     CK(cudaMemsetAsync(c->d_hist.p, 0, hist_bins * 8, s));
-    CK(c->d_lb.ensure(((size_t)6 * TG + 8) * 8 + ((size_t)3 * TG + 16) * 4));
+    // per-bin records: look-back cells (zeroed), staging records of the big bins, overflow / big lists
+    int NG = (c->stream_result && TG >= 2048) ? 8 : 1;
+    if (const char *ev = getenv("HSK_GROUPS")) { const int v = atoi(ev); if (v >= 1 && v <= 64 && c->stream_result) NG = v; }
+    const u32 group_bins = (TG + (u32)NG - 1) / (u32)NG;
+    NG = group_bins ? (int)((TG + group_bins - 1) / group_bins) : 1;
+    CK(c->d_lb.ensure(((size_t)8 * TG + 16) * 8 + ((size_t)2 * TG + 16) * 4));
+    CK(c->d_grp.ensure((size_t)NG * 24 + 64));
+    CK(c->h_grp.ensure((size_t)NG * 32 + 64));
+    CK(cudaMemsetAsync(c->d_lb.p, 0, (size_t)2 * TG * 8, s));
+    CK(cudaMemsetAsync(c->d_grp.p, 0, (size_t)NG * 24 + 64, s));
+    BP.lb_state = c->d_lb.as<u64>();
+    BP.bin_rec = BP.lb_state + (size_t)2 * TG; BP.fin = BP.bin_rec + (size_t)4 * TG;
     BP.st_words = c->d_swords.as<u64>(); BP.st_cnt = c->d_scnt.as<u32>();
     BP.st_pos = c->d_spos.as<u32>(); BP.st_rid = c->d_srid.as<int>();
     BP.stage_cursor = d_stagecur;
-    BP.bin_rec = c->d_lb.as<u64>(); BP.fin = BP.bin_rec + (size_t)4 * TG;
     BP.out_words = c->d_owords.as<u64>(); BP.out_cnt = c->d_ocnt.as<u32>();
     BP.out_occ_off = c->d_oocc_off.as<u64>(); BP.out_pos = c->d_opos.as<u32>(); BP.out_rid = c->d_orid.as<int>();
     BP.histogram = c->d_hist.as<u64>(); BP.cursor = d_cursor;
     BP.ticket = d_ticket; BP.ovf_count = d_ovfc;
     BP.ovf_list = reinterpret_cast<u32 *>(BP.fin + (size_t)2 * TG + 8);
-    u32 *const big_base = BP.ovf_list + TG + 4, *const mid_base = big_base + TG + 4;
-    BP.big_list = big_base; BP.big_count = d_bigc; BP.mid_list = mid_base; BP.mid_count = d_bigc; BP.snap = nullptr;
+    BP.big_list = BP.ovf_list + TG + 4; BP.big_count = d_bigc;
+    BP.group_bins = group_bins ? group_bins : 1;
+    BP.grp_end = c->d_grp.as<u64>();
+    BP.grp_done = reinterpret_cast<u32 *>(BP.grp_end + (size_t)2 * NG); BP.grp_big = BP.grp_done + NG;
+    volatile u64 *snap = c->h_grp.as<u64>();
+    BP.snap = c->stream_result ? c->h_grp.as<u64>() : nullptr;
+    for (int i = 0; i < 4 * NG; ++i) snap[i] = 0;
 
-    // ---- stages 4+5 on chip, in groups of bins.  hsk_count streams every group's part of the arena to the host
-    //      while the next group is counted; hsk_count_device runs one group.
-    int NG = (c->stream_result && TG >= 2048) ? 8 : 1;
-    if (const char *ev = getenv("HSK_GROUPS")) { const int v = atoi(ev); if (v >= 1 && v <= 8 && c->stream_result) NG = v; }
-    CK(c->d_grp.ensure((size_t)NG * 16));
-    CK(c->h_grp.ensure((size_t)NG * 32));
-    CK(cudaMemsetAsync(c->d_grp.p, 0, (size_t)NG * 16, s));
+    // ---- stages 4+5 on chip: one persistent launch over all bins.  hsk_count streams the arena to the host group by
+    //      group while the kernel is still running: the CTA that completes a group says so in page-locked memory.
     const size_t hist_bytes = hist_bins * 8;
     u64 sent_kept = 0, sent_occ = 0;
-    cudaEvent_t ev_grp[8], ev_d0 = nullptr, ev_d1 = nullptr;
+    cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
     if (c->stream_result) { ev_d0 = c->ev(); ev_d1 = c->ev(); CK(cudaEventRecord(ev_d0, c->copy_stream)); }
-    // copy arena entries [sent_kept, kept_end) / occurrences [sent_occ, occ_end) once `ready` has fired
+    // copy arena entries [sent_kept, kept_end) / occurrences [sent_occ, occ_end) (after `ready`, if given)
     auto send_result = [&](u64 kept_end, u64 occ_end, u64 kept_total_hint, cudaEvent_t ready) -> int {
         const u64 want = std::max<u64>(kept_end, kept_total_hint) + 1;
         if (want * NW * 8 > c->h_owords.cap || want * 4 > c->h_ocnt.cap || (ext && (want + 1) * 8 > c->h_oocc_off.cap)) {
@@ -675,7 +685,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
             CK(c->h_orid.ensure_keep(wo * 4, sent_occ * 4));
         }
         cudaStream_t cs = c->copy_stream;
-        CK(cudaStreamWaitEvent(cs, ready, 0));
+        if (ready) CK(cudaStreamWaitEvent(cs, ready, 0));
         const u64 nk = kept_end - sent_kept, no = occ_end - sent_occ;
         if (nk) {
             CK(cudaMemcpyAsync(c->h_owords.as<u64>() + sent_kept * NW, c->d_owords.as<u64>() + sent_kept * NW, nk * NW * 8, cudaMemcpyDeviceToHost, cs));
@@ -689,49 +699,35 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         sent_kept = kept_end; sent_occ = occ_end;
         return 0;
     };
-    // h_grp[4g..4g+2] = arena cursor (entries, occurrences) after group g, number of its big bins.
-    // Bins with too many kept k-mers for the small gather are rare: their gather is launched only when the group
-    // reports some, one group late, and the group's copy waits for it.
-    auto group_params = [&](int g) {
-        BP.bin_lo = (u32)((u64)TG * g / NG); BP.bin_hi = (u32)((u64)TG * (g + 1) / NG);
-        BP.ticket = c->d_grp.as<u32>() + 4 * g; BP.mid_count = BP.ticket + 1; BP.big_count = BP.ticket + 2;
-        BP.mid_list = mid_base + BP.bin_lo; BP.big_list = big_base + BP.bin_lo;
-        BP.snap = c->h_grp.as<u64>() + 4 * g;
-    };
-    auto flush_group = [&](int g) -> int {
-        CK(cudaEventSynchronize(ev_grp[g]));
-        g_trace.mark("bin group done");
-        const u64 kept_end = c->h_grp.as<u64>()[4 * g], occ_end = c->h_grp.as<u64>()[4 * g + 1];
-        cudaEvent_t ready = ev_grp[g];
-        if ((u32)c->h_grp.as<u64>()[4 * g + 2]) {
-            group_params(g);
-            CK(launch_bin_gather_big(BP, NW, ext, c->sm_count, s));
-            c->stats.n_launches += 1;
-            ready = c->ev();
-            CK(cudaEventRecord(ready, s));
+    c->begin(c->ev_bins);
+    CK(launch_bin_count(BP, NW, ext, c->sm_count, s));
+    c->end(c->ev_bins);
+    c->stats.n_launches += 1;
+    cudaEvent_t ev_bins_done = c->ev();
+    CK(cudaEventRecord(ev_bins_done, s));
+    if (c->stream_result) {
+        // follow the kernel: a finished group whose bins are all in place goes out at once; after the first group
+        // that waits for the big gather the rest is sent at the end
+        for (int g = 0; g < NG; ++g) {
+            while (snap[4 * g + 3] == 0) {
+                if (cudaEventQuery(ev_bins_done) != cudaErrorNotReady) break;   // finished (or failed): the final sync tells
+            }
+            if (snap[4 * g + 3] == 0 || snap[4 * g + 2] != 0) break;
+            g_trace.mark("bin group in the arena");
+            const u64 kept_end = snap[4 * g], occ_end = snap[4 * g + 1];
+            const u64 hint = (u64)((double)kept_end * (double)NG / (double)(g + 1) * 1.15) + 4096;
+            if (send_result(kept_end, occ_end, hint, nullptr)) return 1;
         }
-        if (!c->stream_result) return 0;
-        // size the host buffers for the whole result from the groups seen so far
-        const u64 hint = (u64)((double)kept_end * (double)NG / (double)(g + 1) * 1.15) + 4096;
-        return send_result(kept_end, occ_end, hint, ready);
-    };
-    for (int g = 0; g < NG; ++g) {
-        group_params(g);
-        c->begin(c->ev_bins);
-        CK(launch_bin_count(BP, NW, ext, c->sm_count, s));
-        c->end(c->ev_bins);
-        c->stats.n_launches += 3;
-        c->stats.n_launches += 1;
-        ev_grp[g] = c->ev();
-        CK(cudaEventRecord(ev_grp[g], s));
-        if (g > 0 && flush_group(g - 1)) return 1;   // the host waits one group behind the GPU
     }
-    if (flush_group(NG - 1)) return 1;
     c->stats.n_batches = 1;
     CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const u32 novf = reinterpret_cast<u32 *>(c->h_cursor.as<u64>() + 3)[1];
     c->stats.n_overflow_bins = novf;
+    if (*reinterpret_cast<u32 *>(c->h_cursor.as<u64>() + 6)) {   // bins that keep more k-mers than a CTA sorts
+        CK(launch_bin_gather_big(BP, NW, ext, c->sm_count, s));
+        c->stats.n_launches += 1;
+    }
 
     if (novf) {
         // ---- leftovers through HBM: fetch the tables of the overflow bins

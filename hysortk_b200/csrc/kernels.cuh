@@ -67,31 +67,34 @@ struct BinParams {
     int k;
     u32 lower, upper;
     u32 nbins;                           // owned bins, local index 0..nbins-1
-    u32 bin_lo, bin_hi;                  // bins of this launch group
     int nsrc;
     const u32 *slots[BN_MAX_SRC];        // supermer slot stream per source rank
     const u64 *seg_start[BN_MAX_SRC];    // nbins+1: first slot of every bin inside the source's stream
     const u64 *bin_kmers;                // nbins: (slots << 40 | k-mers) per bin over all sources; low 40 bits used
-    // staging area (bins in completion order, unsorted inside a bin)
+    // final arena (bins in index order, ascending k-mers inside a bin)
+    u64 *out_words; u32 *out_cnt; u64 *out_occ_off; u32 *out_pos; int *out_rid;
+    u64 *histogram;
+    u64 *cursor;                         // [0] entries, [1] occurrences in the arena once every bin is done
+    u64 *lb_state;                       // 2 x nbins, zeroed: look-back cells (entries, occurrences)
+    u32 *ticket;                         // zeroed
+    u32 *ovf_list, *ovf_count;           // bins left to the HBM path
+    // bins that keep more k-mers than a CTA sorts itself: unsorted in the staging area, listed for the big gather
     u64 *st_words; u32 *st_cnt; u32 *st_pos; int *st_rid;
     u64 *stage_cursor;                   // [0] entries, [1] occurrences claimed so far (zeroed)
     u64 *bin_rec;                        // nbins x {stage entry base, kept, stage occurrence base, occurrences}
     u64 *fin;                            // nbins x {final entry base, final occurrence base}
-    // final arena (bins in index order, ascending k-mers inside a bin)
-    u64 *out_words; u32 *out_cnt; u64 *out_occ_off; u32 *out_pos; int *out_rid;
-    u64 *histogram;
-    u64 *cursor;                         // [0] entries, [1] occurrences in the arena: advanced by k_bin_offsets
-    u32 *ticket;                         // zeroed
-    u32 *ovf_list, *ovf_count;           // bins left to the HBM path
-    u32 *mid_list, *mid_count;           // bins with 513..1024 kept k-mers (mid gather)
-    u32 *big_list, *big_count;           // bins with more (big gather, launched only when there are some)
-    u64 *snap;                           // page-locked host memory or null: {entries, occurrences, big bins} after the group
+    u32 *big_list, *big_count;
+    // groups of group_bins consecutive bins: completion is reported to the host, which streams the arena out
+    u32 group_bins;
+    u32 *grp_done, *grp_big;             // per group, zeroed: finished bins, bins left to the big gather
+    u64 *grp_end;                        // per group: arena cursor (entries, occurrences) after its last bin
+    u64 *snap;                           // page-locked host memory or null: per group {entries, occurrences, big bins, ready}
 };
 
 int bin_target_kmers(int nwords, bool ext);  // k-mer occurrences per bin the on-chip path is sized for
-// k_bin_count + k_bin_offsets + k_bin_gather_small over the bins [bin_lo, bin_hi)
+// k_bin_count: every bin counted, sorted and written to the arena (or listed for the big gather / the HBM path)
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
-// k_bin_gather over the group's big_list; needed only when *big_count != 0
+// k_bin_gather over big_list; needed only when *big_count != 0
 cudaError_t launch_bin_gather_big(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
 // multi-rank: segment tables of the owned bins inside the per-source streams + send/recv sizes (meta)
 cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start, u64 *seg_start,
