@@ -786,56 +786,71 @@ __global__ void __launch_bounds__(THREADS) k_bin_gather(BinParams P)
   }
 }
 
-// ---- per-source segment tables of the bins a rank owns (multi-rank) ---------------------------------
-// alltot[src][b] = (slots << 40 | k-mers) of bin b as extracted by rank src (all-gathered).  Block src scans
-// its row over the owned bins [b_lo, b_lo + tg): exclusive prefix of the slot counts = where the bin starts
-// inside the stream received from src.  meta[src] = slots received from src; meta[G + p] = bin_start[p * tg]
-// of the LOCAL stream = the boundaries of what this rank sends to rank p (p = 0..G).
-__global__ void __launch_bounds__(1024) k_seg_scan(const u64 *__restrict__ alltot, u32 T, u32 b_lo, u32 tg, int nranks,
-                                                    const u64 *__restrict__ local_start, u64 *__restrict__ seg_start,
-                                                    u64 *__restrict__ meta)
+// ---- multi-rank bookkeeping from the all-gathered bin totals -----------------------------------------
+// alltot[src][b] = (slots << 40 | k-mers) of bin b as extracted by rank src.  Rank r owns bins [r*tg, (r+1)*tg) and
+// receives them in one buffer: one region per source rank (in rank order), bins in index order inside a region.
+
+// block-wide exclusive scan helper for one u64 per thread (1024 threads), with a running carry
+__device__ __forceinline__ u64 scan1024(u64 v, u64 *s_c, u64 &carry)
 {
-    __shared__ u64 s_c[32];
-    __shared__ u64 carry_c;
-    const int src = blockIdx.x;
-    const u64 *row = alltot + (size_t)src * T + b_lo;
-    u64 *os = seg_start + (size_t)src * (tg + 1);
-    if (threadIdx.x == 0) carry_c = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u32 base = 0; base < tg; base += 1024) {
-        const u32 b = base + threadIdx.x;
-        const u64 c = b < tg ? (row[b] >> 40) : 0;
-        u64 ic = c;
+    u64 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 x = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += x;
+    }
+    if (lane == 31) s_c[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const u64 x = s_c[lane];
+        u64 ix = x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            u64 x = __shfl_up_sync(0xFFFFFFFFu, ic, d);
-            if (lane >= d) ic += x;
+            const u64 y = __shfl_up_sync(0xFFFFFFFFu, ix, d);
+            if (lane >= d) ix += y;
         }
-        if (lane == 31) s_c[warp] = ic;
-        __syncthreads();
-        if (warp == 0) {
-            u64 x = s_c[lane], ix = x;
+        s_c[lane] = ix - x;
+    }
+    __syncthreads();
+    const u64 ex = carry + s_c[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = ex + v;
+    __syncthreads();
+    return ex;
+}
+
+// block src: where the owned bins start inside the bin-major supermer stream of rank src (absolute slot index in
+// src's buffer when `absolute`, else relative to the first owned bin); meta[src] = slots of the owned bins in it
+__global__ void __launch_bounds__(1024) k_seg_scan(const u64 *__restrict__ alltot, u32 T, u32 b_lo, u32 tg, int absolute,
+                                                    u64 *__restrict__ seg_start, u64 *__restrict__ meta)
+{
+    __shared__ u64 s_c[32];
+    __shared__ u64 carry, first;
+    const int src = blockIdx.x;
+    const u64 *row0 = alltot + (size_t)src * T;
+    u64 before = 0;
+    if (absolute) {
+        for (u32 b = threadIdx.x; b < b_lo; b += 1024) before += row0[b] >> 40;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u64 p = __shfl_up_sync(0xFFFFFFFFu, ix, d);
-                if (lane >= d) ix += p;
-            }
-            s_c[lane] = ix - x;
-        }
-        __syncthreads();
-        const u64 ec = carry_c + s_c[warp] + ic - c;
-        if (b < tg) os[b] = ec;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_c = ec + c;
-        __syncthreads();
+        for (int d = 16; d >= 1; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
     }
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = before;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        os[tg] = carry_c;
-        meta[src] = carry_c;
-        meta[nranks + src] = local_start[(size_t)src * tg];
-        if (src == 0) meta[nranks + nranks] = local_start[(size_t)nranks * tg];
+        u64 t = 0;
+        for (int w = 0; w < 32; ++w) t += s_c[w];
+        carry = t; first = t;
     }
+    __syncthreads();
+    const u64 *row = row0 + b_lo;
+    u64 *os = seg_start + (size_t)src * (tg + 1);
+    for (u32 base = 0; base < tg; base += 1024) {
+        const u32 b = base + threadIdx.x;
+        const u64 ex = scan1024(b < tg ? (row[b] >> 40) : 0, s_c, carry);
+        if (b < tg) os[b] = ex;
+    }
+    if (threadIdx.x == 0) { os[tg] = carry; meta[src] = carry - first; }
 }
 
 // k-mers per owned bin summed over the source ranks, and their grand total (atomicAdd into *owned_total)
@@ -853,10 +868,11 @@ __global__ void __launch_bounds__(256) k_sum_kmers(const u64 *__restrict__ allto
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(owned_total, s);
 }
 
-cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start, u64 *seg_start,
-                            u64 *meta, u64 *bin_kmers, u64 *owned_total, cudaStream_t s)
+cudaError_t launch_seg_scan(const u64 *alltot, u32 T, int me, u32 tg, int nranks, bool absolute, u64 *seg_start, u64 *meta,
+                            u64 *bin_kmers, u64 *owned_total, cudaStream_t s)
 {
-    k_seg_scan<<<nranks, 1024, 0, s>>>(alltot, T, b_lo, tg, nranks, local_start, seg_start, meta);
+    const u32 b_lo = (u32)me * tg;
+    k_seg_scan<<<nranks, 1024, 0, s>>>(alltot, T, b_lo, tg, absolute ? 1 : 0, seg_start, meta);
     k_sum_kmers<<<(tg + 255) / 256, 256, 0, s>>>(alltot, T, b_lo, tg, nranks, bin_kmers, owned_total);
     return cudaGetLastError();
 }

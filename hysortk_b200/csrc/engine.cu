@@ -19,6 +19,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -182,9 +184,17 @@ struct hsk_ctx {
     HostBuf h_bucket;
     DevBuf d_slots;
     // exchange
-    DevBuf d_alltot, d_rslots, d_seg, d_lb;
-    HostBuf h_alltot, h_meta;
+    DevBuf d_alltot, d_rslots, d_seg, d_lb, d_peerinfo;
+    HostBuf h_alltot, h_meta, h_peerinfo;
     std::vector<u64> rbase_idx;
+    // peer supermer buffers mapped into this process (fused scatter + exchange over NVLink)
+    struct PeerMap { unsigned char info[128]; void *mapped = nullptr; bool ipc = false; bool valid = false; };
+    PeerMap peers[BN_MAX_SRC];
+    bool use_p2p = true;
+    // extraction state between the count pass and the scatter pass
+    ExtractParams xp;
+    u32 x_nctas = 0;
+    const u32 *src_slots[BN_MAX_SRC] = {};   // per source: first slot of the stream the bins read
     // batch buffers
     DevBuf d_keys[2][MAX_WORDS], d_val[2], d_rscratch, d_cscratch, d_tsum, d_tbase;
     // result arena
@@ -290,6 +300,7 @@ int hsk_create(hsk_ctx **out, const hsk_config *cfg)
         if (r != ncclSuccess) { delete c; return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
     }
     memset(&c->stats, 0, sizeof(c->stats));
+    if (const char *ev = getenv("HSK_EXCHANGE")) c->use_p2p = strcmp(ev, "nccl") != 0;
     *out = c;
     return 0;
 }
@@ -302,12 +313,13 @@ void hsk_destroy(hsk_ctx *c)
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->comm) g_nccl.CommDestroy(c->comm);
     DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_len64, &c->d_rtscratch, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bucket, &c->d_slots,
-                    &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
+                    &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_peerinfo, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
     for (int h = 0; h < 2; ++h) for (int w = 0; w < MAX_WORDS; ++w) c->d_keys[h][w].release();
-    HostBuf *hb[] = {&c->h_bucket, &c->h_alltot, &c->h_meta, &c->h_cursor, &c->h_owords, &c->h_ocnt,
+    for (int p = 0; p < BN_MAX_SRC; ++p) if (c->peers[p].valid && c->peers[p].ipc && c->peers[p].mapped) cudaIpcCloseMemHandle(c->peers[p].mapped);
+    HostBuf *hb[] = {&c->h_peerinfo, &c->h_bucket, &c->h_alltot, &c->h_meta, &c->h_cursor, &c->h_owords, &c->h_ocnt,
                      &c->h_oocc_off, &c->h_opos, &c->h_orid, &c->h_hist};
     for (auto *b : hb) b->release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -348,22 +360,25 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
 // Device layout of d_bucket (u64 units): [bin_tot T][start T+1][run_cursor][kmers_total][cursor T]
 // bin_tot = slots << 40 | k-mers.  Host (h_meta): S, run cursor, local k-mer total.  With full_d2h bin_tot and
 // start are also copied to h_bucket (debug entry point).  d_slots receives the bin-major supermer slots.
-static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
-                       const u32 *d_read_len, u64 nreads, int readid_base, bool full_d2h)
+// extract_count: tile table, pass A (per-bin totals + run list), bin scan; `before_sync` may queue more work that
+// only needs the totals (multi-rank bookkeeping) before the one host synchronisation.  extract_scatter: pass B into
+// c->xp.out_base with the cursors in `d_cur`.
+static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
+                         const u32 *d_read_len, u64 nreads, int readid_base, const std::function<int()> &before_sync)
 {
     if (choose_bins(c, nbytes)) return 1;
     const u32 T = c->tt;
     cudaStream_t s = c->stream;
     const bool ext = c->cfg.ext != 0;
-    const int SW = slot_words(c->nwords, ext);
     const int w = c->cfg.k - c->m_eff + 1;
-    ExtractParams P;
+    ExtractParams &P = c->xp;
+    memset(&P, 0, sizeof(P));
     P.packed = d_packed; P.nbytes = nbytes; P.nbytes_padded = nbytes_padded;
     P.read_off = d_read_off; P.read_len = d_read_len; P.nreads = nreads;
     P.out_slots = (u32)xt_out_slots(w);
     const u64 nslots = nbytes * 4;
     P.ntiles = (nslots + P.out_slots - 1) / P.out_slots;
-    const u32 nctas = extract_grid(w, c->sm_count);
+    const u32 nctas = c->x_nctas = extract_grid(w, c->sm_count);
     const u64 nwarps = (u64)nctas * XT_WARPS;
     P.tile_begin = 0; P.tile_end = P.ntiles;
     P.tiles_per_warp = (u32)((P.ntiles + nwarps - 1) / nwarps);
@@ -409,6 +424,8 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
             tb = te;
         }
         CK(launch_bin_scan(d_tot, T, d_start, d_cur, d_ktot, s));
+        c->end(c->ev_extract);
+        if (before_sync && before_sync()) return 1;
         CK(cudaMemcpyAsync(hm + 0, d_start + T, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(hm + 2, d_runcur, 16, cudaMemcpyDeviceToHost, s));   // run cursor, k-mer total
         hm[5] = 0;
@@ -421,23 +438,46 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
         if (hm[2] <= run_cap) break;
         if (attempt) return fail("internal: run list overflow after resize");
         run_cap = nslots + 1024;   // pathological input (runs shorter than 3 k-mers on average): worst-case list
+        c->begin(c->ev_extract);
     }
     P.tile_begin = 0; P.tile_end = P.ntiles;
     P.tiles_per_warp = (u32)((P.ntiles + nwarps - 1) / nwarps);
-    const u64 S = hm[0];
-    CK(c->d_slots.ensure((S + 4) * (size_t)SW * 4));
-    if (P.ntiles) CK(launch_supermer_scatter(P, nctas, c->nwords, ext, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_cur,
-                                             c->d_slots.as<u32>(), s));
+    c->stats.n_supermers = hm[0];
+    c->stats.supermer_bytes = hm[0] * (u64)slot_words(c->nwords, ext) * 4;
+    c->stats.n_kmers_local = hm[3];
+    return 0;
+}
+
+static int extract_scatter(hsk_ctx *c, u64 *d_cur)
+{
+    cudaStream_t s = c->stream;
+    const ExtractParams &P = c->xp;
+    c->begin(c->ev_extract);
+    if (P.ntiles) CK(launch_supermer_scatter(P, c->x_nctas, c->nwords, c->cfg.ext != 0, c->d_run_list.as<u64>(),
+                                             c->d_tile_hdr.as<ulonglong2>(), d_cur, s));
     c->end(c->ev_extract);
     g_trace.mark("scatter enqueued");
     c->stats.n_launches += 1;
-    c->stats.n_supermers = S;
-    c->stats.supermer_bytes = S * (u64)SW * 4;
-    c->stats.n_kmers_local = hm[3];
+    return 0;
+}
+
+// single-rank extraction into c->d_slots (also the debug entry point)
+static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
+                       const u32 *d_read_len, u64 nreads, int readid_base, bool full_d2h)
+{
+    if (extract_count(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base, nullptr)) return 1;
+    const u32 T = c->tt;
+    const int SW = slot_words(c->nwords, c->cfg.ext != 0);
+    const u64 S = c->stats.n_supermers;
+    CK(c->d_slots.ensure((S + 4) * (size_t)SW * 4));
+    c->xp.out_stream = c->d_slots.as<u32>();
+    u64 *d_cur = c->d_bucket.as<u64>() + (size_t)T + (T + 1) + 2;
+    if (extract_scatter(c, d_cur)) return 1;
     if (full_d2h) {
+        const size_t host_u64 = (size_t)T + ((size_t)T + 1);
         CK(c->h_bucket.ensure((host_u64 + 1) * 8));
-        CK(cudaMemcpyAsync(c->h_bucket.p, c->d_bucket.p, host_u64 * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(c->h_bucket.p, c->d_bucket.p, host_u64 * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
     }
     return 0;
 }
@@ -488,7 +528,7 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
             const bool local = (g.src == me);
             const int SW = slot_words(NW, ext);
             ExpandSegment seg;
-            seg.slots = (local ? c->d_slots.as<u32>() : c->d_rslots.as<u32>() + c->rbase_idx[g.src] * (u64)SW) + g.i0 * (u64)SW;
+            seg.slots = c->src_slots[g.src] + g.i0 * (u64)SW;
             seg.nslots = g.nslots;
             seg.out_base = out_base;
             CK(launch_expand(seg, c->cfg.k, NW, ext, c->d_tsum.as<u32>(), c->d_tbase.as<u64>(), A, VA, s));
@@ -543,19 +583,11 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     cudaEvent_t ev_t0 = c->ev(), ev_t1 = c->ev();
     CK(cudaEventRecord(ev_t0, s));
 
-    if (run_extract(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base, false)) return 1;
-    const u32 T = c->tt, TG = c->tg;
-    const u32 b_lo = (u32)me * TG;
-    u64 *d_tot = c->d_bucket.as<u64>();
-    u64 *d_start = d_tot + T;
-    u64 *hm = c->h_meta.as<u64>();
-    const int SW = slot_words(NW, ext);
-
     // ---- small device state of this call:
-    //      [cursor 2][owned total 1][ticket, ovf_count (u32 x2)][stage cursor 2][big_count (u32)]
-    CK(c->d_cursor.ensure(64));
-    CK(c->h_cursor.ensure(64));
-    CK(cudaMemsetAsync(c->d_cursor.p, 0, 64, s));
+    //      [cursor 2][owned total 1][ticket, ovf_count (u32 x2)][stage cursor 2][big_count (u32)][barrier word]
+    CK(c->d_cursor.ensure(128));
+    CK(c->h_cursor.ensure(128));
+    CK(cudaMemsetAsync(c->d_cursor.p, 0, 128, s));
     u64 *d_cursor = c->d_cursor.as<u64>();
     u64 *d_owned = d_cursor + 2;
     u32 *d_ticket = reinterpret_cast<u32 *>(d_cursor + 3), *d_ovfc = d_ticket + 1;
@@ -565,58 +597,152 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     BinParams BP;
     memset(&BP, 0, sizeof(BP));
     BP.k = c->cfg.k; BP.lower = (u32)c->cfg.lower; BP.upper = (u32)c->cfg.upper;
-    BP.nbins = TG; BP.nsrc = G;
+    BP.nsrc = G;
     c->rbase_idx.assign(G, 0);
     u64 owned = 0;
+    const int SW = slot_words(NW, ext);
+    u32 T = 0, TG = 0, b_lo = 0;
+    u64 *d_tot = nullptr, *d_start = nullptr;
+    u64 *hm = nullptr;
 
     if (G == 1) {
+        if (run_extract(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base, false)) return 1;
+        T = c->tt; TG = c->tg;
+        d_tot = c->d_bucket.as<u64>(); d_start = d_tot + T;
+        hm = c->h_meta.as<u64>();
         BP.slots[0] = c->d_slots.as<u32>();
         BP.seg_start[0] = d_start;
         BP.bin_kmers = d_tot;
         owned = c->stats.n_kmers_local;
     } else {
-        // ---- stage 3: supermer all-to-all.  Bin totals of every rank -> segment tables and transfer sizes
-        const size_t meta_n = (size_t)G + ((size_t)G + 1);
-        CK(c->d_alltot.ensure((size_t)G * T * 8));
-        CK(c->d_seg.ensure(((size_t)G * (TG + 1) + TG + meta_n) * 8));
-        u64 *d_seg_start = c->d_seg.as<u64>();
-        u64 *d_binkm = d_seg_start + (size_t)G * (TG + 1), *d_meta = d_binkm + TG;
-        c->begin(c->ev_exchange);
-        NK(g_nccl.AllGather(d_tot, c->d_alltot.p, (size_t)T, ncclUint64, c->comm, s));
-        CK(launch_seg_scan(c->d_alltot.as<u64>(), T, b_lo, TG, G, d_start, d_seg_start, d_meta, d_binkm, d_owned, s));
-        c->stats.n_launches += 2;
-        CK(cudaMemcpyAsync(hm + 8, d_meta, meta_n * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(hm + 7, d_owned, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        // ---- stages 1-3 across ranks.  Every rank scatters its supermers into its own bin-major stream; after the
+        //      count pass the bin totals of every rank are all-gathered, so that everybody knows where the bins it owns
+        //      lie inside every rank's stream.  Then either
+        //      (default) nothing is shipped at all: the streams are exchanged once as CUDA IPC handles and the bin
+        //      kernel reads the supermers of its bins in place, out of the peers' memory over NVLink, while it counts
+        //      (fused exchange + count: the all-to-all costs no pass and no buffer of its own), or
+        //      (HSK_EXCHANGE=nccl) whole bin ranges are shipped with grouped ncclSend/ncclRecv first.
+        u64 *d_seg_start = nullptr, *d_binkm = nullptr, *d_meta = nullptr;
+        auto bookkeeping = [&]() -> int {
+            T = c->tt; TG = c->tg; b_lo = (u32)me * TG;
+            d_tot = c->d_bucket.as<u64>(); d_start = d_tot + T;
+            hm = c->h_meta.as<u64>();
+            CK(c->d_alltot.ensure((size_t)G * T * 8));
+            CK(c->d_seg.ensure(((size_t)G * (TG + 1) + TG + G + 8) * 8));
+            d_seg_start = c->d_seg.as<u64>();
+            d_binkm = d_seg_start + (size_t)G * (TG + 1); d_meta = d_binkm + TG;
+            c->begin(c->ev_exchange);
+            NK(g_nccl.AllGather(d_tot, c->d_alltot.p, (size_t)T, ncclUint64, c->comm, s));
+            CK(cudaMemsetAsync(d_owned, 0, 8, s));
+            CK(launch_seg_scan(c->d_alltot.as<u64>(), T, me, TG, G, c->use_p2p, d_seg_start, d_meta, d_binkm, d_owned, s));
+            c->end(c->ev_exchange);
+            c->stats.n_launches += 3;
+            CK(cudaMemcpyAsync(hm + 8, d_meta, (size_t)G * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(hm + 7, d_owned, 8, cudaMemcpyDeviceToHost, s));
+            // local bin starts at the rank boundaries: what goes to every peer
+            CK(cudaMemcpy2DAsync(hm + 8 + G, 8, d_start, (size_t)TG * 8, 8, (size_t)G + 1, cudaMemcpyDeviceToHost, s));
+            return 0;
+        };
+        if (extract_count(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base, bookkeeping)) return 1;
         owned = hm[7];
         const u64 *rtot = hm + 8, *bounds = hm + 8 + (size_t)G;
-        u64 ri = 0;
-        for (int src = 0; src < G; ++src) {
-            if (src == me) continue;
-            c->rbase_idx[src] = ri;
-            ri += rtot[src];
-        }
-        CK(c->d_rslots.ensure((ri + 4) * (size_t)SW * 4));
-        NK(g_nccl.GroupStart());
+        u64 *d_cur = d_start + T + 1 + 2;
+        const u64 S = c->stats.n_supermers;
+        CK(c->d_slots.ensure((S + S / 8 + 64) * (size_t)SW * 4));
+        c->xp.out_stream = c->d_slots.as<u32>();
         for (int peer = 0; peer < G; ++peer) {
             if (peer == me) continue;
-            const u64 si = bounds[peer], sn = bounds[peer + 1] - si;
-            const u64 rn = rtot[peer];
-            if (sn) NK(g_nccl.Send(c->d_slots.as<u32>() + si * SW, sn * SW, ncclUint32, peer, c->comm, s));
-            if (rn) NK(g_nccl.Recv(c->d_rslots.as<u32>() + c->rbase_idx[peer] * SW, rn * SW, ncclUint32, peer, c->comm, s));
-            c->stats.bytes_sent += sn * SW * 4;
-            c->stats.bytes_received += rn * SW * 4;
+            c->stats.bytes_sent += (bounds[peer + 1] - bounds[peer]) * SW * 4;
+            c->stats.bytes_received += rtot[peer] * SW * 4;
         }
-        NK(g_nccl.GroupEnd());
-        c->end(c->ev_exchange);
-        for (int src = 0; src < G; ++src) {
-            const bool local = (src == me);
-            BP.slots[src] = local ? c->d_slots.as<u32>() : c->d_rslots.as<u32>() + c->rbase_idx[src] * (u64)SW;
-            // the local stream is addressed with its own (absolute) bin starts, the received ones with the scanned tables
-            BP.seg_start[src] = local ? d_start + b_lo : d_seg_start + (size_t)src * (TG + 1);
+        if (c->use_p2p) {
+            // tell the peers where my stream is: IPC handle + process id + pointer, all-gathered every call (128 bytes a
+            // rank); a peer is (re)mapped only when its record changes
+            CK(c->h_peerinfo.ensure((size_t)(G + 1) * 128));
+            CK(c->d_peerinfo.ensure((size_t)(G + 1) * 128));
+            unsigned char *mine = c->h_peerinfo.as<unsigned char>() + (size_t)G * 128;
+            memset(mine, 0, 128);
+            cudaIpcMemHandle_t hnd;
+            CK(cudaIpcGetMemHandle(&hnd, c->d_slots.p));
+            static_assert(sizeof(hnd) <= 64, "ipc handle size");
+            memcpy(mine, &hnd, sizeof(hnd));
+            const u64 pid = (u64)getpid(), ptr = (u64)(uintptr_t)c->d_slots.p, cap = (u64)c->d_slots.cap;
+            memcpy(mine + 64, &pid, 8); memcpy(mine + 72, &ptr, 8); memcpy(mine + 80, &cap, 8);
+            c->begin(c->ev_exchange);
+            CK(cudaMemcpyAsync(c->d_peerinfo.as<unsigned char>() + (size_t)G * 128, mine, 128, cudaMemcpyHostToDevice, s));
+            NK(g_nccl.AllGather(c->d_peerinfo.as<unsigned char>() + (size_t)G * 128, c->d_peerinfo.p, 128, ncclUint8, c->comm, s));
+            CK(cudaMemcpyAsync(c->h_peerinfo.p, c->d_peerinfo.p, (size_t)G * 128, cudaMemcpyDeviceToHost, s));
+            c->end(c->ev_exchange);
+            // pass B into my own stream while the records travel
+            if (extract_scatter(c, d_cur)) return 1;
+            // every rank's stream has to be complete before anybody reads it: a one-word all-reduce is the barrier
+            c->begin(c->ev_exchange);
+            NK(g_nccl.AllReduce(d_cursor + 8, d_cursor + 9, 1, ncclUint64, ncclSum, c->comm, s));
+            c->end(c->ev_exchange);
+            CK(cudaStreamSynchronize(s));
+            for (int p = 0; p < G; ++p) {
+                const unsigned char *info = c->h_peerinfo.as<unsigned char>() + (size_t)p * 128;
+                hsk_ctx::PeerMap &pm = c->peers[p];
+                BP.seg_start[p] = d_seg_start + (size_t)p * (TG + 1);
+                if (p == me) { BP.slots[p] = c->d_slots.as<u32>(); continue; }
+                if (!pm.valid || memcmp(pm.info, info, 128) != 0) {
+                    if (pm.valid && pm.ipc && pm.mapped) cudaIpcCloseMemHandle(pm.mapped);
+                    pm.valid = false;
+                    u64 ppid, pptr;
+                    memcpy(&ppid, info + 64, 8); memcpy(&pptr, info + 72, 8);
+                    if (ppid == pid) {
+                        // a context of the same process: plain peer access
+                        cudaPointerAttributes at;
+                        CK(cudaPointerGetAttributes(&at, (void *)(uintptr_t)pptr));
+                        if (at.device != c->cfg.device) {
+                            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess(%d): %s", at.device, cudaGetErrorString(e));
+                            (void)cudaGetLastError();
+                        }
+                        pm.mapped = (void *)(uintptr_t)pptr; pm.ipc = false;
+                    } else {
+                        cudaIpcMemHandle_t ph;
+                        memcpy(&ph, info, sizeof(ph));
+                        cudaError_t e = cudaIpcOpenMemHandle(&pm.mapped, ph, cudaIpcMemLazyEnablePeerAccess);
+                        if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle(rank %d): %s (set HSK_EXCHANGE=nccl where peer access is unavailable)", p, cudaGetErrorString(e));
+                        pm.ipc = true;
+                    }
+                    memcpy(pm.info, info, 128);
+                    pm.valid = true;
+                }
+                BP.slots[p] = reinterpret_cast<const u32 *>(pm.mapped);
+            }
+        } else {
+            if (extract_scatter(c, d_cur)) return 1;
+            u64 ri = 0;
+            for (int src = 0; src < G; ++src) {
+                if (src == me) continue;
+                c->rbase_idx[src] = ri;
+                ri += rtot[src];
+            }
+            CK(c->d_rslots.ensure((ri + 4) * (size_t)SW * 4));
+            c->begin(c->ev_exchange);
+            NK(g_nccl.GroupStart());
+            for (int peer = 0; peer < G; ++peer) {
+                if (peer == me) continue;
+                const u64 si = bounds[peer], sn = bounds[peer + 1] - si;
+                const u64 rn = rtot[peer];
+                if (sn) NK(g_nccl.Send(c->d_slots.as<u32>() + si * SW, sn * SW, ncclUint32, peer, c->comm, s));
+                if (rn) NK(g_nccl.Recv(c->d_rslots.as<u32>() + c->rbase_idx[peer] * SW, rn * SW, ncclUint32, peer, c->comm, s));
+            }
+            NK(g_nccl.GroupEnd());
+            c->end(c->ev_exchange);
+            for (int src = 0; src < G; ++src) {
+                const bool local = (src == me);
+                BP.slots[src] = local ? c->d_slots.as<u32>() : c->d_rslots.as<u32>() + c->rbase_idx[src] * (u64)SW;
+                // the local stream is addressed with its own (absolute) bin starts, the received ones with the scanned tables
+                BP.seg_start[src] = local ? d_start + b_lo : d_seg_start + (size_t)src * (TG + 1);
+            }
         }
         BP.bin_kmers = d_binkm;
     }
+    BP.nbins = TG;
+    for (int src = 0; src < G; ++src) c->src_slots[src] = BP.slots[src];
     c->stats.n_kmers_owned = owned;
 
     // ---- result arena, staging area, per-bin records

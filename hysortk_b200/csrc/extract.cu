@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_t
 template <int SW, bool EXT>
 __global__ void __launch_bounds__(XT_THREADS) k_supermer_scatter(ExtractParams P, const u64 *__restrict__ run_list,
                                                                   const ulonglong2 *__restrict__ tile_hdr,
-                                                                  u64 *__restrict__ bin_cursor, u32 *__restrict__ out_slots)
+                                                                  u64 *__restrict__ bin_cursor)
 {
     constexpr int PW = SW - (EXT ? 2 : 0);
     __shared__ u32 s_w[XT_WARPS][XT_STAGE_WORDS];
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_supermer_scatter(ExtractParams P
                 }
                 w[PW - 1] = (w[PW - 1] & 0xFFFFFF00u) | len;
                 if (EXT) { w[SW - 2] = pos0 + pc * P.slot_nmax; w[SW - 1] = rid; }
-                uint4 *dst = reinterpret_cast<uint4 *>(out_slots + gs * SW);
+                uint4 *dst = reinterpret_cast<uint4 *>(P.out_stream + gs * SW);
 #pragma unroll
                 for (int x = 0; x < SW / 4; ++x) dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
             }
@@ -424,9 +424,9 @@ cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *
 }
 
 cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, int nwords, bool ext, const u64 *run_list,
-                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, u32 *out_slots, cudaStream_t s)
+                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, cudaStream_t s)
 {
-#define HSK_SC(SW_, EXT_) k_supermer_scatter<SW_, EXT_><<<nctas, XT_THREADS, 0, s>>>(P, run_list, tile_hdr, bin_cursor, out_slots)
+#define HSK_SC(SW_, EXT_) k_supermer_scatter<SW_, EXT_><<<nctas, XT_THREADS, 0, s>>>(P, run_list, tile_hdr, bin_cursor)
     if (nwords == 1) { if (ext) HSK_SC(8, true); else HSK_SC(4, false); }
     else { if (ext) HSK_SC(12, true); else HSK_SC(8, false); }
 #undef HSK_SC

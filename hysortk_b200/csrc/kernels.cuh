@@ -11,6 +11,8 @@ size_t read_table_scratch_bytes(u64 nreads);
 cudaError_t launch_read_table(const u64 *len64, u64 nreads, u64 nbytes, u64 *read_off, u32 *read_len, u64 *scratch, u32 *flags,
                               cudaStream_t s);
 
+constexpr int BN_MAX_SRC = 16;       // ranks (sources of a bin's supermers / destinations of the scatter)
+
 // ---- stage 1+2: extract.cu -----------------------------------------------------------------------
 struct ExtractParams {
     const u8 *packed;        // DnaBuffer bytes on the device, 16-byte aligned
@@ -29,6 +31,7 @@ struct ExtractParams {
     u32 slot_nmax;           // k-mers per supermer slot: slot_max_bases - k + 1
     u32 slot_ninv;           // ceil(2^32 / slot_nmax)
     int readid_base;
+    u32 *out_stream;         // pass B destination: the bin-major supermer stream of this rank
 };
 
 // grid of the two extraction passes (persistent warps, contiguous tile ranges)
@@ -40,9 +43,9 @@ cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_to
                                   u64 *run_cursor, u64 run_capacity, cudaStream_t s);
 // bin_start: nbins+1 exclusive prefix of the slot counts, bin_cursor[b] = bin_start[b]; *kmers_total += all k-mers
 cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *bin_cursor, u64 *kmers_total, cudaStream_t s);
-// pass B: bin_cursor hands out absolute slot indices
+// pass B: bin_cursor hands out slot indices inside P.out_stream
 cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, int nwords, bool ext, const u64 *run_list,
-                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, u32 *out_slots, cudaStream_t s);
+                                    const ulonglong2 *tile_hdr, u64 *bin_cursor, cudaStream_t s);
 
 // ---- stage 4 (HBM path): expand.cu -------------------------------------------------------------------
 constexpr int XP_THREADS = 256;
@@ -61,7 +64,6 @@ cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext,
 
 // ---- stages 4+5 on chip: bins.cu ---------------------------------------------------------------------
 constexpr int BN_THREADS = 512;
-constexpr int BN_MAX_SRC = 16;       // source ranks per bin
 
 struct BinParams {
     int k;
@@ -96,9 +98,13 @@ int bin_target_kmers(int nwords, bool ext);  // k-mer occurrences per bin the on
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
 // k_bin_gather over big_list; needed only when *big_count != 0
 cudaError_t launch_bin_gather_big(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
-// multi-rank: segment tables of the owned bins inside the per-source streams + send/recv sizes (meta)
-cudaError_t launch_seg_scan(const u64 *alltot, u32 T, u32 b_lo, u32 tg, int nranks, const u64 *local_start, u64 *seg_start,
-                            u64 *meta, u64 *bin_kmers, u64 *owned_total, cudaStream_t s);
+// multi-rank, from the all-gathered bin totals alltot[src][bin]:
+//   seg_start[src][0..tg]  first slot of every owned bin inside the bin-major supermer stream of rank src: absolute
+//                          (index in src's own buffer, read in place over NVLink) or relative to the first owned bin
+//                          (index in the region received from src)
+//   meta[src]              slots of the owned bins in src's stream;  bin_kmers / owned_total: k-mers per owned bin / in all
+cudaError_t launch_seg_scan(const u64 *alltot, u32 T, int me, u32 tg, int nranks, bool absolute, u64 *seg_start, u64 *meta,
+                            u64 *bin_kmers, u64 *owned_total, cudaStream_t s);
 
 // ---- stage 5a: radix.cu ------------------------------------------------------------------------------
 // scratch layout (u32 units): [RS_MAX_PASSES*256 bins][RS_MAX_PASSES tile counters][ntiles*256 look-back]
