@@ -245,25 +245,31 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
     u16 *scan = sm.scan(warp);
     u32 *heads = sm.heads(warp);
     u32 seen = 0;
-    while (true) {
+    // the slot of the NEXT batch is fetched while the current one is processed: the supermers may sit in a peer's
+    // memory (NVLink latency), and even local ones come from L2 / HBM
+    uint4 pre[SW / 4];
+    auto claim = [&](u32 &j0) {
         u32 bt = 0;
         if (lane == 0) bt = atomicAdd(&sm.next_batch, 1u);
-        bt = __shfl_sync(0xFFFFFFFFu, bt, 0);
-        const u32 j0 = bt * 32u;
-        if (j0 >= S) break;
-        u32 n = 0;
-        if (j0 + lane < S) {
+        j0 = __shfl_sync(0xFFFFFFFFu, bt, 0) * 32u;
+        if (j0 < S && j0 + lane < S) {
             const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j0 + lane, SW));
 #pragma unroll
-            for (int x = 0; x < SW / 4; ++x) {
-                const uint4 v = __ldg(sp + x);
-                stg4[lane * (SW / 4) + x] = v;
-                if (x == (PW - 1) / 4) {
-                    const u32 lw = ((PW - 1) % 4 == 3) ? v.w : ((PW - 1) % 4 == 1 ? v.y : ((PW - 1) % 4 == 2 ? v.z : v.x));
-                    n = (lw & 0xFFu) - (u32)k + 1;
-                }
-            }
+            for (int x = 0; x < SW / 4; ++x) pre[x] = __ldg(sp + x);
         }
+    };
+    u32 j0;
+    claim(j0);
+    while (j0 < S) {
+        u32 n = 0;
+        if (j0 + lane < S) {
+#pragma unroll
+            for (int x = 0; x < SW / 4; ++x) stg4[lane * (SW / 4) + x] = pre[x];
+            const uint4 v = pre[(PW - 1) / 4];
+            const u32 lw = ((PW - 1) % 4 == 3) ? v.w : ((PW - 1) % 4 == 1 ? v.y : ((PW - 1) % 4 == 2 ? v.z : v.x));
+            n = (lw & 0xFFu) - (u32)k + 1;
+        }
+        claim(j0);
         u32 inc = n;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
