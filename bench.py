@@ -8,16 +8,19 @@
 A "step" is one full kmer_count over the synthetic read set of BASELINE.json configs[1]
 (K=31 M=17, 30x reads of a 5 Mbp uniform genome, ~150 Mbp, 1 % substitutions) per GPU; with N GPUs
 the genome is N times larger and every rank holds its own contiguous 150 Mbp share of the reads
-(weak scaling), the supermer all-to-all running over NCCL.
+(weak scaling); the supermer all-to-all is fused into the count kernel (bins read the peers' supermer
+streams in place over NVLink; HSK_EXCHANGE=nccl selects the grouped ncclSend/ncclRecv baseline).
 
   value  device path: reads resident in HBM when the timed region starts, result left in HBM
          (hsk_count_device), timed with CUDA events on the launching stream, max over ranks.
   e2e    the same metric through the host-buffer C-ABI call hsk_count (what
-         hysortk::kmer_count(const DnaBuffer&, MPI_Comm) binds to): pinned host input, H2D copy,
-         count, D2H copy of the (k-mer, count) list inside the timed region.
-  roofline   dominant kernel = the per-digit radix pass k_onesweep: algorithmic bytes per launch
-             (read + write of every key record) / average launch time from CUDA events recorded
-             around the pass kernels, against the measured HBM copy bandwidth.
+         hysortk::kmer_count(const DnaBuffer&, MPI_Comm) binds to): pinned host input, H2D copies
+         (chunked, overlapped with the extraction), count, D2H copy of the (k-mer, count) list (streamed
+         out behind the count kernel) inside the timed region.
+  roofline   dominant kernel = k_bin_count (stages 4+5 fused on chip): SURVEY.md 8(d) algorithmic bytes
+             of the stages it replaces (expand + 8-bit LSD sort + count) / its launch time from CUDA
+             events around the launch, against the measured HBM copy bandwidth; `hbm_bytes_needed`
+             and `traffic` (ncu dram bytes, profiles/) say what the kernel really moves.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, built from /root/reference with the
              single-rank MPI shim) on this box's host cores, on a bounded prefix of the same reads.
 
@@ -46,7 +49,7 @@ UNIT = "kmers/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_150Mbp_10kbp")
@@ -295,7 +298,7 @@ def main_ours(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = total_kmers * args.steps / (ms_e2e * 1e-3)
-    h2d = rs.packed.nbytes + (rs.nreads + 1) * 8 + (rs.nreads + 1) * 4
+    h2d = rs.packed.nbytes + rs.nreads * 8
     d2h = int(re.n_kept) * (8 * ctx.nwords + 4) + (UPPER + 1) * 8 + 16
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
@@ -313,18 +316,35 @@ def main_ours(args):
     real_bytes = st["supermer_bytes"] + n_kept * (8 * ctx.nwords + 4)
     ms_bins = st["ms_bins"]
     achieved = alg_bytes / (ms_bins * 1e-3) / 1e9 if ms_bins > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_bin_count (expand + count one bin per CTA in shared memory) + k_bin_offsets + k_bin_gather",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:   # per-launch dram bytes of the kernel from the committed ncu --set full capture of this workload
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"k_bin_count:{args.workload}:k{K}:ext{EXT}")
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_bin_count (expand + hash-count + sort one bin per CTA in shared memory; supermers read "
+                                          "in place from local HBM or from the peers over NVLink)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_bins,
-                "launches_per_step": 4,
+                "launches_per_step": 1,
                 "note": "algorithmic bytes = SURVEY 8(d) formula for stages 4+5 (HBM-resident expand, 8-bit LSD sort, count); "
                         "the kernel keeps the k-mers on chip, so a fraction above 1 is expected: bytes it really has to move "
-                        "per launch are in hbm_bytes_needed",
+                        "per launch are in hbm_bytes_needed (frac_needed = that / time / peak); its limiter is instruction "
+                        "issue + shared-memory wavefronts (ncu: profiles/)",
                 "hbm_bytes_needed": real_bytes,
+                "frac_needed": (real_bytes / (ms_bins * 1e-3) / 1e9 / peak) if ms_bins > 0 else 0.0,
                 "hbm_path": {"overflow_bins": st["n_overflow_bins"], "ms_expand": st["ms_expand"], "ms_sort": st["ms_sort"],
                              "ms_count": st["ms_count"]},
                 "stage_ms": {k: st[k] for k in ["ms_extract", "ms_exchange", "ms_bins", "ms_expand", "ms_sort", "ms_count", "ms_total"]}}
-
+    exchange = None
+    if world > 1:
+        mode = "nccl send/recv" if os.environ.get("HSK_EXCHANGE") == "nccl" else "fused: bins read peer streams in place (P2P loads over NVLink)"
+        t_x = st["ms_exchange"] if os.environ.get("HSK_EXCHANGE") == "nccl" else st["ms_bins"]
+        exchange = {"mode": mode, "bytes_received_per_rank": st["bytes_received"], "ms_exchange_only": st["ms_exchange"],
+                    "ms_window": t_x, "gbs_per_rank": st["bytes_received"] / (t_x * 1e-3) / 1e9 if t_x > 0 else 0.0,
+                    "nvlink_peak_gbs_per_dir": 900.0,
+                    "note": "fused mode: ms_exchange_only = all-gathers of the bin totals / IPC records + the barrier; the "
+                            "supermers cross NVLink inside k_bin_count, so gbs_per_rank is bytes over that kernel's time"}
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -346,13 +366,15 @@ def main_ours(args):
                 "dtype": "u64", "data": "synthetic",
                 "config": {"workload": args.workload, "k": K, "m": M, "lower": LOWER, "upper": UPPER, "ext": EXT,
                            "kmers_per_gpu": nk_local, "reads_per_gpu": rs.nreads, "kept_kmers_rank0": n_kept,
-                           "l2_policy": "buffers written every step (run list 0.4 GB, supermers 0.27 GB, results 74 MB) exceed the 126 MB L2; no flush",
+                           "l2_policy": "buffers written every step (run list 0.13 GB, supermers 0.27 GB, results 74 MB) exceed the 126 MB L2; no flush",
                            "bins_per_rank": args.buckets_per_rank or "auto", "overflow_bins": st["n_overflow_bins"], **meta},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(round(st["n_launches"] * args.steps)),
                 "roofline": roofline, "cpu_baseline": cpu}
+        if exchange:
+            line["exchange"] = exchange
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -49,6 +49,7 @@ constexpr u64 BN_EMPTY = ~0ull;                // never a canonical k-mer: a K-m
 constexpr u32 BN_EMPTY32 = 0xFFFFFFFFu;        // K > 32: state of a fingerprint cell
 constexpr u32 BN_LOCK32 = 0xFFFFFFFEu;         //          claimed, key words not yet written
 constexpr u32 BN_NOTKEPT = 0xFFFFFFFFu;
+constexpr int BN_DDTS = 2048;                  // cells of the supermer table of a bin (dedup_bin)
 constexpr int BN_CAND = 1024;                  // candidate list; a bin with more candidates scans its whole table
 
 template <int NW, bool EXT>
@@ -65,6 +66,8 @@ struct BinCfg {
     static constexpr int HEADW = (NMAX + 31) / 32 * 32;
     static constexpr int TARGET = NW == 1 ? (EXT ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
 };
+
+size_t bin_dedup_scratch_bytes(int sm_count) { return (size_t)sm_count * 2 * BN_DDLIMIT * (sizeof(uint4) + sizeof(u32)); }
 
 int bin_target_kmers(int nwords, bool ext)
 {
@@ -103,6 +106,8 @@ struct BinSmem {
     u64 base_k, base_o;                                     // where the bin's entries / occurrences go
     u32 *occ_pos; int *occ_rid;                             // EXT pass 2 target arrays (arena, or staging for big bins)
     u32 bin, nk, S, bail, next_batch, seen, ncand;
+    int nsrc;                                               // sources of the walk: P.nsrc, or 1 when the bin was de-duplicated
+    const u32 *mult;                                        // weight per slot (de-duplicated bins) or null
 
     // walk layout
     __device__ uint4 *stg(int warp) { return reinterpret_cast<uint4 *>(scratch) + (size_t)warp * Scr::STG_U4; }
@@ -170,7 +175,8 @@ __device__ __forceinline__ u64 key_mix(const u64 (&w)[NW])
 template <typename SM>
 __device__ __forceinline__ const u32 *slot_ptr(const SM &sm, const BinParams &P, u32 j, int sw)
 {
-    if (P.nsrc == 1) return sm.src_ptr[0] + (size_t)j * (u32)sw;
+    (void)P;
+    if (sm.nsrc == 1) return sm.src_ptr[0] + (size_t)j * (u32)sw;
     int s = 0;
     while (j >= sm.src_sbase[s + 1]) ++s;
     return sm.src_ptr[s] + (size_t)(j - sm.src_sbase[s]) * (u32)sw;
@@ -229,6 +235,74 @@ __device__ __forceinline__ u32 table_find(BinSmem<NW, EXT> &sm, const u64 (&key)
     return (u32)Cfg::TS;
 }
 
+// ---- identical supermers of a bin are counted once, with a weight ------------------------------------------
+// At 30x coverage most supermers of a bin are exact copies of another one: the same locus read again without an error
+// in those ~40 bases (the scatter pass stores every supermer in its canonical orientation, so the strand does not
+// matter).  Before the walk, the slots of the bin go through a small table in the (still unused) k-mer table memory:
+// key = the 16-byte slot, guarded by a fingerprint cell with the same EMPTY -> LOCK -> publish claim as the K > 32
+// k-mer table; value = number of copies.  The distinct slots and their weights are compacted into the CTA's own list
+// in global memory (L2-resident) and the walk then expands each of them once.  K <= 32 without EXTENSION only: with
+// EXTENSION every occurrence needs its own (pos, rid) anyway.
+//   cells: sm.cnt[0 .. BN_DDTS)   weights: sm.cnt[BN_DDTS .. 2 BN_DDTS)   keys: (uint4 *)sm.fp [0 .. BN_DDTS)
+template <int NW, bool EXT>
+__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &P, u32 S)
+{
+    constexpr int SW = BinCfg<NW, EXT>::SW;
+    const u32 tid = threadIdx.x;
+    uint4 *dk = reinterpret_cast<uint4 *>(sm.fp);
+    u32 *cell = sm.cnt, *wgt = sm.cnt + BN_DDTS;
+    for (u32 j = tid; j < S; j += BN_THREADS) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j, SW)));
+        const u64 a = ((u64)v.y << 32) | v.x, b = ((u64)v.w << 32) | v.z;
+        u64 h = (a * 0x9E3779B97F4A7C15ull) ^ (b * 0xC2B2AE3D27D4EB4Full);
+        h ^= h >> 29;
+        h *= 0xBF58476D1CE4E5B9ull;
+        const u32 f = (u32)h & 0x7FFFFFFFu;
+        u32 idx = (u32)(h >> 53) & (BN_DDTS - 1);
+        while (true) {   // S <= BN_DDLIMIT < BN_DDTS: an empty cell always exists
+            volatile u32 *c = &cell[idx];
+            u32 old = *c;
+            if (old == BN_EMPTY32) {
+                old = atomicCAS(&cell[idx], BN_EMPTY32, BN_LOCK32);
+                if (old == BN_EMPTY32) {
+                    dk[idx] = v;
+                    __threadfence_block();
+                    *c = f;
+                    break;
+                }
+            }
+            while (old == BN_LOCK32) old = *c;
+            if (old == f) {
+                const volatile u32 *q = reinterpret_cast<const volatile u32 *>(&dk[idx]);
+                if (q[0] == v.x && q[1] == v.y && q[2] == v.z && q[3] == v.w) break;
+            }
+            idx = (idx + 1) & (BN_DDTS - 1);
+        }
+        atomicAdd(&wgt[idx], 1u);
+    }
+    __syncthreads();
+    // compact the used cells into the CTA's list
+    constexpr int PER = BN_DDTS / BN_THREADS;
+    u32 used = 0, mask = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        if (cell[tid * PER + i] != BN_EMPTY32) { mask |= 1u << i; ++used; }
+    }
+    u32 ex, d0, total, d1;
+    block_scan2(used, 0u, sm.wa, sm.wb, ex, d0, total, d1);
+    uint4 *outs = P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT;
+    u32 *outm = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        if ((mask >> i) & 1) {
+            __stcg(&outs[ex], dk[tid * PER + i]);
+            __stcg(&outm[ex], wgt[tid * PER + i]);
+            ++ex;
+        }
+    }
+    return total;
+}
+
 // One pass over the k-mers of the bin.  Warps take batches of 32 consecutive slots (ticket in shared memory): the
 // lanes stage one slot each, a warp scan of the k-mers per slot and a bitmap of the slot starts map k-mer g of
 // the batch to (slot, offset) without a search, and round r gives k-mer 32r + lane to every lane — all lanes
@@ -248,26 +322,36 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
     // the slot of the NEXT batch is fetched while the current one is processed: the supermers may sit in a peer's
     // memory (NVLink latency), and even local ones come from L2 / HBM
     uint4 pre[SW / 4];
+    u32 pre_m = 1;
+    const u32 *const mult = sm.mult;   // de-duplicated bin: slots come from the CTA's own list (written by this kernel:
+                                       // coherent loads), each with the number of copies it stands for
     auto claim = [&](u32 &j0) {
         u32 bt = 0;
         if (lane == 0) bt = atomicAdd(&sm.next_batch, 1u);
         j0 = __shfl_sync(0xFFFFFFFFu, bt, 0) * 32u;
         if (j0 < S && j0 + lane < S) {
             const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j0 + lane, SW));
+            if (mult) {
 #pragma unroll
-            for (int x = 0; x < SW / 4; ++x) pre[x] = __ldg(sp + x);
+                for (int x = 0; x < SW / 4; ++x) pre[x] = __ldcg(sp + x);
+                pre_m = __ldcg(mult + j0 + lane);
+            } else {
+#pragma unroll
+                for (int x = 0; x < SW / 4; ++x) pre[x] = __ldg(sp + x);
+            }
         }
     };
     u32 j0;
     claim(j0);
     while (j0 < S) {
-        u32 n = 0;
+        u32 n = 0, my_m = 1;
         if (j0 + lane < S) {
 #pragma unroll
             for (int x = 0; x < SW / 4; ++x) stg4[lane * (SW / 4) + x] = pre[x];
             const uint4 v = pre[(PW - 1) / 4];
             const u32 lw = ((PW - 1) % 4 == 3) ? v.w : ((PW - 1) % 4 == 1 ? v.y : ((PW - 1) % 4 == 2 ? v.z : v.x));
             n = (lw & 0xFFu) - (u32)k + 1;
+            my_m = pre_m;
         }
         claim(j0);
         u32 inc = n;
@@ -306,10 +390,12 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
                 u32 slot = (u32)Cfg::TS;
                 if (act) slot = table_find<NW, EXT, true>(sm, key);
                 __syncwarp();   // the probe loop diverges; everything after it runs once per warp
+                const u32 m1 = mult ? __shfl_sync(0xFFFFFFFFu, my_m, s & 31) : 1u;   // copies of the k-mer's slot
                 if (act) {
                     if (slot < (u32)Cfg::TS) {
                         // the occurrence that lifts a counter to LOWER makes its slot a candidate for the output
-                        if (atomicAdd(&sm.cnt[slot], 1u) + 1 == P.lower) {
+                        const u32 before = atomicAdd(&sm.cnt[slot], m1);
+                        if (before < P.lower && before + m1 >= P.lower) {
                             const u32 ci = atomicAdd(&sm.ncand, 1u);
                             if (ci < (u32)BN_CAND) sm.cand[ci] = (u16)slot;
                         }
@@ -326,7 +412,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
                 }
             }
         }
-        seen += T;
+        seen += mult ? __reduce_add_sync(0xFFFFFFFFu, n * my_m) : T;
         __syncwarp();   // the staging area is reused by the next batch
     }
     if (!PASS2 && lane == 0 && seen) atomicAdd(&sm.seen, seen);
@@ -512,6 +598,8 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
 {
     using Cfg = BinCfg<NW, EXT>;
     constexpr int SW = Cfg::SW;
+    constexpr bool DEDUP = (NW == 1) && !EXT;
+    static_assert(!DEDUP || (2 * BN_DDTS <= Cfg::TS && BN_DDTS % BN_THREADS == 0 && BN_DDLIMIT < BN_DDTS), "supermer table fits the k-mer table");
     extern __shared__ __align__(16) unsigned char smraw[];
     BinSmem<NW, EXT> &sm = *reinterpret_cast<BinSmem<NW, EXT> *>(smraw);
     const int tid = threadIdx.x;
@@ -527,7 +615,9 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
             const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
             if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
             else { for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp32)[i] = ones; }
-            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
+            // de-duplication first uses the counters as its cells (empty = all ones) and weights
+            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS)
+                reinterpret_cast<uint4 *>(sm.cnt)[i] = (DEDUP && i < BN_DDTS / 4) ? ones : zero;
         }
         __syncthreads();
         const u32 lb = sm.bin;
@@ -548,9 +638,29 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
             sm.nk = (u32)min(nk, (u64)0xFFFFFFFFu);
             sm.S = (u32)min(s, (u64)0xFFFFFFFFu);
             if (nk >= 0xFFFFFFFFull || s >= 0xFFFFFFFFull) sm.bail = 1;   // 32-bit counters
+            sm.nsrc = P.nsrc; sm.mult = nullptr;
         }
         __syncthreads();
-        const u32 nk = sm.nk, S = sm.S;
+        const u32 nk = sm.nk;
+        u32 S = sm.S;
+        if (DEDUP) {
+            const bool dd = !sm.bail && S > 0 && S <= (u32)BN_DDLIMIT && P.dd_slots != nullptr;
+            u32 Sd = 0;
+            if (dd) Sd = dedup_bin<NW, EXT>(sm, P, S);
+            __syncthreads();   // the list is complete; the table memory goes back to the k-mers
+            {
+                const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
+                for (int i = tid; i < BN_DDTS; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones;
+                for (int i = tid; i < 2 * BN_DDTS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
+            }
+            if (dd && tid == 0) {
+                sm.nsrc = 1;
+                sm.src_ptr[0] = reinterpret_cast<const u32 *>(P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT);
+                sm.mult = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
+            }
+            if (dd) S = Sd;
+            __syncthreads();
+        }
 
         // ---- expand + insert + count
         if (!sm.bail) walk_bin<NW, EXT, false>(sm, P, k, padbits, S);

@@ -177,10 +177,11 @@ struct hsk_ctx {
     std::vector<InChunk> in_chunks;
     bool stream_result = false;          // hsk_count: results go to the host buffers group by group
     u32 *d_in_flags = nullptr;           // hsk_count: read table checks (reads.cu), looked at after the first sync
+    DevBuf d_dd;                         // per-CTA lists of distinct supermers (bins.cu: dedup_bin)
     DevBuf d_grp;                        // per bin group: ticket, big-bin counter
     HostBuf h_grp;                       // per bin group: arena cursor after the group
     // extraction
-    DevBuf d_bucket, d_run_list, d_tile_hdr, d_tile_read;   // d_bucket: see run_extract
+    DevBuf d_bucket, d_run_list, d_tile_hdr, d_tile_read, d_bscratch;   // d_bucket: see run_extract
     HostBuf h_bucket;
     DevBuf d_slots;
     // exchange
@@ -312,8 +313,8 @@ void hsk_destroy(hsk_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_len64, &c->d_rtscratch, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bucket, &c->d_slots,
-                    &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_peerinfo, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
+    DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_len64, &c->d_rtscratch, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bscratch, &c->d_bucket, &c->d_slots,
+                    &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_peerinfo, &c->d_dd, &c->d_grp, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
@@ -392,6 +393,7 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
     CK(c->h_meta.ensure(128 * 8));
     CK(c->d_tile_hdr.ensure((P.ntiles + 1) * sizeof(ulonglong2)));
     CK(c->d_tile_read.ensure((P.ntiles + 2) * sizeof(u32)));
+    CK(c->d_bscratch.ensure(bin_scan_scratch_bytes(T)));
     P.tile_read = c->d_tile_read.as<u32>();
     u64 *d_tot = c->d_bucket.as<u64>();
     u64 *d_start = d_tot + T, *d_runcur = d_start + T + 1, *d_ktot = d_runcur + 1;
@@ -423,7 +425,7 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
             c->stats.n_launches += 1;
             tb = te;
         }
-        CK(launch_bin_scan(d_tot, T, d_start, d_cur, d_ktot, s));
+        CK(launch_bin_scan(d_tot, T, d_start, d_cur, d_ktot, c->d_bscratch.as<u64>(), s));
         c->end(c->ev_extract);
         if (before_sync && before_sync()) return 1;
         CK(cudaMemcpyAsync(hm + 0, d_start + T, 8, cudaMemcpyDeviceToHost, s));
@@ -431,7 +433,7 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
         hm[5] = 0;
         if (c->d_in_flags) CK(cudaMemcpyAsync(hm + 5, c->d_in_flags, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        c->stats.n_launches += 1;
+        c->stats.n_launches += 3;
         g_trace.mark("pass A + bin scan done (host sync)");
         if (hm[5] & 1) return fail("a read is longer than 2^32-1 bases");
         if (hm[5] & 2) return fail("DnaBuffer size %llu does not match the read lengths", (unsigned long long)nbytes);
@@ -783,6 +785,14 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     BP.ovf_list = reinterpret_cast<u32 *>(BP.fin + (size_t)2 * TG + 8);
     BP.big_list = BP.ovf_list + TG + 4; BP.big_count = d_bigc;
     BP.group_bins = group_bins ? group_bins : 1;
+    {
+        const char *ev = getenv("HSK_DEDUP");
+        if (NW == 1 && !ext && !(ev && *ev == '0')) {
+            CK(c->d_dd.ensure(bin_dedup_scratch_bytes(c->sm_count)));
+            BP.dd_slots = c->d_dd.as<uint4>();
+            BP.dd_mult = reinterpret_cast<u32 *>(BP.dd_slots + (size_t)c->sm_count * 2 * BN_DDLIMIT);
+        }
+    }
     BP.grp_end = c->d_grp.as<u64>();
     BP.grp_done = reinterpret_cast<u32 *>(BP.grp_end + (size_t)2 * NG); BP.grp_big = BP.grp_done + NG;
     volatile u64 *snap = c->h_grp.as<u64>();

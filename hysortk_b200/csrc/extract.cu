@@ -252,60 +252,121 @@ __global__ void __launch_bounds__(XT_THREADS, XT_CTAS_PER_SM) k_supermer_count(E
     }
 }
 
-// ---- bin scan: exclusive prefix over bins of the slot counts -> bin starts; k-mer total.  One block. ---
-__global__ void __launch_bounds__(1024) k_bin_scan(const u64 *__restrict__ bin_tot, u32 nbins, u64 *__restrict__ bin_start,
-                                                    u64 *__restrict__ bin_cursor, u64 *__restrict__ kmers_total)
+// ---- bin scan: exclusive prefix over bins of the slot counts -> bin starts / cursors; k-mer total ---------
+// Three small launches (tile sums, scan of the tile sums, per-tile scan with its base): the number of bins grows with
+// the number of ranks (150 K at 8 GPUs), so one block must not walk them all.
+constexpr int BS_THREADS = 1024, BS_PER = 4, BS_TILE = BS_THREADS * BS_PER;
+
+__device__ __forceinline__ u64 block_sum_1024(u64 v, u64 *s_c)
+{
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = v;
+    __syncthreads();
+    u64 t = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += s_c[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(BS_THREADS) k_bin_tile_sums(const u64 *__restrict__ bin_tot, u32 nbins, u64 *__restrict__ tile_sums,
+                                                               u64 *__restrict__ kmers_total)
 {
     __shared__ u64 s_c[32];
-    __shared__ u64 carry_c;
-    u64 ksum = 0;
-    if (threadIdx.x == 0) carry_c = 0;
+    u64 slots = 0, kmers = 0;
+#pragma unroll
+    for (int i = 0; i < BS_PER; ++i) {
+        const u32 b = blockIdx.x * BS_TILE + threadIdx.x * BS_PER + i;
+        const u64 v = b < nbins ? bin_tot[b] : 0;
+        slots += v >> 40;
+        kmers += v & ((1ull << 40) - 1);
+    }
+    slots = block_sum_1024(slots, s_c);
+    kmers = block_sum_1024(kmers, s_c);
+    if (threadIdx.x == 0) {
+        tile_sums[blockIdx.x] = slots;
+        if (kmers) atomicAdd(kmers_total, kmers);
+    }
+}
+
+// one block: exclusive scan of the tile sums in place; bin_start[nbins] = total
+__global__ void __launch_bounds__(BS_THREADS) k_bin_tile_scan(u64 *__restrict__ tile_sums, u32 ntiles, u64 *__restrict__ total_out)
+{
+    __shared__ u64 s_c[32];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int PER = 4;
-    for (u32 base = 0; base < nbins; base += 1024 * PER) {
-        u64 c[PER], tc = 0;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            u32 b = base + threadIdx.x * PER + i;
-            u64 v = b < nbins ? bin_tot[b] : 0;
-            ksum += v & ((1ull << 40) - 1);
-            c[i] = v >> 40;
-            tc += c[i];
-        }
-        u64 ic = tc;
+    for (u32 base = 0; base < ntiles; base += BS_THREADS) {
+        const u32 t = base + threadIdx.x;
+        const u64 v = t < ntiles ? tile_sums[t] : 0;
+        u64 inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            u64 a = __shfl_up_sync(FULL, ic, d);
-            if (lane >= d) ic += a;
+            const u64 x = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += x;
         }
-        if (lane == 31) s_c[warp] = ic;
+        if (lane == 31) s_c[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            u64 a = s_c[lane], ia = a;
+            const u64 x = s_c[lane];
+            u64 ix = x;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                u64 x = __shfl_up_sync(FULL, ia, d);
-                if (lane >= d) ia += x;
+                const u64 y = __shfl_up_sync(FULL, ix, d);
+                if (lane >= d) ix += y;
             }
-            s_c[lane] = ia - a;
+            s_c[lane] = ix - x;
         }
         __syncthreads();
-        u64 ec = carry_c + s_c[warp] + ic - tc;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            u32 b = base + threadIdx.x * PER + i;
-            if (b < nbins) { bin_start[b] = ec; bin_cursor[b] = ec; }
-            ec += c[i];
-        }
+        const u64 ex = carry + s_c[warp] + inc - v;
+        if (t < ntiles) tile_sums[t] = ex;
         __syncthreads();
-        if (threadIdx.x == 1023) carry_c = ec;
+        if (threadIdx.x == BS_THREADS - 1) carry = ex + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) bin_start[nbins] = carry_c;
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(BS_THREADS) k_bin_starts(const u64 *__restrict__ bin_tot, u32 nbins, const u64 *__restrict__ tile_base,
+                                                            u64 *__restrict__ bin_start, u64 *__restrict__ bin_cursor)
+{
+    __shared__ u64 s_c[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 c[BS_PER], tc = 0;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) ksum += __shfl_xor_sync(FULL, ksum, d);
-    if (lane == 0 && ksum) atomicAdd(kmers_total, ksum);
+    for (int i = 0; i < BS_PER; ++i) {
+        const u32 b = blockIdx.x * BS_TILE + threadIdx.x * BS_PER + i;
+        c[i] = b < nbins ? (bin_tot[b] >> 40) : 0;
+        tc += c[i];
+    }
+    u64 ic = tc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 a = __shfl_up_sync(FULL, ic, d);
+        if (lane >= d) ic += a;
+    }
+    if (lane == 31) s_c[warp] = ic;
+    __syncthreads();
+    if (warp == 0) {
+        const u64 a = s_c[lane];
+        u64 ia = a;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 x = __shfl_up_sync(FULL, ia, d);
+            if (lane >= d) ia += x;
+        }
+        s_c[lane] = ia - a;
+    }
+    __syncthreads();
+    u64 ec = tile_base[blockIdx.x] + s_c[warp] + ic - tc;
+#pragma unroll
+    for (int i = 0; i < BS_PER; ++i) {
+        const u32 b = blockIdx.x * BS_TILE + threadIdx.x * BS_PER + i;
+        if (b < nbins) { bin_start[b] = ec; bin_cursor[b] = ec; }
+        ec += c[i];
+    }
 }
 
 // ---- pass B: one slot per piece of every valid run ----------------------------------------------------
@@ -369,7 +430,21 @@ __global__ void __launch_bounds__(XT_THREADS) k_supermer_scatter(ExtractParams P
                     }
                     w[x] = wv;
                 }
-                w[PW - 1] = (w[PW - 1] & 0xFFFFFF00u) | len;
+                w[PW - 1] &= 0xFFFFFF00u;
+                if (SW == 4 && !EXT) {
+                    // Orientation: of the supermer and its reverse complement keep the smaller string.  Both hold the
+                    // same canonical k-mers, and copies of a locus read from either strand become bit-identical slots,
+                    // which the bin kernel counts once with a weight (bins.cu: dedup_bin).
+                    const u64 fh = ((u64)w[0] << 32) | w[1], fl = ((u64)w[2] << 32) | w[3];
+                    u64 rh = revcomp64(fl), rl = revcomp64(fh);   // all 64 positions reversed: the string is now at the end
+                    const u32 sh = 2 * (64 - len);                // >= 8: a slot holds at most 60 bases
+                    if (sh >= 64) { rh = rl << (sh - 64); rl = 0; }
+                    else { rh = (rh << sh) | (rl >> (64 - sh)); rl <<= sh; }
+                    if (rh < fh || (rh == fh && rl < fl)) {
+                        w[0] = (u32)(rh >> 32); w[1] = (u32)rh; w[2] = (u32)(rl >> 32); w[3] = (u32)rl;
+                    }
+                }
+                w[PW - 1] |= len;
                 if (EXT) { w[SW - 2] = pos0 + pc * P.slot_nmax; w[SW - 1] = rid; }
                 uint4 *dst = reinterpret_cast<uint4 *>(P.out_stream + gs * SW);
 #pragma unroll
@@ -417,9 +492,15 @@ cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_to
                           std::make_integer_sequence<int, XT_WMAX>{});
 }
 
-cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *bin_cursor, u64 *kmers_total, cudaStream_t s)
+size_t bin_scan_scratch_bytes(u32 nbins) { return ((size_t)(nbins + BS_TILE - 1) / BS_TILE + 2) * sizeof(u64); }
+
+cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *bin_cursor, u64 *kmers_total, u64 *scratch,
+                            cudaStream_t s)
 {
-    k_bin_scan<<<1, 1024, 0, s>>>(bin_tot, nbins, bin_start, bin_cursor, kmers_total);
+    const u32 ntiles = (nbins + BS_TILE - 1) / BS_TILE;
+    k_bin_tile_sums<<<ntiles, BS_THREADS, 0, s>>>(bin_tot, nbins, scratch, kmers_total);
+    k_bin_tile_scan<<<1, BS_THREADS, 0, s>>>(scratch, ntiles, bin_start + nbins);
+    k_bin_starts<<<ntiles, BS_THREADS, 0, s>>>(bin_tot, nbins, scratch, bin_start, bin_cursor);
     return cudaGetLastError();
 }
 

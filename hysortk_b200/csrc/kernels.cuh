@@ -42,7 +42,9 @@ cudaError_t launch_tile_reads(const ExtractParams &P, u32 *tile_read, cudaStream
 cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_tot, u64 *run_list, ulonglong2 *tile_hdr,
                                   u64 *run_cursor, u64 run_capacity, cudaStream_t s);
 // bin_start: nbins+1 exclusive prefix of the slot counts, bin_cursor[b] = bin_start[b]; *kmers_total += all k-mers
-cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *bin_cursor, u64 *kmers_total, cudaStream_t s);
+size_t bin_scan_scratch_bytes(u32 nbins);
+cudaError_t launch_bin_scan(const u64 *bin_tot, u32 nbins, u64 *bin_start, u64 *bin_cursor, u64 *kmers_total, u64 *scratch,
+                            cudaStream_t s);
 // pass B: bin_cursor hands out slot indices inside P.out_stream
 cudaError_t launch_supermer_scatter(const ExtractParams &P, u32 nctas, int nwords, bool ext, const u64 *run_list,
                                     const ulonglong2 *tile_hdr, u64 *bin_cursor, cudaStream_t s);
@@ -64,6 +66,7 @@ cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext,
 
 // ---- stages 4+5 on chip: bins.cu ---------------------------------------------------------------------
 constexpr int BN_THREADS = 512;
+constexpr int BN_DDLIMIT = 1536;     // bins with more supermer slots skip the de-duplication; entries per CTA list
 
 struct BinParams {
     int k;
@@ -91,8 +94,11 @@ struct BinParams {
     u32 *grp_done, *grp_big;             // per group, zeroed: finished bins, bins left to the big gather
     u64 *grp_end;                        // per group: arena cursor (entries, occurrences) after its last bin
     u64 *snap;                           // page-locked host memory or null: per group {entries, occurrences, big bins, ready}
+    // per CTA: list of the distinct supermer slots of the bin it works on and their weights (K <= 32 without EXTENSION)
+    uint4 *dd_slots; u32 *dd_mult;
 };
 
+size_t bin_dedup_scratch_bytes(int sm_count);   // dd_slots + dd_mult of every resident CTA
 int bin_target_kmers(int nwords, bool ext);  // k-mer occurrences per bin the on-chip path is sized for
 // k_bin_count: every bin counted, sorted and written to the arena (or listed for the big gather / the HBM path)
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);

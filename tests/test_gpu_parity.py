@@ -222,3 +222,54 @@ def test_large_properties():
         assert int((w[1:] < w[:-1]).sum()) <= nbins_est + 64
         exp = po.kmer_count(rs.packed, rs.readlens, k, m, 1, 65535, 0, via_supermers=False)
         po.assert_equal(po.canonicalize(k, r["words"], r["cnt"]), exp, "20 Mbp vs oracle")
+
+
+def test_host_pipeline_groups_and_device_path_agree(monkeypatch):
+    """hsk_count streams the arena out in groups of bins while the kernel runs (page-locked completion records);
+    whatever the number of groups, the host result equals hsk_count_device + hsk_fetch_result and the oracle."""
+    import torch
+    k, m = 31, 17
+    rs = synth.sample_fixed(600_000, 12.0, 3000, 0.01, seed=5)
+    exp = po.kmer_count(rs.packed, rs.readlens, k, m, 2, 50, 0, via_supermers=False)
+    off = rs.byte_offsets()
+    d_packed = torch.zeros(((rs.packed.nbytes + 15) // 16) * 16 + 64, dtype=torch.uint8, device="cuda")
+    d_packed[: rs.packed.nbytes].copy_(torch.from_numpy(rs.packed))
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    d_len = torch.from_numpy(rs.readlens.astype(np.uint32).view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    with capi.Context(k, m, 2, 50, 0) as ctx:
+        ctx.count_device(d_packed.data_ptr(), rs.packed.nbytes, d_off.data_ptr(), d_len.data_ptr(), rs.nreads)
+        dev = ctx.fetch()
+        po.assert_equal(po.canonicalize(k, dev["words"], dev["cnt"]), exp, "device path")
+        for groups in ("1", "3", "8", "37"):
+            monkeypatch.setenv("HSK_GROUPS", groups)
+            r = ctx.count(rs.packed, rs.readlens)
+            # same arena, same order: bins in index order, ascending k-mers inside a bin
+            assert np.array_equal(r["words"], dev["words"]) and np.array_equal(r["cnt"], dev["cnt"]), groups
+            assert np.array_equal(r["histogram"], dev["histogram"])
+    monkeypatch.delenv("HSK_GROUPS")
+    # EXTENSION through the same pipeline
+    exp = po.kmer_count(rs.packed, rs.readlens, k, m, 2, 50, 1, via_supermers=False)
+    with capi.Context(k, m, 2, 50, 1) as ctx:
+        for groups in ("2", "8"):
+            monkeypatch.setenv("HSK_GROUPS", groups)
+            c, _ = gpu_counts(ctx, rs.packed, rs.readlens)
+            po.assert_equal(c, exp, f"EXT, {groups} groups")
+
+
+def test_read_table_many_short_and_empty_reads():
+    """reads.cu: offsets / lengths of 50 000 reads (several scan tiles), every fourth one empty, lengths 0..99."""
+    k, m = 21, 11
+    rng = np.random.default_rng(3)
+    genome = synth.make_genome(20_000, 9)
+    reads = []
+    for i in range(50_000):
+        n = 0 if i % 4 == 0 else int(rng.integers(0, 100))
+        st = int(rng.integers(0, len(genome) - 100))
+        reads.append(genome[st:st + n])
+    rs = synth.pack_reads(reads)
+    exp = po.kmer_count(rs.packed, rs.readlens, k, m, 1, 65535, 1, via_supermers=False)
+    with capi.Context(k, m, 1, 65535, 1) as ctx:
+        c, raw = gpu_counts(ctx, rs.packed, rs.readlens)
+        po.assert_equal(c, exp, "short and empty reads")
+        assert raw["stats"]["n_kmers_local"] == rs.num_kmers(k)

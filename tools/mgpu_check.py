@@ -22,7 +22,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
-    for (k, m, ext, read_len) in [(31, 17, 0, 150), (55, 23, 0, 2000), (31, 17, 1, 1000)]:
+    for (k, m, ext, read_len, mode) in [(31, 17, 0, 150, "p2p"), (55, 23, 0, 2000, "p2p"), (31, 17, 1, 1000, "p2p"),
+                                        (31, 17, 0, 1000, "nccl"), (55, 23, 1, 400, "nccl")]:
+        os.environ["HSK_EXCHANGE"] = mode   # read when the context is created
         rs = synth.sample_fixed(300_000, 8.0, read_len, 0.01, seed=17 + k + ext)
         first = hd.partition_reads(rs.readlens, world)
         packed, lens, base = hd.shard(rs.packed, rs.readlens, first, rank)
@@ -33,7 +35,7 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, {kk: r[kk] for kk in ("words", "cnt", "occ_off", "pos", "rid") if kk in r})
         st = r["stats"]
-        print(f"[rank {rank}] k={k} ext={ext}: local k-mers {st['n_kmers_local']} owned {st['n_kmers_owned']} kept {r['n_kept']} "
+        print(f"[rank {rank}] k={k} ext={ext} exchange={mode}: local k-mers {st['n_kmers_local']} owned {st['n_kmers_owned']} kept {r['n_kept']} "
               f"sent {st['bytes_sent']} B recv {st['bytes_received']} B exchange {st['ms_exchange']:.3f} ms", flush=True)
         if rank == 0:
             exp = po.kmer_count(rs.packed, rs.readlens, k, m, 2, 50, ext, via_supermers=False)
@@ -53,7 +55,7 @@ def main():
                 po.assert_equal(got, exp, f"{world}-GPU union vs oracle")
                 assert len(np.unique(words, axis=0)) == len(words), "per-rank results overlap"
                 assert np.array_equal(hist, exp.hist), "all-reduced histogram"
-                print(f"PASS k={k} ext={ext} world={world} kept={got.n}", flush=True)
+                print(f"PASS k={k} ext={ext} exchange={mode} world={world} kept={got.n}", flush=True)
             except AssertionError as e:
                 ok = False
                 print(f"FAIL k={k} ext={ext}: {e}", flush=True)
