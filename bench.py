@@ -57,7 +57,16 @@ def parse_args():
     ap.add_argument("--buckets-per-rank", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-mbp", type=float, default=60.0)
-    return ap.parse_args()
+    # the compile-time parameters of the reference (defaults: BASELINE.json configs[1]); other values time the other
+    # configurations (K=55 M=23: 128-bit k-mer words; --ext 1: ReadId/PosInRead extension)
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--m", type=int, default=M)
+    ap.add_argument("--lower", type=int, default=LOWER)
+    ap.add_argument("--upper", type=int, default=UPPER)
+    ap.add_argument("--ext", type=int, default=EXT)
+    a = ap.parse_args()
+    globals().update(K=a.k, M=a.m, LOWER=a.lower, UPPER=a.upper, EXT=a.ext)
+    return a
 
 
 WORKLOADS = {
@@ -299,7 +308,7 @@ def main_ours(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = total_kmers * args.steps / (ms_e2e * 1e-3)
     h2d = rs.packed.nbytes + rs.nreads * 8
-    d2h = int(re.n_kept) * (8 * ctx.nwords + 4) + (UPPER + 1) * 8 + 16
+    d2h = int(re.n_kept) * (8 * ctx.nwords + 4 + (8 if EXT else 0)) + int(re.n_occ) * 8 * (1 if EXT else 0) + (UPPER + 1) * 8 + 16
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     st = {k: float(np.mean([s[k] for s in stats_acc])) for k in stats_acc[0]}

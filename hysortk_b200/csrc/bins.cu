@@ -63,7 +63,12 @@ struct BinCfg {
     static constexpr int CTAS = NW == 1 ? (EXT ? 3 : 2) : 1;
     // most k-mers one slot can hold (smallest K of the word count) = rounds of 32 k-mers a batch of 32 slots can need
     static constexpr int NMAX = 16 * (PW - 1) + 12 - (NW == 1 ? 3 : (NW == 2 ? 33 : 65)) + 1;
-    static constexpr int HEADW = (NMAX + 31) / 32 * 32;
+    // slots per walk batch (a warp stages them) and kept k-mers a CTA sorts itself (two per thread); a bin that keeps
+    // more goes through the staging area + big gather.  (Two CTAs per SM with half-size tables for K in 33..64 were
+    // measured slower than one CTA with the big table: 7.1 vs 6.0 ms at c2.)
+    static constexpr int BATCH = 32;
+    static constexpr int SORTCAP = 2 * BN_THREADS;
+    static constexpr int HEADW = ((BATCH * NMAX + 31) / 32 + 3) / 4 * 4;   // rounds of 32 k-mers a batch can need
     static constexpr int TARGET = NW == 1 ? (EXT ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
 };
 
@@ -76,16 +81,15 @@ int bin_target_kmers(int nwords, bool ext)
     return BinCfg<3, false>::TARGET;
 }
 
-constexpr int BN_SORTCAP = 2 * BN_THREADS;      // kept k-mers a CTA sorts itself (two per thread); more: staging + big gather
 
 // scratch of a CTA, used by the walk (staged slots, scan, slot-start bitmap of every warp) and then by the sort of
 // the kept k-mers (exchange buffers; the compacted slot list sits at their start until it has been consumed)
 template <int NW, bool EXT>
 struct BinScratchCfg {
     using Cfg = BinCfg<NW, EXT>;
-    static constexpr int STG_U4 = 32 * Cfg::SW / 4 + 2;                       // uint4 per warp (+ pad)
+    static constexpr int STG_U4 = Cfg::BATCH * Cfg::SW / 4 + 2;                       // uint4 per warp (+ pad)
     static constexpr size_t WALK = (size_t)BN_WARPS * (STG_U4 * 16 + 32 * 2 + Cfg::HEADW * 4);
-    static constexpr size_t SORT = (size_t)BN_SORTCAP * (8 * NW + 4);
+    static constexpr size_t SORT = (size_t)Cfg::SORTCAP * (8 * NW + 4);
     static constexpr size_t BYTES = (WALK > SORT ? WALK : SORT + 15) / 16 * 16;
 };
 
@@ -106,6 +110,7 @@ struct BinSmem {
     u64 base_k, base_o;                                     // where the bin's entries / occurrences go
     u32 *occ_pos; int *occ_rid;                             // EXT pass 2 target arrays (arena, or staging for big bins)
     u32 bin, nk, S, bail, next_batch, seen, ncand;
+    u32 batch_slots;                                        // slots per walk batch: 32, fewer when the bin has few slots
     int nsrc;                                               // sources of the walk: P.nsrc, or 1 when the bin was de-duplicated
     const u32 *mult;                                        // weight per slot (de-duplicated bins) or null
 
@@ -117,9 +122,9 @@ struct BinSmem {
         return reinterpret_cast<u32 *>(scratch + (size_t)BN_WARPS * (Scr::STG_U4 * 16 + 64)) + (size_t)warp * Cfg::HEADW;
     }
     // sort layout
-    __device__ u64 *xkey() { return reinterpret_cast<u64 *>(scratch); }                                   // [NW][BN_SORTCAP]
-    __device__ u32 *xpay() { return reinterpret_cast<u32 *>(scratch + (size_t)BN_SORTCAP * 8 * NW); }     // [BN_SORTCAP]
-    __device__ u16 *klist() { return reinterpret_cast<u16 *>(scratch); }                                  // [BN_SORTCAP], before the sort
+    __device__ u64 *xkey() { return reinterpret_cast<u64 *>(scratch); }                                   // [NW][SORTCAP]
+    __device__ u32 *xpay() { return reinterpret_cast<u32 *>(scratch + (size_t)Cfg::SORTCAP * 8 * NW); }   // [SORTCAP]
+    __device__ u16 *klist() { return reinterpret_cast<u16 *>(scratch); }                                  // [SORTCAP], before the sort
 };
 
 // block-wide exclusive scan of two u32 values (BN_THREADS threads); returns exclusive prefixes and totals
@@ -325,11 +330,12 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
     u32 pre_m = 1;
     const u32 *const mult = sm.mult;   // de-duplicated bin: slots come from the CTA's own list (written by this kernel:
                                        // coherent loads), each with the number of copies it stands for
+    const u32 BS = sm.batch_slots;
     auto claim = [&](u32 &j0) {
         u32 bt = 0;
         if (lane == 0) bt = atomicAdd(&sm.next_batch, 1u);
-        j0 = __shfl_sync(0xFFFFFFFFu, bt, 0) * 32u;
-        if (j0 < S && j0 + lane < S) {
+        j0 = __shfl_sync(0xFFFFFFFFu, bt, 0) * BS;
+        if ((u32)lane < BS && j0 + lane < S) {
             const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j0 + lane, SW));
             if (mult) {
 #pragma unroll
@@ -345,7 +351,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
     claim(j0);
     while (j0 < S) {
         u32 n = 0, my_m = 1;
-        if (j0 + lane < S) {
+        if ((u32)lane < BS && j0 + lane < S) {
 #pragma unroll
             for (int x = 0; x < SW / 4; ++x) stg4[lane * (SW / 4) + x] = pre[x];
             const uint4 v = pre[(PW - 1) / 4];
@@ -454,7 +460,7 @@ __device__ __forceinline__ u64 lookback(volatile u64 *st, u32 lb)
 
 // Bitonic sort of BN_THREADS * EPT elements spread over the CTA (element e = tid * EPT + r): partners inside a
 // thread are exchanged in registers, inside a warp by shuffles, further away through the exchange buffers.
-template <int NW, int EPT>
+template <int NW, int EPT, int CAP>
 __device__ __forceinline__ void block_sort(u64 (&key)[EPT][NW], u32 (&pay)[EPT], u32 n2, u64 *xkey, u32 *xpay)
 {
     const u32 tid = threadIdx.x;
@@ -481,7 +487,7 @@ __device__ __forceinline__ void block_sort(u64 (&key)[EPT][NW], u32 (&pay)[EPT],
                     for (int r = 0; r < EPT; ++r) {
                         const u32 e = tid * EPT + r;
 #pragma unroll
-                        for (int l = 0; l < NW; ++l) xkey[(size_t)l * BN_SORTCAP + e] = key[r][l];
+                        for (int l = 0; l < NW; ++l) xkey[(size_t)l * CAP + e] = key[r][l];
                         xpay[e] = pay[r];
                     }
                 }
@@ -496,7 +502,7 @@ __device__ __forceinline__ void block_sort(u64 (&key)[EPT][NW], u32 (&pay)[EPT],
                 if (ts >= 32) {
                     const u32 j = e ^ stride;
 #pragma unroll
-                    for (int l = 0; l < NW; ++l) pk[l] = xkey[(size_t)l * BN_SORTCAP + j];
+                    for (int l = 0; l < NW; ++l) pk[l] = xkey[(size_t)l * CAP + j];
                     pp = xpay[j];
                 } else {
 #pragma unroll
@@ -560,7 +566,7 @@ __device__ __forceinline__ void sort_emit(BinSmem<NW, EXT> &sm, const BinParams 
     u32 n2 = 2;
     while (n2 < tk) n2 <<= 1;
     __syncthreads();   // the slot list has been read: the scratch becomes the exchange buffer
-    block_sort<NW, EPT>(key, pay, n2, sm.xkey(), sm.xpay());
+    block_sort<NW, EPT, BinCfg<NW, EXT>::SORTCAP>(key, pay, n2, sm.xkey(), sm.xpay());
     u32 off[EPT];
     if (EXT) {
         // occurrence lists follow the sorted order: offsets inside the bin, left in the slots' counters as cursors
@@ -662,7 +668,12 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
             __syncthreads();
         }
 
-        // ---- expand + insert + count
+        // ---- expand + insert + count.  About two batches per warp, so that the warps finish together
+        if (tid == 0) {
+            u32 bs = (S + 2 * BN_WARPS - 1) / (2 * BN_WARPS);
+            sm.batch_slots = min((u32)Cfg::BATCH, max(8u, bs));
+        }
+        __syncthreads();
         if (!sm.bail) walk_bin<NW, EXT, false>(sm, P, k, padbits, S);
         __syncthreads();
         if (!sm.bail && sm.seen != nk && tid == 0) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
@@ -685,7 +696,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         u32 ek, eo, tk, to;
         block_scan2(kept, occ, sm.wa, sm.wb, ek, eo, tk, to);
         if (!EXT) to = 0;
-        const bool big = tk > (u32)BN_SORTCAP;   // too many kept k-mers to sort here: staging area + big gather
+        const bool big = tk > (u32)Cfg::SORTCAP;   // too many kept k-mers to sort here: staging area + big gather
         if (tid == 0) {
             volatile u64 *lbs = P.lb_state;
             lbs[lb] = LB_AGG | tk;
@@ -721,7 +732,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
                 }
             }
             __syncthreads();
-            if (tk <= (u32)BN_THREADS) sort_emit<NW, EXT, 1>(sm, P, lb, tk, to);
+            if (Cfg::SORTCAP <= BN_THREADS || tk <= (u32)BN_THREADS) sort_emit<NW, EXT, 1>(sm, P, lb, tk, to);
             else sort_emit<NW, EXT, 2>(sm, P, lb, tk, to);
             if (EXT && tid == 0) { sm.occ_pos = P.out_pos; sm.occ_rid = P.out_rid; }
         } else {
