@@ -249,15 +249,29 @@ __device__ __forceinline__ u32 table_find(BinSmem<NW, EXT> &sm, const u64 (&key)
 // in global memory (L2-resident) and the walk then expands each of them once.  K <= 32 without EXTENSION only: with
 // EXTENSION every occurrence needs its own (pos, rid) anyway.
 //   cells: sm.cnt[0 .. BN_DDTS)   weights: sm.cnt[BN_DDTS .. 2 BN_DDTS)   keys: (uint4 *)sm.fp [0 .. BN_DDTS)
+constexpr int BN_DDPT = BN_DDLIMIT / BN_THREADS;   // slots per thread
+
+// the slots of a thread, fetched early (they may come over NVLink) while the table is being cleared
 template <int NW, bool EXT>
-__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &P, u32 S)
+__device__ __forceinline__ void dedup_fetch(const BinSmem<NW, EXT> &sm, const BinParams &P, u32 S, uint4 (&v)[BN_DDPT])
 {
-    constexpr int SW = BinCfg<NW, EXT>::SW;
+#pragma unroll
+    for (int i = 0; i < BN_DDPT; ++i) {
+        const u32 j = threadIdx.x + i * BN_THREADS;
+        if (j < S) v[i] = __ldg(reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j, BinCfg<NW, EXT>::SW)));
+    }
+}
+
+template <int NW, bool EXT>
+__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &P, u32 S, const uint4 (&vs)[BN_DDPT])
+{
     const u32 tid = threadIdx.x;
     uint4 *dk = reinterpret_cast<uint4 *>(sm.fp);
     u32 *cell = sm.cnt, *wgt = sm.cnt + BN_DDTS;
-    for (u32 j = tid; j < S; j += BN_THREADS) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j, SW)));
+#pragma unroll
+    for (int i = 0; i < BN_DDPT; ++i) {
+        if (tid + i * BN_THREADS >= S) break;
+        const uint4 v = vs[i];
         const u64 a = ((u64)v.y << 32) | v.x, b = ((u64)v.w << 32) | v.z;
         u64 h = (a * 0x9E3779B97F4A7C15ull) ^ (b * 0xC2B2AE3D27D4EB4Full);
         h ^= h >> 29;
@@ -605,7 +619,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
     using Cfg = BinCfg<NW, EXT>;
     constexpr int SW = Cfg::SW;
     constexpr bool DEDUP = (NW == 1) && !EXT;
-    static_assert(!DEDUP || (2 * BN_DDTS <= Cfg::TS && BN_DDTS % BN_THREADS == 0 && BN_DDLIMIT < BN_DDTS), "supermer table fits the k-mer table");
+    static_assert(!DEDUP || (2 * BN_DDTS <= Cfg::TS && BN_DDTS % BN_THREADS == 0 && BN_DDLIMIT < BN_DDTS && BN_DDLIMIT % BN_THREADS == 0), "supermer table fits the k-mer table");
     extern __shared__ __align__(16) unsigned char smraw[];
     BinSmem<NW, EXT> &sm = *reinterpret_cast<BinSmem<NW, EXT> *>(smraw);
     const int tid = threadIdx.x;
@@ -617,14 +631,6 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
     while (true) {
         __syncthreads();   // end of the previous bin: shared memory is free again
         if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; }
-        {
-            const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
-            if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
-            else { for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp32)[i] = ones; }
-            // de-duplication first uses the counters as its cells (empty = all ones) and weights
-            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS)
-                reinterpret_cast<uint4 *>(sm.cnt)[i] = (DEDUP && i < BN_DDTS / 4) ? ones : zero;
-        }
         __syncthreads();
         const u32 lb = sm.bin;
         if (lb >= P.nbins) break;
@@ -649,23 +655,37 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         __syncthreads();
         const u32 nk = sm.nk;
         u32 S = sm.S;
-        if (DEDUP) {
-            const bool dd = !sm.bail && S > 0 && S <= (u32)BN_DDLIMIT && P.dd_slots != nullptr;
-            u32 Sd = 0;
-            if (dd) Sd = dedup_bin<NW, EXT>(sm, P, S);
-            __syncthreads();   // the list is complete; the table memory goes back to the k-mers
-            {
-                const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
-                for (int i = tid; i < BN_DDTS; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones;
-                for (int i = tid; i < 2 * BN_DDTS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
+        const bool dd = DEDUP && !sm.bail && S > 0 && S <= (u32)BN_DDLIMIT && P.dd_slots != nullptr;
+        uint4 ddv[BN_DDPT];
+        if constexpr (DEDUP) { if (dd) dedup_fetch<NW, EXT>(sm, P, S, ddv); }
+
+        // ---- empty table (the slots of a de-duplicated bin are on their way meanwhile)
+        {
+            const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
+            if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
+            else { for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp32)[i] = ones; }
+            // de-duplication first uses the counters as its cells (empty = all ones) and weights
+            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS)
+                reinterpret_cast<uint4 *>(sm.cnt)[i] = (dd && i < BN_DDTS / 4) ? ones : zero;
+        }
+        __syncthreads();
+        if constexpr (DEDUP) {
+            if (dd) {
+                const u32 Sd = dedup_bin<NW, EXT>(sm, P, S, ddv);
+                __syncthreads();   // the list is complete; the table memory goes back to the k-mers
+                {
+                    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
+                    for (int i = tid; i < BN_DDTS; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones;
+                    for (int i = tid; i < 2 * BN_DDTS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
+                }
+                if (tid == 0) {
+                    sm.nsrc = 1;
+                    sm.src_ptr[0] = reinterpret_cast<const u32 *>(P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT);
+                    sm.mult = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
+                }
+                S = Sd;
+                __syncthreads();
             }
-            if (dd && tid == 0) {
-                sm.nsrc = 1;
-                sm.src_ptr[0] = reinterpret_cast<const u32 *>(P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT);
-                sm.mult = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
-            }
-            if (dd) S = Sd;
-            __syncthreads();
         }
 
         // ---- expand + insert + count.  About two batches per warp, so that the warps finish together

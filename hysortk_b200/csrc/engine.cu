@@ -22,6 +22,7 @@
 #include <functional>
 #include <unistd.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace hsk;
@@ -1098,10 +1099,21 @@ int hsk_fill_entries(hsk_ctx *c, void *entries, uint64_t capacity_entries)
     const u64 *w = c->h_owords.as<u64>();
     const u32 *cnt = c->h_ocnt.as<u32>();
     u64 *dst = reinterpret_cast<u64 *>(entries);
-    for (u64 i = 0; i < c->n_kept; ++i) {
-        for (int l = 0; l < NW; ++l) dst[i * (NW + 1) + l] = w[i * NW + l];
-        dst[i * (NW + 1) + NW] = cnt[i];
-    }
+    // SoA -> {TKmer kmer; uint64_t cnt;} entries (reference KmerListEntryS, include/kmer.hpp:368-407), a few host
+    // threads: the loop is memory-bound and the list has millions of entries
+    const u64 n = c->n_kept;
+    auto fill = [=](u64 lo, u64 hi) {
+        for (u64 i = lo; i < hi; ++i) {
+            for (int l = 0; l < NW; ++l) dst[i * (NW + 1) + l] = w[i * NW + l];
+            dst[i * (NW + 1) + NW] = cnt[i];
+        }
+    };
+    unsigned nt = std::min<unsigned>(8u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
+    if (n < (1u << 16)) nt = 1;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(fill, n * t / nt, n * (t + 1) / nt);
+    fill(0, n / nt);
+    for (auto &x : th) x.join();
     return 0;
 }
 

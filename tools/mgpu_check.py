@@ -22,14 +22,16 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
-    for (k, m, ext, read_len, mode) in [(31, 17, 0, 150, "p2p"), (55, 23, 0, 2000, "p2p"), (31, 17, 1, 1000, "p2p"),
-                                        (31, 17, 0, 1000, "nccl"), (55, 23, 1, 400, "nccl")]:
+    # (k, m, ext, read length, exchange mode, bins per rank: 0 = sized from the input -> small bins, supermer
+    # de-duplication across the sources of a bin)
+    for (k, m, ext, read_len, mode, bpr) in [(31, 17, 0, 150, "p2p", 64), (55, 23, 0, 2000, "p2p", 64), (31, 17, 1, 1000, "p2p", 64),
+                                             (31, 17, 0, 3000, "p2p", 0), (31, 17, 0, 1000, "nccl", 0), (55, 23, 1, 400, "nccl", 64)]:
         os.environ["HSK_EXCHANGE"] = mode   # read when the context is created
-        rs = synth.sample_fixed(300_000, 8.0, read_len, 0.01, seed=17 + k + ext)
+        rs = synth.sample_fixed(300_000, 8.0 if bpr else 30.0, read_len, 0.01, seed=17 + k + ext)
         first = hd.partition_reads(rs.readlens, world)
         packed, lens, base = hd.shard(rs.packed, rs.readlens, first, rank)
         assert hd.readid_base(len(lens)) == base
-        ctx = hd.create_context(k, m, 2, 50, ext, buckets_per_rank=64)
+        ctx = hd.create_context(k, m, 2, 50, ext, buckets_per_rank=bpr)
         r = ctx.count(packed, lens, readid_base=base)
         hist = ctx.allreduce_histogram()
         gathered = [None] * world
