@@ -49,7 +49,7 @@ UNIT = "kmers/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_150Mbp_10kbp")
@@ -116,7 +116,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.device), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -219,6 +219,15 @@ def main_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if args.gpus > 1 and world == 1:
         raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+    if world > 1:
+        # one rank per GPU: keep the rank's host thread (and so its page-locked buffers, first touch) on the CPUs next to
+        # its GPU; without it half of the ranks stage their H2D / D2H copies through the other socket
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception as e:   # not fatal: only the host-buffer (e2e) path is affected
+            print(f"[bench] no CPU affinity for rank {rank}: {e}", file=sys.stderr)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     nccl_id = None

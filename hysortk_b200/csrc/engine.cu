@@ -454,9 +454,16 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
 static int extract_scatter(hsk_ctx *c, u64 *d_cur)
 {
     cudaStream_t s = c->stream;
-    const ExtractParams &P = c->xp;
+    ExtractParams P = c->xp;
+    // the scatter pass is latency-bound (one atomic + one store per supermer) and light on registers: more CTAs per SM
+    // than the count pass
+    u32 per_sm = 8;
+    if (const char *ev = getenv("HSK_SCATTER_CTAS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) per_sm = (u32)v; }
+    const u32 nctas = (u32)c->sm_count * per_sm;
+    const u64 nwarps = (u64)nctas * XT_WARPS;
+    P.tiles_per_warp = (u32)((P.ntiles + nwarps - 1) / nwarps);
     c->begin(c->ev_extract);
-    if (P.ntiles) CK(launch_supermer_scatter(P, c->x_nctas, c->nwords, c->cfg.ext != 0, c->d_run_list.as<u64>(),
+    if (P.ntiles) CK(launch_supermer_scatter(P, nctas, c->nwords, c->cfg.ext != 0, c->d_run_list.as<u64>(),
                                              c->d_tile_hdr.as<ulonglong2>(), d_cur, s));
     c->end(c->ev_extract);
     g_trace.mark("scatter enqueued");
@@ -765,7 +772,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     CK(c->d_hist.ensure(hist_bins * 8));
     CK(cudaMemsetAsync(c->d_hist.p, 0, hist_bins * 8, s));
     // per-bin records: look-back cells (zeroed), staging records of the big bins, overflow / big lists
-    int NG = (c->stream_result && TG >= 2048) ? 8 : 1;
+    int NG = (c->stream_result && TG >= 2048) ? 32 : 1;
     if (const char *ev = getenv("HSK_GROUPS")) { const int v = atoi(ev); if (v >= 1 && v <= 64 && c->stream_result) NG = v; }
     const u32 group_bins = (TG + (u32)NG - 1) / (u32)NG;
     NG = group_bins ? (int)((TG + group_bins - 1) / group_bins) : 1;
