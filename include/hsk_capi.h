@@ -37,7 +37,7 @@ typedef struct hsk_ctx hsk_ctx;
  * the C++ shim forwards here at run time. */
 typedef struct hsk_config {
     int32_t k;     /* KMER_SIZE, 2 < k < 96                                   */
-    int32_t m;     /* MINIMIZER_SIZE, 0 < m < k (values above 32 use the first 32 bases' window; the
+    int32_t m;     /* MINIMIZER_SIZE, 0 < m < k (the engine uses min(m, 32), raised so that k - m + 1 <= 64; the
                       result does not depend on the minimizer)  */
     int32_t lower; /* LOWER_KMER_FREQ                                          */
     int32_t upper; /* UPPER_KMER_FREQ, lower <= upper <= 65535                 */
@@ -73,8 +73,9 @@ typedef struct hsk_stats {
 /* Result of one rank.  Arrays live in page-locked host memory owned by the context and stay valid
  * until the next hsk_count / hsk_destroy on it.  Entry i: k-mer words kmer_words[i*nwords + w]
  * (word 0 = bases 0..31, 2 bits per base from the most significant bit; reference
- * include/kmer.hpp:165-185), count cnt[i].  Entries are grouped in batches of minimizer buckets;
- * inside a batch they ascend by k-mer (reference: per-task sorted runs, kmerops.cpp:883-904).
+ * include/kmer.hpp:165-185), count cnt[i].  Entries are grouped by minimizer bin, bins in index order
+ * (bins that went through the HBM path follow at the end), and ascend by k-mer inside a bin
+ * (reference: per-task sorted runs, kmerops.cpp:883-904); the order is deterministic.
  * With ext, the occurrences of entry i are pos/rid[occ_off[i] .. occ_off[i+1]) (reference
  * KmerListEntryS::pos/rid, kmer.hpp:383-400).  histogram[c] = number of kept k-mers with count c
  * on this rank, upper+1 bins (hysortk.cpp:106-113). */
@@ -109,8 +110,9 @@ typedef struct hsk_device_result {
 const char *hsk_last_error(void);
 int hsk_version(void);
 
-/* ncclGetUniqueId for the supermer all-to-all (replaces the MPI communicator of
- * exchange_supermer, kmerops.cpp:130-195). */
+/* ncclGetUniqueId for the collectives of the supermer exchange (bin totals, barrier, histogram; the
+ * supermers themselves are read in place from the peers' memory, or shipped with ncclSend/ncclRecv when
+ * HSK_EXCHANGE=nccl) — replaces the MPI communicator of exchange_supermer, kmerops.cpp:130-195. */
 int hsk_get_unique_id(void *id_out /* HSK_NCCL_ID_BYTES */);
 
 int hsk_create(hsk_ctx **ctx, const hsk_config *cfg);
