@@ -193,7 +193,10 @@ def main_reference(args):
         return
     rs, meta = make_shard(args.workload, 0, 1)
     steps, warmup = args.steps, min(args.warmup, 1) if args.steps <= 2 else args.warmup
-    r = run_reference(rs, args.cpu_sample_mbp * 1e6 / 2, steps, warmup)
+    # every step = the reference on a prefix of the workload, sized so that the whole run stays around a minute of CPU
+    # time at the reference's ~45 M k-mers/s (30 Mbp per step for short runs, less when many steps are asked for)
+    sample_mbp = min(args.cpu_sample_mbp / 2, max(2.0, 2400.0 / max(1, steps + warmup)))
+    r = run_reference(rs, sample_mbp * 1e6, steps, warmup)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference; run oracle/build_ref.sh)"}))
         return

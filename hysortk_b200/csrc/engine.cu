@@ -1,12 +1,15 @@
 // C-ABI engine (include/hsk_capi.h): context, buffers, stage orchestration, supermer exchange.
 //
 // Replaces the body of the reference's hysortk::kmer_count (src/hysortk.cpp:36-95):
-//   prepare_supermer  (kmerops.cpp:23-126)   -> extract.cu   (count pass, bucket scan, scatter pass)
-//   exchange_supermer (kmerops.cpp:130-195)  -> grouped ncclSend/ncclRecv of whole bucket ranges
-//                                               (TaskManager::exchange 80 KB rounds, :814-1007)
-//   filter_kmer       (kmerops.cpp:198-250)  -> per batch of buckets: expand.cu, radix.cu, count.cu
-// The reference's task system (TaskManager, classifier, dispatcher) has no equivalent here: buckets
-// are owned by rank in contiguous ranges and processed in batches sized for HBM.
+//   prepare_supermer  (kmerops.cpp:23-126)   -> reads.cu (read table), extract.cu (count pass, bin scan, scatter pass)
+//   exchange_supermer (kmerops.cpp:130-195)  -> all-gather of the bin totals + CUDA IPC: the bin kernel reads the peers'
+//                                               supermer streams in place over NVLink (TaskManager::exchange 80 KB
+//                                               rounds, :814-1007); HSK_EXCHANGE=nccl: grouped ncclSend/ncclRecv
+//   filter_kmer       (kmerops.cpp:198-250)  -> bins.cu: one persistent kernel expands, counts, sorts and emits every
+//                                               bin; skewed bins go through expand.cu, radix.cu, count.cu (HBM path)
+// The reference's task system (TaskManager, classifier, dispatcher) has no equivalent here: bins are owned by rank in
+// contiguous ranges.  hsk_count additionally pipelines the host copies around the kernels (chunked H2D under the
+// extraction count pass, result groups streamed out while the bin kernel runs).
 #include "../../include/hsk_capi.h"
 #include "kernels.cuh"
 
