@@ -16,7 +16,7 @@ SO = os.path.join(HERE, "libhysortk_b200.so")
 SOURCES = ["reads.cu", "extract.cu", "expand.cu", "radix.cu", "count.cu", "bins.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]
+         "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function", "-Xcompiler", "-Wno-unknown-pragmas"]
 
 
 def _newest(paths):

@@ -503,7 +503,6 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
     cudaStream_t s = c->stream;
     const int NW = c->nwords;
     const bool ext = c->cfg.ext != 0;
-    const int me = c->cfg.rank;
     u64 cap = c->cfg.batch_kmers ? c->cfg.batch_kmers : (1ull << 28);
     cap = std::min<u64>(cap, (1ull << 29) - 1);
     size_t first = 0;
@@ -538,7 +537,6 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
         for (size_t i = first; i < last; ++i) {
             const OvfSeg &g = segs[i];
             if (g.nslots == 0) continue;
-            const bool local = (g.src == me);
             const int SW = slot_words(NW, ext);
             ExpandSegment seg;
             seg.slots = c->src_slots[g.src] + g.i0 * (u64)SW;
