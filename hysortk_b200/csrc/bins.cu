@@ -72,7 +72,7 @@ struct BinCfg {
     static constexpr int TARGET = NW == 1 ? (EXT ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
 };
 
-size_t bin_dedup_scratch_bytes(int sm_count) { return (size_t)sm_count * 2 * BN_DDLIMIT * (sizeof(uint4) + sizeof(u32)); }
+size_t bin_dedup_scratch_bytes(int sm_count, int slot_words) { return (size_t)sm_count * 2 * BN_DDLIMIT * ((size_t)slot_words * 4 + sizeof(u32)); }
 
 int bin_target_kmers(int nwords, bool ext)
 {
@@ -98,7 +98,7 @@ struct BinSmem {
     using Cfg = BinCfg<NW, EXT>;
     using Scr = BinScratchCfg<NW, EXT>;
     alignas(16) u64 fp[NW == 1 ? Cfg::TS : 1];              // K <= 32: the k-mer itself is the CAS key
-    u64 kw[NW > 1 ? NW : 1][NW > 1 ? Cfg::TS : 1];          // K > 32: full key words ...
+    alignas(16) u64 kw[NW > 1 ? NW : 1][NW > 1 ? Cfg::TS : 1];   // K > 32: full key words ...
     alignas(16) u32 fp32[NW > 1 ? Cfg::TS : 1];             //         ... guarded by a 32-bit fingerprint cell
     alignas(16) u32 cnt[Cfg::TS];                           // occurrences per slot; EXT pass 2: next occurrence offset
     alignas(16) unsigned char scratch[Scr::BYTES];
@@ -244,36 +244,54 @@ __device__ __forceinline__ u32 table_find(BinSmem<NW, EXT> &sm, const u64 (&key)
 // At 30x coverage most supermers of a bin are exact copies of another one: the same locus read again without an error
 // in those ~40 bases (the scatter pass stores every supermer in its canonical orientation, so the strand does not
 // matter).  Before the walk, the slots of the bin go through a small table in the (still unused) k-mer table memory:
-// key = the 16-byte slot, guarded by a fingerprint cell with the same EMPTY -> LOCK -> publish claim as the K > 32
-// k-mer table; value = number of copies.  The distinct slots and their weights are compacted into the CTA's own list
-// in global memory (L2-resident) and the walk then expands each of them once.  K <= 32 without EXTENSION only: with
-// EXTENSION every occurrence needs its own (pos, rid) anyway.
-//   cells: sm.cnt[0 .. BN_DDTS)   weights: sm.cnt[BN_DDTS .. 2 BN_DDTS)   keys: (uint4 *)sm.fp [0 .. BN_DDTS)
+// key = the whole slot (16 bytes for K <= 32, 32 bytes for K in 33..64), guarded by a fingerprint cell with the same
+// EMPTY -> LOCK -> publish claim as the K > 32 k-mer table; value = number of copies.  The distinct slots and their
+// weights are compacted into the CTA's own list in global memory (L2-resident) and the walk then expands each of them
+// once.  Without EXTENSION only: with EXTENSION every occurrence needs its own (pos, rid) anyway.
+//   cells: sm.cnt[0 .. BN_DDTS)   weights: sm.cnt[BN_DDTS .. 2 BN_DDTS)   keys: sm.fp (K <= 32) / sm.kw (K > 32), as uint4
 constexpr int BN_DDPT = BN_DDLIMIT / BN_THREADS;   // slots per thread
+
+template <int NW, bool EXT>
+__device__ __forceinline__ uint4 *dedup_keys(BinSmem<NW, EXT> &sm)
+{
+    return NW == 1 ? reinterpret_cast<uint4 *>(sm.fp) : reinterpret_cast<uint4 *>(&sm.kw[0][0]);
+}
 
 // the slots of a thread, fetched early (they may come over NVLink) while the table is being cleared
 template <int NW, bool EXT>
-__device__ __forceinline__ void dedup_fetch(const BinSmem<NW, EXT> &sm, const BinParams &P, u32 S, uint4 (&v)[BN_DDPT])
+__device__ __forceinline__ void dedup_fetch(const BinSmem<NW, EXT> &sm, const BinParams &P, u32 S,
+                                            uint4 (&v)[BN_DDPT][BinCfg<NW, EXT>::SW / 4])
 {
+    constexpr int SW = BinCfg<NW, EXT>::SW;
 #pragma unroll
     for (int i = 0; i < BN_DDPT; ++i) {
         const u32 j = threadIdx.x + i * BN_THREADS;
-        if (j < S) v[i] = __ldg(reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j, BinCfg<NW, EXT>::SW)));
+        if (j < S) {
+            const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j, SW));
+#pragma unroll
+            for (int x = 0; x < SW / 4; ++x) v[i][x] = __ldg(sp + x);
+        }
     }
 }
 
 template <int NW, bool EXT>
-__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &P, u32 S, const uint4 (&vs)[BN_DDPT])
+__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &P, u32 S,
+                                         const uint4 (&vs)[BN_DDPT][BinCfg<NW, EXT>::SW / 4])
 {
+    constexpr int Q = BinCfg<NW, EXT>::SW / 4;   // uint4 per slot
     const u32 tid = threadIdx.x;
-    uint4 *dk = reinterpret_cast<uint4 *>(sm.fp);
+    uint4 *dk = dedup_keys<NW, EXT>(sm);
     u32 *cell = sm.cnt, *wgt = sm.cnt + BN_DDTS;
 #pragma unroll
     for (int i = 0; i < BN_DDPT; ++i) {
         if (tid + i * BN_THREADS >= S) break;
-        const uint4 v = vs[i];
-        const u64 a = ((u64)v.y << 32) | v.x, b = ((u64)v.w << 32) | v.z;
-        u64 h = (a * 0x9E3779B97F4A7C15ull) ^ (b * 0xC2B2AE3D27D4EB4Full);
+        u64 h = 0;
+#pragma unroll
+        for (int x = 0; x < Q; ++x) {
+            const uint4 v = vs[i][x];
+            const u64 a = ((u64)v.y << 32) | v.x, b = ((u64)v.w << 32) | v.z;
+            h = (h ^ (h >> 31)) * 0x94D049BB133111EBull + ((a * 0x9E3779B97F4A7C15ull) ^ (b * 0xC2B2AE3D27D4EB4Full));
+        }
         h ^= h >> 29;
         h *= 0xBF58476D1CE4E5B9ull;
         const u32 f = (u32)h & 0x7FFFFFFFu;
@@ -284,7 +302,8 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &
             if (old == BN_EMPTY32) {
                 old = atomicCAS(&cell[idx], BN_EMPTY32, BN_LOCK32);
                 if (old == BN_EMPTY32) {
-                    dk[idx] = v;
+#pragma unroll
+                    for (int x = 0; x < Q; ++x) dk[idx * Q + x] = vs[i][x];
                     __threadfence_block();
                     *c = f;
                     break;
@@ -292,8 +311,14 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &
             }
             while (old == BN_LOCK32) old = *c;
             if (old == f) {
-                const volatile u32 *q = reinterpret_cast<const volatile u32 *>(&dk[idx]);
-                if (q[0] == v.x && q[1] == v.y && q[2] == v.z && q[3] == v.w) break;
+                const volatile u32 *q = reinterpret_cast<const volatile u32 *>(&dk[idx * Q]);
+                bool same = true;
+#pragma unroll
+                for (int x = 0; x < Q; ++x) {
+                    const uint4 v = vs[i][x];
+                    same = same && q[4 * x] == v.x && q[4 * x + 1] == v.y && q[4 * x + 2] == v.z && q[4 * x + 3] == v.w;
+                }
+                if (same) break;
             }
             idx = (idx + 1) & (BN_DDTS - 1);
         }
@@ -309,12 +334,13 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &
     }
     u32 ex, d0, total, d1;
     block_scan2(used, 0u, sm.wa, sm.wb, ex, d0, total, d1);
-    uint4 *outs = P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT;
+    uint4 *outs = P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT * Q;
     u32 *outm = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         if ((mask >> i) & 1) {
-            __stcg(&outs[ex], dk[tid * PER + i]);
+#pragma unroll
+            for (int x = 0; x < Q; ++x) __stcg(&outs[(size_t)ex * Q + x], dk[(tid * PER + i) * Q + x]);
             __stcg(&outm[ex], wgt[tid * PER + i]);
             ++ex;
         }
@@ -618,7 +644,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
 {
     using Cfg = BinCfg<NW, EXT>;
     constexpr int SW = Cfg::SW;
-    constexpr bool DEDUP = (NW == 1) && !EXT;
+    constexpr bool DEDUP = (NW <= 2) && !EXT;
     static_assert(!DEDUP || (2 * BN_DDTS <= Cfg::TS && BN_DDTS % BN_THREADS == 0 && BN_DDLIMIT < BN_DDTS && BN_DDLIMIT % BN_THREADS == 0), "supermer table fits the k-mer table");
     extern __shared__ __align__(16) unsigned char smraw[];
     BinSmem<NW, EXT> &sm = *reinterpret_cast<BinSmem<NW, EXT> *>(smraw);
@@ -656,7 +682,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         const u32 nk = sm.nk;
         u32 S = sm.S;
         const bool dd = DEDUP && !sm.bail && S > 0 && S <= (u32)BN_DDLIMIT && P.dd_slots != nullptr;
-        uint4 ddv[BN_DDPT];
+        uint4 ddv[BN_DDPT][SW / 4];
         if constexpr (DEDUP) { if (dd) dedup_fetch<NW, EXT>(sm, P, S, ddv); }
 
         // ---- empty table (the slots of a de-duplicated bin are on their way meanwhile)
@@ -675,12 +701,12 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
                 __syncthreads();   // the list is complete; the table memory goes back to the k-mers
                 {
                     const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
-                    for (int i = tid; i < BN_DDTS; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones;
+                    if (NW == 1) { for (int i = tid; i < BN_DDTS; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
                     for (int i = tid; i < 2 * BN_DDTS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
                 }
                 if (tid == 0) {
                     sm.nsrc = 1;
-                    sm.src_ptr[0] = reinterpret_cast<const u32 *>(P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT);
+                    sm.src_ptr[0] = reinterpret_cast<const u32 *>(P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT * (SW / 4));
                     sm.mult = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
                 }
                 S = Sd;

@@ -796,10 +796,10 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     BP.group_bins = group_bins ? group_bins : 1;
     {
         const char *ev = getenv("HSK_DEDUP");
-        if (NW == 1 && !ext && !(ev && *ev == '0')) {
-            CK(c->d_dd.ensure(bin_dedup_scratch_bytes(c->sm_count)));
+        if (NW <= 2 && !ext && !(ev && *ev == '0')) {
+            CK(c->d_dd.ensure(bin_dedup_scratch_bytes(c->sm_count, SW)));
             BP.dd_slots = c->d_dd.as<uint4>();
-            BP.dd_mult = reinterpret_cast<u32 *>(BP.dd_slots + (size_t)c->sm_count * 2 * BN_DDLIMIT);
+            BP.dd_mult = reinterpret_cast<u32 *>(BP.dd_slots + (size_t)c->sm_count * 2 * BN_DDLIMIT * (SW / 4));
         }
     }
     BP.grp_end = c->d_grp.as<u64>();

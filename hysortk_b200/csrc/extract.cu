@@ -443,6 +443,40 @@ __global__ void __launch_bounds__(XT_THREADS) k_supermer_scatter(ExtractParams P
                     if (rh < fh || (rh == fh && rl < fl)) {
                         w[0] = (u32)(rh >> 32); w[1] = (u32)rh; w[2] = (u32)(rl >> 32); w[3] = (u32)rl;
                     }
+                } else if (!EXT) {
+                    // the same for the 32-byte slots of K in 33..64  Both hold the
+                    // same canonical k-mers, and copies of a locus read from either strand become bit-identical slots,
+                    // which the bin kernel counts once with a weight (bins.cu: dedup_bin).
+                    constexpr int NQ = SW / 2;   // 64-bit words of the slot
+                    u64 f[NQ], r[NQ];
+#pragma unroll
+                    for (int x = 0; x < NQ; ++x) f[x] = ((u64)w[2 * x] << 32) | w[2 * x + 1];
+                    // all 32 NQ positions reversed and complemented: the string is now at the end; shift it to the front
+#pragma unroll
+                    for (int x = 0; x < NQ; ++x) r[x] = revcomp64(f[NQ - 1 - x]);
+                    const u32 sh = 2 * (32 * NQ - len);   // >= 8: the last 4 positions of a slot are never bases
+                    const u32 ws = sh >> 6, bs = sh & 63;
+#pragma unroll
+                    for (int x = 0; x < NQ; ++x) {
+                        // word x of (r << sh) = r[x + ws] << bs | r[x + ws + 1] >> (64 - bs)
+                        u64 a = 0, b = 0;
+#pragma unroll
+                        for (int y = 0; y < NQ; ++y) {
+                            if ((u32)y == x + ws) a = r[y];
+                            if ((u32)y == x + ws + 1) b = r[y];
+                        }
+                        f[x] = bs ? ((a << bs) | (b >> (64 - bs))) : a;   // f is re-used below: keep the original in w
+                    }
+                    bool less = false, decided = false;
+#pragma unroll
+                    for (int x = 0; x < NQ; ++x) {
+                        const u64 o = ((u64)w[2 * x] << 32) | w[2 * x + 1];
+                        if (!decided && f[x] != o) { less = f[x] < o; decided = true; }
+                    }
+                    if (less) {
+#pragma unroll
+                        for (int x = 0; x < NQ; ++x) { w[2 * x] = (u32)(f[x] >> 32); w[2 * x + 1] = (u32)f[x]; }
+                    }
                 }
                 w[PW - 1] |= len;
                 if (EXT) { w[SW - 2] = pos0 + pc * P.slot_nmax; w[SW - 1] = rid; }

@@ -94,11 +94,11 @@ struct BinParams {
     u32 *grp_done, *grp_big;             // per group, zeroed: finished bins, bins left to the big gather
     u64 *grp_end;                        // per group: arena cursor (entries, occurrences) after its last bin
     u64 *snap;                           // page-locked host memory or null: per group {entries, occurrences, big bins, ready}
-    // per CTA: list of the distinct supermer slots of the bin it works on and their weights (K <= 32 without EXTENSION)
+    // per CTA: list of the distinct supermer slots of the bin it works on and their weights (K <= 64 without EXTENSION)
     uint4 *dd_slots; u32 *dd_mult;
 };
 
-size_t bin_dedup_scratch_bytes(int sm_count);   // dd_slots + dd_mult of every resident CTA
+size_t bin_dedup_scratch_bytes(int sm_count, int slot_words);   // dd_slots + dd_mult of every resident CTA
 int bin_target_kmers(int nwords, bool ext);  // k-mer occurrences per bin the on-chip path is sized for
 // k_bin_count: every bin counted, sorted and written to the arena (or listed for the big gather / the HBM path)
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);
