@@ -12,6 +12,12 @@
 #include "hsk_capi.h"
 
 #include <chrono>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cstring>
+#include <algorithm>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -108,32 +114,71 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
     first[nranks] = rec.size();
     const size_t lo = first[rank], hi = first[rank + 1];
 
-    std::vector<size_t> lens;
+    /* One read() of this rank's byte range, then every record is 2-bit encoded straight into its place in the buffer
+     * by the host threads (the reference encodes record by record on one thread per rank, fastaindex.cpp:269-286 +
+     * dnaseq.cpp:9-31).  The bytes are exactly those of DnaSeq::compress. */
+    std::vector<size_t> lens, byteoff;
     lens.reserve(hi - lo);
-    size_t maxlen = 0;
-    for (size_t i = lo; i < hi; ++i) { lens.push_back(rec[i].len); maxlen = std::max(maxlen, rec[i].len); }
-    auto dna = std::make_shared<DnaBuffer>(DnaBuffer::computebufsize(lens));
+    byteoff.reserve(hi - lo + 1);
+    size_t bufsize = 0;
+    for (size_t i = lo; i < hi; ++i) {
+        lens.push_back(rec[i].len);
+        byteoff.push_back(bufsize);
+        bufsize += DnaSeq::bytesneeded(rec[i].len);
+    }
+    byteoff.push_back(bufsize);
+    uint8_t *buf = new uint8_t[bufsize ? bufsize : 1];
     if (hi > lo) {
-        std::ifstream fa(fasta_fname, std::ios::binary);
-        if (!fa) throw std::runtime_error("cannot open FASTA file " + fasta_fname);
         const size_t start = rec[lo].pos;
         const FaiRecord& last = rec[hi - 1];
         const size_t end = last.pos + last.len + (last.bases ? last.len / last.bases : 0) + 1;
-        std::string chunk(end - start, '\n');
-        fa.seekg(static_cast<std::streamoff>(start));
-        fa.read(&chunk[0], static_cast<std::streamsize>(chunk.size()));
-        std::string seq(maxlen, 'A');
-        for (size_t i = lo; i < hi; ++i) {
-            const FaiRecord& r = rec[i];
-            size_t src = r.pos - start, dst = 0, remain = r.len;
-            while (remain > 0) {   /* strip the newline after every `bases` characters */
-                const size_t cnt = std::min(r.bases ? r.bases : remain, remain);
-                std::memcpy(&seq[dst], &chunk[src], cnt);
-                dst += cnt; remain -= cnt; src += cnt + 1;
+        /* the rank's byte range: mapped read-only (the encoder threads read the page cache directly); a plain
+         * read() into a string is the fallback */
+        const char *text = nullptr;
+        std::string chunk;
+        void *map = MAP_FAILED;
+        size_t map_len = 0, map_skew = 0;
+        const int fd = ::open(fasta_fname.c_str(), O_RDONLY);
+        if (fd < 0) { delete[] buf; throw std::runtime_error("cannot open FASTA file " + fasta_fname); }
+        struct stat st;
+        if (::fstat(fd, &st) == 0 && static_cast<size_t>(st.st_size) > start) {
+            const size_t page = static_cast<size_t>(::sysconf(_SC_PAGESIZE));
+            map_skew = start % page;
+            map_len = std::min(end, static_cast<size_t>(st.st_size)) - start + map_skew;
+            map = ::mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, static_cast<off_t>(start - map_skew));
+            if (map != MAP_FAILED) {
+                ::madvise(map, map_len, MADV_SEQUENTIAL);
+                text = static_cast<const char *>(map) + map_skew;
             }
-            dna->push_back(seq.data(), r.len);
         }
+        if (!text) {
+            chunk.assign(end - start, '\n');
+            const ssize_t got = ::pread(fd, &chunk[0], chunk.size(), static_cast<off_t>(start));
+            (void)got;
+            text = chunk.data();
+        }
+        ::close(fd);
+        const long nrec = static_cast<long>(hi - lo);
+        #pragma omp parallel for schedule(dynamic, 64)
+        for (long ii = 0; ii < nrec; ++ii) {
+            const FaiRecord& r = rec[lo + ii];
+            const char *src = text + (r.pos - start);
+            uint8_t *dst = buf + byteoff[ii];
+            const size_t width = r.bases ? r.bases : r.len;   /* characters per FASTA line */
+            size_t col = 0;
+            for (size_t p = 0; p < r.len;) {
+                unsigned byte = 0;
+                for (int j = 0; j < 4 && p < r.len; ++j, ++p) {
+                    if (col == width) { ++src; col = 0; }   /* the newline after every `bases` characters */
+                    byte |= (static_cast<unsigned>(DnaSeq::getcharcode(*src++)) << (6 - 2 * j)) & 0xFFu;
+                    ++col;
+                }
+                *dst++ = static_cast<uint8_t>(byte);
+            }
+        }
+        if (map != MAP_FAILED) ::munmap(map, map_len);
     }
+    auto dna = std::make_shared<DnaBuffer>(bufsize, lens.size(), buf, lens.data());   /* adopts buf */
     MPI_Barrier(comm);
 #if LOG_LEVEL >= 1
     if (rank == 0) {

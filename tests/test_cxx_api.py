@@ -81,6 +81,36 @@ def test_makefile_artefacts():
     assert r.returncode != 0 and "must be less than" in (r.stderr + r.stdout)   # reference Makefile:50-52
 
 
+@pytest.mark.parametrize("line_width", [0, 60, 7])
+def test_read_dna_buffer_bytes(line_width, tmp_path):
+    """read_dna_buffer (host threads encode the records in place) yields exactly the packed bytes of the reads,
+    whatever the FASTA line width; no GPU involved."""
+    obj, _ = make(31, 17, 2, 50, 0, target="lib")
+    exe = os.path.join(BUILD, "test_read")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fopenmp", "-DKMER_SIZE=31", "-DMINIMIZER_SIZE=17", "-DLOWER_KMER_FREQ=2",
+                           "-DUPPER_KMER_FREQ=50", "-DEXTENSION=0", "-DLOG_LEVEL=0", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "hysortk_b200", "shim"), os.path.join(ROOT, "tests", "cxx", "test_read.cpp"),
+                           os.path.join(obj, "libhysortk.o"), "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-ldl", "-lpthread",
+                           "-o", exe])
+    rng = np.random.default_rng(line_width + 1)
+    lens = [1, 2, 3, 4, 5, 30, 31, 59, 60, 61, 120, 121, 1000, 4097] + [int(x) for x in rng.integers(1, 700, 300)]
+    reads = [rng.integers(0, 4, n).astype(np.uint8) for n in lens]
+    rs = synth.pack_reads(reads)
+    fasta = str(tmp_path / "reads.fa")
+    synth.write_fasta(fasta, rs, line_width)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(cuda, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([exe, fasta], capture_output=True, text=True, check=True, env=env).stdout.splitlines()
+    n, bufsize = (int(x) for x in out[0].split())
+    assert n == len(reads) and bufsize == rs.packed.nbytes
+    off = rs.byte_offsets()
+    for i, line in enumerate(out[1:]):
+        parts = line.split()
+        assert int(parts[0]) == lens[i]
+        got = bytes.fromhex(parts[1]) if len(parts) > 1 else b""
+        assert got == rs.packed[int(off[i]):int(off[i + 1])].tobytes(), i
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,line_width", [("k31_e0_mixed", 0), ("k55_e0_mixed", 80), ("k31_e0_lowcomplexity", 60)])
 def test_standalone_cli_matches_reference_output(name, line_width, tmp_path):
