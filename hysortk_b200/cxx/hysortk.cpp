@@ -12,6 +12,7 @@
 #include "hsk_capi.h"
 
 #include <chrono>
+#include <omp.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -286,16 +287,44 @@ void write_output_file(const KmerListS& kmerlist, const std::string& output_dir,
         std::cerr << "Error: cannot open output file " << fname << std::endl;
         MPI_Abort(comm, 1);
     }
-    std::string buf;
-    buf.reserve(1 << 22);
-    for (const auto& e : kmerlist) {   /* "<K bases>\t<cnt>\n" per entry (reference hysortk.cpp:159-162) */
-        buf += e.kmer.GetString();
-        buf += '\t';
-        buf += std::to_string(e.cnt);
-        buf += '\n';
-        if (buf.size() > (1u << 22) - 256) { ofs.write(buf.data(), static_cast<std::streamsize>(buf.size())); buf.clear(); }
+    /* "<K bases>\t<cnt>\n" per entry, the reference's lines (hysortk.cpp:159-162) without its flush per line: blocks of
+     * entries are formatted by the host threads into per-thread strings and written in order */
+    constexpr size_t BLOCK = size_t(1) << 20;
+    const size_t n = kmerlist.size();
+    int nt = 1;
+    #pragma omp parallel
+    {
+        #pragma omp single
+        nt = omp_get_num_threads();
     }
-    ofs.write(buf.data(), static_cast<std::streamsize>(buf.size()));
+    std::vector<std::string> part(static_cast<size_t>(nt));
+    for (size_t b0 = 0; b0 < n; b0 += BLOCK) {
+        const size_t b1 = std::min(n, b0 + BLOCK);
+        #pragma omp parallel num_threads(nt)
+        {
+            const size_t t = static_cast<size_t>(omp_get_thread_num());
+            const size_t lo = b0 + (b1 - b0) * t / nt, hi = b0 + (b1 - b0) * (t + 1) / nt;
+            std::string& out = part[t];
+            out.clear();
+            out.reserve((hi - lo) * (KMER_SIZE + 8));
+            char line[KMER_SIZE + 24];
+            for (size_t i = lo; i < hi; ++i) {
+                const KmerListEntryS& e = kmerlist[i];
+                const uint64_t *w = static_cast<const uint64_t *>(e.kmer.GetBytes());
+                for (int j = 0; j < KMER_SIZE; ++j) line[j] = "ACGT"[(w[j >> 5] >> (2 * (31 - (j & 31)))) & 3];
+                int len = KMER_SIZE;
+                line[len++] = '\t';
+                char digits[24];
+                int nd = 0;
+                unsigned long long c = e.cnt;
+                do { digits[nd++] = static_cast<char>('0' + c % 10); c /= 10; } while (c);
+                while (nd) line[len++] = digits[--nd];
+                line[len++] = '\n';
+                out.append(line, static_cast<size_t>(len));
+            }
+        }
+        for (const std::string& sp : part) ofs.write(sp.data(), static_cast<std::streamsize>(sp.size()));
+    }
 }
 
 } // namespace hysortk

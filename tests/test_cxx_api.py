@@ -111,6 +111,29 @@ def test_read_dna_buffer_bytes(line_width, tmp_path):
         assert got == rs.packed[int(off[i]):int(off[i + 1])].tobytes(), i
 
 
+@pytest.mark.parametrize("k", [31, 55])
+def test_write_output_file_lines(k, tmp_path):
+    """write_output_file (blocks formatted by the host threads) writes "<k-mer>\\t<count>" per entry in list order; no GPU."""
+    obj, _ = make(k, 17, 2, 50, 0, target="lib")
+    exe = os.path.join(BUILD, f"test_write_k{k}")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fopenmp", f"-DKMER_SIZE={k}", "-DMINIMIZER_SIZE=17", "-DLOWER_KMER_FREQ=2",
+                           "-DUPPER_KMER_FREQ=50", "-DEXTENSION=0", "-DLOG_LEVEL=0", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "hysortk_b200", "shim"), os.path.join(ROOT, "tests", "cxx", "test_write.cpp"),
+                           os.path.join(obj, "libhysortk.o"), "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-ldl", "-lpthread",
+                           "-o", exe])
+    rng = np.random.default_rng(k)
+    n = 3000
+    kmers = ["".join("ACGT"[c] for c in rng.integers(0, 4, k)) for _ in range(n)]
+    cnts = [int(x) for x in rng.integers(1, 70000, n)]
+    cnts[:4] = [1, 9, 10, 65535]
+    inp = "".join(f"{a} {c}\n" for a, c in zip(kmers, cnts))
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(cuda, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="5")
+    subprocess.run([exe, str(tmp_path)], input=inp, text=True, check=True, env=env)
+    got = open(tmp_path / "0.out").read()
+    assert got == "".join(f"{a}\t{c}\n" for a, c in zip(kmers, cnts))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,line_width", [("k31_e0_mixed", 0), ("k55_e0_mixed", 80), ("k31_e0_lowcomplexity", 60)])
 def test_standalone_cli_matches_reference_output(name, line_width, tmp_path):
