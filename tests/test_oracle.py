@@ -128,3 +128,40 @@ def test_edge_cases():
         assert (a.n == 70) == kept, (copies, lower, upper, a.n)
         if kept:
             assert np.all(a.cnt == copies)
+
+
+@pytest.mark.parametrize("k", [3, 17, 31, 32, 33, 55, 64, 65, 77, 95])
+def test_device_helpers_on_host_match_oracle(k, tmp_path):
+    """kmer_twin / kmer_canonical of hysortk_b200/csrc/common.cuh (the source the kernels compile, run here on the host)
+    against the oracle's restatement of Kmer::GetTwin / GetRep (reference include/kmer.hpp:265-303)."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    build = os.path.join(root, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "test_common")
+    src = os.path.join(root, "tests", "cxx", "test_common.cu")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(root, "hysortk_b200", "csrc", "common.cuh"))):
+        subprocess.check_call([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-O1", "-std=c++17", src, "-o", exe])
+    L = po.lib()
+    nw = 1 if k <= 32 else (2 if k <= 64 else 3)
+    rng = np.random.default_rng(k)
+    lines, kmers = [], []
+    for i in range(300):
+        codes = rng.integers(0, 4, k)
+        if i < 4:   # homopolymers and a palindrome-like pattern
+            codes = np.full(k, i % 4)
+        w = [0, 0, 0]
+        for j, c in enumerate(codes):
+            w[j // 32] |= int(c) << (2 * (31 - j % 32))
+        kmers.append(w)
+        lines.append(f"{k} {w[0]:x} {w[1]:x} {w[2]:x}")
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.splitlines()
+    assert len(out) == len(kmers)
+    for w, line in zip(kmers, out):
+        got = [int(x, 16) for x in line.split()]
+        km, tw, rp = (C.c_uint64 * 3)(*w), (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+        L.orc_kmer_twin(km, k, tw)
+        L.orc_kmer_rep(km, k, rp)
+        assert got[:nw] == list(tw)[:nw] and got[3:3 + nw] == list(rp)[:nw]
