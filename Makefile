@@ -65,7 +65,11 @@ standalone: all
 	$(CXX) $(CXXFLAGS) -c -o $(OBJ)/standalone.o hysortk_b200/cxx/main.cpp
 	$(CXX) $(OPT) -fopenmp -o $(BIN) $(OBJ)/standalone.o $(OBJ)/libhysortk.o -L$(CUDA)/lib64 -lcudart -ldl -lpthread $(MPI_LIB)
 
-clean:
-	rm -rf $(OBJ) $(BIN)
+# launcher for several ranks on one node with the bundled MPI stand-in (hysortk_b200/shim/mpi.h); with a real MPI use mpirun
+mpirun:
+	$(CXX) -O2 -std=c++17 -o hsk_mpirun hysortk_b200/shim/hsk_mpirun.cpp
 
-.PHONY: all print lib standalone clean
+clean:
+	rm -rf $(OBJ) $(BIN) hsk_mpirun
+
+.PHONY: all print lib standalone mpirun clean

@@ -17,7 +17,7 @@ SO_PATH = os.path.join(HERE, "libhysortk_b200.so")
 NCCL_ID_BYTES = 128
 
 EXPORTS = ["hsk_last_error", "hsk_version", "hsk_get_unique_id", "hsk_create", "hsk_destroy", "hsk_count",
-           "hsk_count_device", "hsk_fetch_result", "hsk_allreduce_histogram", "hsk_fill_entries", "hsk_debug_sort",
+           "hsk_count_stream", "hsk_count_device", "hsk_fetch_result", "hsk_allreduce_histogram", "hsk_fill_entries", "hsk_debug_sort",
            "hsk_debug_extract"]
 
 
@@ -56,6 +56,10 @@ class DeviceResult(C.Structure):
                 ("d_histogram", C.c_void_p), ("stats", Stats)]
 
 
+# hsk_sink_fn: int sink(void *user, const hsk_result *view, first_entry, n_entries, first_occ, n_occ, total_hint)
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Result), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64)
+
+
 class Supermers(C.Structure):
     _fields_ = [("n_bins", C.c_uint64), ("bin_slots", C.POINTER(C.c_uint64)), ("bin_kmers", C.POINTER(C.c_uint64)),
                 ("n_slots", C.c_uint64), ("slot_words", C.c_uint32), ("slots", C.POINTER(C.c_uint32))]
@@ -78,6 +82,8 @@ def load():
         L.hsk_destroy.argtypes = [C.c_void_p]
         L.hsk_destroy.restype = None
         L.hsk_count.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(Result)]
+        L.hsk_count_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.POINTER(Result)]
         L.hsk_count_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32,
                                        C.POINTER(DeviceResult)]
         L.hsk_fetch_result.argtypes = [C.c_void_p, C.POINTER(Result)]
@@ -164,6 +170,47 @@ class Context:
         if not copy:
             return dict(n_kept=int(r.n_kept), n_occ=int(r.n_occ), stats=r.stats.as_dict())
         return self._unpack(r)
+
+    def count_stream(self, packed: np.ndarray, readlens: np.ndarray, readid_base: int = 0) -> dict:
+        """hsk_count_stream: the result is collected part by part by a sink (a Python callback, called from the
+        context's delivery thread) while the GPU is still counting; returns the concatenated parts like count()
+        plus `parts` = the (first_entry, n_entries, total_hint) of every delivery."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        readlens = np.ascontiguousarray(readlens, dtype=np.uint64)
+        nw = self.nwords
+        got = dict(words=[], cnt=[], occ_n=[], pos=[], rid=[], parts=[])
+
+        def sink(user, view, first, n, first_occ, n_occ, hint):
+            v = view.contents
+            got["parts"].append((int(first), int(n), int(hint)))
+            if n:
+                w = np.ctypeslib.as_array(v.kmer_words, shape=(int(first + n) * nw,))[int(first) * nw:].copy()
+                got["words"].append(w.reshape(int(n), nw))
+                got["cnt"].append(np.ctypeslib.as_array(v.cnt, shape=(int(first + n),))[int(first):].copy())
+                if self.ext:
+                    off = np.ctypeslib.as_array(v.occ_off, shape=(int(first + n),))[int(first):].astype(np.uint64)
+                    ends = np.concatenate([off[1:], np.array([first_occ + n_occ], dtype=np.uint64)])
+                    got["occ_n"].append(ends - off)
+                    if n_occ:
+                        got["pos"].append(np.ctypeslib.as_array(v.pos, shape=(int(first_occ + n_occ),))[int(first_occ):].copy())
+                        got["rid"].append(np.ctypeslib.as_array(v.rid, shape=(int(first_occ + n_occ),))[int(first_occ):].copy())
+            return 0
+
+        cb = SINK_FN(sink)
+        r = Result()
+        _check(self.lib.hsk_count_stream(self.handle, packed.ctypes.data, packed.nbytes, readlens.ctypes.data, len(readlens),
+                                         readid_base, C.cast(cb, C.c_void_p), None, C.byref(r)))
+        n = int(r.n_kept)
+        out = dict(nwords=nw, n_kept=n, n_occ=int(r.n_occ), parts=got["parts"],
+                   words=np.concatenate(got["words"]) if got["words"] else np.zeros((0, nw), np.uint64),
+                   cnt=np.concatenate(got["cnt"]) if got["cnt"] else np.zeros(0, np.uint32),
+                   histogram=_arr(r.histogram, self.upper + 1, np.uint64), stats=r.stats.as_dict())
+        if self.ext:
+            occ_n = np.concatenate(got["occ_n"]) if got["occ_n"] else np.zeros(0, np.uint64)
+            out["occ_off"] = np.concatenate([np.zeros(1, np.uint64), np.cumsum(occ_n, dtype=np.uint64)])
+            out["pos"] = np.concatenate(got["pos"]) if got["pos"] else np.zeros(0, np.uint32)
+            out["rid"] = np.concatenate(got["rid"]) if got["rid"] else np.zeros(0, np.int32)
+        return out
 
     def count_device(self, d_packed: int, nbytes: int, d_read_off: int, d_read_len: int, nreads: int,
                      readid_base: int = 0) -> DeviceResult:

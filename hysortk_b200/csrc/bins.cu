@@ -40,94 +40,104 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace hsk {
 
-constexpr int BN_WARPS = BN_THREADS / 32;
 constexpr int BN_HCAP = 128;                   // shared-memory histogram bins (larger counts go to the global histogram)
 constexpr u64 BN_EMPTY = ~0ull;                // never a canonical k-mer: a K-mer of all T is not canonical
 constexpr u32 BN_EMPTY32 = 0xFFFFFFFFu;        // K > 32: state of a fingerprint cell
 constexpr u32 BN_LOCK32 = 0xFFFFFFFEu;         //          claimed, key words not yet written
 constexpr u32 BN_NOTKEPT = 0xFFFFFFFFu;
-constexpr int BN_DDTS = 2048;                  // cells of the supermer table of a bin (dedup_bin)
 constexpr int BN_CAND = 1024;                  // candidate list; a bin with more candidates scans its whole table
 
-template <int NW, bool EXT>
+// TH = threads per CTA: 512 (16 warps; two or three CTAs per SM for K <= 32), or 1024 for the one-CTA-per-SM tables of
+// K > 32 (32 warps on the SM instead of 16)
+template <int NW, bool EXT, int TH>
 struct BinCfg {
+    static constexpr int THREADS = TH, WARPS = TH / 32;
     static constexpr int SW = (NW == 1 ? 4 : 8) + (EXT ? 4 : 0);
     static constexpr int PW = SW - (EXT ? 2 : 0);
     // table slots: K <= 32: 8192 (two CTAs per SM), with EXTENSION 4096 (three CTAs); K > 32: one CTA per SM
     static constexpr int TS_BITS = NW == 1 ? (EXT ? 12 : 13) : (NW == 2 && !EXT ? 13 : 12);
     static constexpr int TS = 1 << TS_BITS;
-    static constexpr int SLOTS_PT = TS / BN_THREADS;
+    static constexpr int SLOTS_PT = TS / TH;
     static constexpr int CTAS = NW == 1 ? (EXT ? 3 : 2) : 1;
     // most k-mers one slot can hold (smallest K of the word count) = rounds of 32 k-mers a batch of 32 slots can need
     static constexpr int NMAX = 16 * (PW - 1) + 12 - (NW == 1 ? 3 : (NW == 2 ? 33 : 65)) + 1;
-    // slots per walk batch (a warp stages them) and kept k-mers a CTA sorts itself (two per thread); a bin that keeps
-    // more goes through the staging area + big gather.  (Two CTAs per SM with half-size tables for K in 33..64 were
-    // measured slower than one CTA with the big table: 7.1 vs 6.0 ms at c2.)
-    static constexpr int BATCH = 32;
-    static constexpr int SORTCAP = 2 * BN_THREADS;
+    // slots per walk batch (a warp stages them) and kept k-mers a CTA sorts itself; a bin that keeps more goes through
+    // the staging area + big gather
+    static constexpr int BATCH = TH > 512 ? 16 : 32;
+    static constexpr int SORTCAP = 1024;
+    static constexpr int EPT = SORTCAP / TH;   // kept k-mers per thread in the sort
     static constexpr int HEADW = ((BATCH * NMAX + 31) / 32 + 3) / 4 * 4;   // rounds of 32 k-mers a batch can need
     static constexpr int TARGET = NW == 1 ? (EXT ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
+    // de-duplication of the supermers of a bin (K <= 64 without EXTENSION): cells of the supermer table, most slots of
+    // a bin that goes through it (a multiple of TH, below the number of cells)
+    static constexpr int DDTS = TH > 512 ? 4096 : 2048;
+    static constexpr int DDLIMIT = TH > 512 ? 2048 : 1536;
+    static constexpr int DDPT = DDLIMIT / TH;
+    static_assert(DDLIMIT <= BN_DDLIMIT_MAX && DDLIMIT % TH == 0 && DDLIMIT < DDTS && DDTS % TH == 0, "supermer table geometry");
+    static_assert(SORTCAP % TH == 0 && SORTCAP <= BN_CAND, "sort geometry");
 };
 
-size_t bin_dedup_scratch_bytes(int sm_count, int slot_words) { return (size_t)sm_count * 2 * BN_DDLIMIT * ((size_t)slot_words * 4 + sizeof(u32)); }
+size_t bin_dedup_scratch_bytes(int sm_count, int slot_words) { return (size_t)sm_count * 2 * BN_DDLIMIT_MAX * ((size_t)slot_words * 4 + sizeof(u32)); }
 
 int bin_target_kmers(int nwords, bool ext)
 {
-    if (nwords == 1) return ext ? BinCfg<1, true>::TARGET : BinCfg<1, false>::TARGET;
-    if (nwords == 2) return ext ? BinCfg<2, true>::TARGET : BinCfg<2, false>::TARGET;
-    return BinCfg<3, false>::TARGET;
+    if (nwords == 1) return ext ? BinCfg<1, true, 512>::TARGET : BinCfg<1, false, 512>::TARGET;
+    if (nwords == 2) return ext ? BinCfg<2, true, 512>::TARGET : BinCfg<2, false, 512>::TARGET;
+    return BinCfg<3, false, 512>::TARGET;
 }
 
-
 // scratch of a CTA, used by the walk (staged slots, scan, slot-start bitmap of every warp) and then by the sort of
-// the kept k-mers (exchange buffers; the compacted slot list sits at their start until it has been consumed)
-template <int NW, bool EXT>
+// the kept k-mers (keys in bucket order, payloads in sorted order, bucket starts)
+template <int NW, bool EXT, int TH>
 struct BinScratchCfg {
-    using Cfg = BinCfg<NW, EXT>;
+    using Cfg = BinCfg<NW, EXT, TH>;
     static constexpr int STG_U4 = Cfg::BATCH * Cfg::SW / 4 + 2;                       // uint4 per warp (+ pad)
-    static constexpr size_t WALK = (size_t)BN_WARPS * (STG_U4 * 16 + 32 * 2 + Cfg::HEADW * 4);
-    static constexpr size_t SORT = (size_t)Cfg::SORTCAP * (8 * NW + 4);
-    static constexpr size_t BYTES = (WALK > SORT ? WALK : SORT + 15) / 16 * 16;
+    static constexpr size_t WALK = (size_t)Cfg::WARPS * (STG_U4 * 16 + 32 * 2 + Cfg::HEADW * 4);
+    static constexpr size_t SORT = (size_t)Cfg::SORTCAP * (8 * NW + 4) + 264 * 4;
+    static constexpr size_t BYTES = ((WALK > SORT ? WALK : SORT) + 15) / 16 * 16;
 };
 
-template <int NW, bool EXT>
+template <int NW, bool EXT, int TH>
 struct BinSmem {
-    using Cfg = BinCfg<NW, EXT>;
-    using Scr = BinScratchCfg<NW, EXT>;
+    using Cfg = BinCfg<NW, EXT, TH>;
+    using Scr = BinScratchCfg<NW, EXT, TH>;
     alignas(16) u64 fp[NW == 1 ? Cfg::TS : 1];              // K <= 32: the k-mer itself is the CAS key
     alignas(16) u64 kw[NW > 1 ? NW : 1][NW > 1 ? Cfg::TS : 1];   // K > 32: full key words ...
     alignas(16) u32 fp32[NW > 1 ? Cfg::TS : 1];             //         ... guarded by a 32-bit fingerprint cell
     alignas(16) u32 cnt[Cfg::TS];                           // occurrences per slot; EXT pass 2: next occurrence offset
     alignas(16) unsigned char scratch[Scr::BYTES];
     u32 hist[BN_HCAP];
-    u16 cand[BN_CAND];                                      // slots whose counter reached LOWER
+    u16 cand[BN_CAND];                                      // slots whose counter reached LOWER; then the kept slots
     const u32 *src_ptr[BN_MAX_SRC];                         // first slot of the bin in every source stream
     u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1];
-    u32 wa[BN_WARPS], wb[BN_WARPS];
+    u32 wa[Cfg::WARPS], wb[Cfg::WARPS];
     u64 base_k, base_o;                                     // where the bin's entries / occurrences go
     u32 *occ_pos; int *occ_rid;                             // EXT pass 2 target arrays (arena, or staging for big bins)
-    u32 bin, nk, S, bail, next_batch, seen, ncand;
+    u32 bin, nk, S, bail, next_batch, seen, ncand, skip_out;
+    u32 xor_hi, xor_lo;                                     // bits in which the kept k-mers' first words differ
     u32 batch_slots;                                        // slots per walk batch: 32, fewer when the bin has few slots
     int nsrc;                                               // sources of the walk: P.nsrc, or 1 when the bin was de-duplicated
     const u32 *mult;                                        // weight per slot (de-duplicated bins) or null
 
     // walk layout
     __device__ uint4 *stg(int warp) { return reinterpret_cast<uint4 *>(scratch) + (size_t)warp * Scr::STG_U4; }
-    __device__ u16 *scan(int warp) { return reinterpret_cast<u16 *>(scratch + (size_t)BN_WARPS * Scr::STG_U4 * 16) + warp * 32; }
+    __device__ u16 *scan(int warp) { return reinterpret_cast<u16 *>(scratch + (size_t)Cfg::WARPS * Scr::STG_U4 * 16) + warp * 32; }
     __device__ u32 *heads(int warp)
     {
-        return reinterpret_cast<u32 *>(scratch + (size_t)BN_WARPS * (Scr::STG_U4 * 16 + 64)) + (size_t)warp * Cfg::HEADW;
+        return reinterpret_cast<u32 *>(scratch + (size_t)Cfg::WARPS * (Scr::STG_U4 * 16 + 64)) + (size_t)warp * Cfg::HEADW;
     }
     // sort layout
     __device__ u64 *xkey() { return reinterpret_cast<u64 *>(scratch); }                                   // [NW][SORTCAP]
-    __device__ u32 *xpay() { return reinterpret_cast<u32 *>(scratch + (size_t)Cfg::SORTCAP * 8 * NW); }   // [SORTCAP]
-    __device__ u16 *klist() { return reinterpret_cast<u16 *>(scratch); }                                  // [SORTCAP], before the sort
+    __device__ u32 *ypay() { return reinterpret_cast<u32 *>(scratch + (size_t)Cfg::SORTCAP * 8 * NW); }   // [SORTCAP]
+    __device__ u32 *bh() { return ypay() + Cfg::SORTCAP; }                                                // [257]
 };
 
-// block-wide exclusive scan of two u32 values (BN_THREADS threads); returns exclusive prefixes and totals
+// block-wide exclusive scan of two u32 values (TH threads); returns exclusive prefixes and totals
+template <int TH>
 __device__ __forceinline__ void block_scan2(u32 a, u32 b, u32 *wa, u32 *wb, u32 &ea, u32 &eb, u32 &ta, u32 &tb)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,14 +151,18 @@ __device__ __forceinline__ void block_scan2(u32 a, u32 b, u32 *wa, u32 *wb, u32 
     __syncthreads();   // protects wa/wb against the previous use
     if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
     __syncthreads();
-    u32 oa = 0, ob = 0;
-    ta = 0; tb = 0;
+    // every warp scans the TH / 32 warp totals itself (one per lane)
+    u32 x = lane < TH / 32 ? wa[lane] : 0u, y = lane < TH / 32 ? wb[lane] : 0u;
+    u32 ix = x, iy = y;
 #pragma unroll
-    for (int i = 0; i < BN_THREADS / 32; ++i) {
-        u32 x = wa[i], y = wb[i];
-        if (i < warp) { oa += x; ob += y; }
-        ta += x; tb += y;
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 p = __shfl_up_sync(0xFFFFFFFFu, ix, d);
+        u32 q = __shfl_up_sync(0xFFFFFFFFu, iy, d);
+        if (lane >= d) { ix += p; iy += q; }
     }
+    ta = __shfl_sync(0xFFFFFFFFu, ix, 31);
+    tb = __shfl_sync(0xFFFFFFFFu, iy, 31);
+    const u32 oa = __shfl_sync(0xFFFFFFFFu, ix - x, warp), ob = __shfl_sync(0xFFFFFFFFu, iy - y, warp);
     ea = oa + ia - a;
     eb = ob + ib - b;
 }
@@ -178,9 +192,8 @@ __device__ __forceinline__ u64 key_mix(const u64 (&w)[NW])
 
 // address of slot j of the bin (j counts over the per-source segments in rank order)
 template <typename SM>
-__device__ __forceinline__ const u32 *slot_ptr(const SM &sm, const BinParams &P, u32 j, int sw)
+__device__ __forceinline__ const u32 *slot_ptr(const SM &sm, u32 j, int sw)
 {
-    (void)P;
     if (sm.nsrc == 1) return sm.src_ptr[0] + (size_t)j * (u32)sw;
     int s = 0;
     while (j >= sm.src_sbase[s + 1]) ++s;
@@ -193,10 +206,10 @@ __device__ __forceinline__ const u32 *slot_ptr(const SM &sm, const BinParams &P,
 //   K > 32:  the cell holds a 32-bit fingerprint; a claim goes EMPTY -> LOCK (CAS), key words written, fence,
 //            fingerprint published, so whoever reads a fingerprint also sees the words and compares them in full:
 //            equal fingerprints of different k-mers just probe on.  Exact, no second pass.
-template <int NW, bool EXT, bool INSERT>
-__device__ __forceinline__ u32 table_find(BinSmem<NW, EXT> &sm, const u64 (&key)[NW])
+template <bool INSERT, int NW, bool EXT, int TH>
+__device__ __forceinline__ u32 table_find(BinSmem<NW, EXT, TH> &sm, const u64 (&key)[NW])
 {
-    using Cfg = BinCfg<NW, EXT>;
+    using Cfg = BinCfg<NW, EXT, TH>;
     const u64 hmix = key_mix<NW>(key);
     u32 slot = (u32)(hmix >> (64 - Cfg::TS_BITS));
     if (NW == 1) {
@@ -248,43 +261,43 @@ __device__ __forceinline__ u32 table_find(BinSmem<NW, EXT> &sm, const u64 (&key)
 // EMPTY -> LOCK -> publish claim as the K > 32 k-mer table; value = number of copies.  The distinct slots and their
 // weights are compacted into the CTA's own list in global memory (L2-resident) and the walk then expands each of them
 // once.  Without EXTENSION only: with EXTENSION every occurrence needs its own (pos, rid) anyway.
-//   cells: sm.cnt[0 .. BN_DDTS)   weights: sm.cnt[BN_DDTS .. 2 BN_DDTS)   keys: sm.fp (K <= 32) / sm.kw (K > 32), as uint4
-constexpr int BN_DDPT = BN_DDLIMIT / BN_THREADS;   // slots per thread
-
-template <int NW, bool EXT>
-__device__ __forceinline__ uint4 *dedup_keys(BinSmem<NW, EXT> &sm)
+//   cells: sm.cnt[0 .. DDTS)   weights: sm.cnt[DDTS .. 2 DDTS)   keys: sm.fp (K <= 32) / sm.kw (K > 32), as uint4
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ uint4 *dedup_keys(BinSmem<NW, EXT, TH> &sm)
 {
     return NW == 1 ? reinterpret_cast<uint4 *>(sm.fp) : reinterpret_cast<uint4 *>(&sm.kw[0][0]);
 }
 
 // the slots of a thread, fetched early (they may come over NVLink) while the table is being cleared
-template <int NW, bool EXT>
-__device__ __forceinline__ void dedup_fetch(const BinSmem<NW, EXT> &sm, const BinParams &P, u32 S,
-                                            uint4 (&v)[BN_DDPT][BinCfg<NW, EXT>::SW / 4])
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ void dedup_fetch(const BinSmem<NW, EXT, TH> &sm, u32 S,
+                                            uint4 (&v)[BinCfg<NW, EXT, TH>::DDPT][BinCfg<NW, EXT, TH>::SW / 4])
 {
-    constexpr int SW = BinCfg<NW, EXT>::SW;
+    constexpr int SW = BinCfg<NW, EXT, TH>::SW;
 #pragma unroll
-    for (int i = 0; i < BN_DDPT; ++i) {
-        const u32 j = threadIdx.x + i * BN_THREADS;
+    for (int i = 0; i < BinCfg<NW, EXT, TH>::DDPT; ++i) {
+        const u32 j = threadIdx.x + i * TH;
         if (j < S) {
-            const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j, SW));
+            const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, j, SW));
 #pragma unroll
             for (int x = 0; x < SW / 4; ++x) v[i][x] = __ldg(sp + x);
         }
     }
 }
 
-template <int NW, bool EXT>
-__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &P, u32 S,
-                                         const uint4 (&vs)[BN_DDPT][BinCfg<NW, EXT>::SW / 4])
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 S,
+                                         const uint4 (&vs)[BinCfg<NW, EXT, TH>::DDPT][BinCfg<NW, EXT, TH>::SW / 4])
 {
-    constexpr int Q = BinCfg<NW, EXT>::SW / 4;   // uint4 per slot
+    using Cfg = BinCfg<NW, EXT, TH>;
+    constexpr int Q = Cfg::SW / 4;   // uint4 per slot
+    constexpr int DDTS = Cfg::DDTS;
     const u32 tid = threadIdx.x;
-    uint4 *dk = dedup_keys<NW, EXT>(sm);
-    u32 *cell = sm.cnt, *wgt = sm.cnt + BN_DDTS;
+    uint4 *dk = dedup_keys<NW, EXT, TH>(sm);
+    u32 *cell = sm.cnt, *wgt = sm.cnt + DDTS;
 #pragma unroll
-    for (int i = 0; i < BN_DDPT; ++i) {
-        if (tid + i * BN_THREADS >= S) break;
+    for (int i = 0; i < Cfg::DDPT; ++i) {
+        if (tid + i * TH >= S) break;
         u64 h = 0;
 #pragma unroll
         for (int x = 0; x < Q; ++x) {
@@ -295,8 +308,8 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &
         h ^= h >> 29;
         h *= 0xBF58476D1CE4E5B9ull;
         const u32 f = (u32)h & 0x7FFFFFFFu;
-        u32 idx = (u32)(h >> 53) & (BN_DDTS - 1);
-        while (true) {   // S <= BN_DDLIMIT < BN_DDTS: an empty cell always exists
+        u32 idx = (u32)(h >> 50) & (DDTS - 1);
+        while (true) {   // S <= DDLIMIT < DDTS: an empty cell always exists
             volatile u32 *c = &cell[idx];
             u32 old = *c;
             if (old == BN_EMPTY32) {
@@ -320,22 +333,22 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &
                 }
                 if (same) break;
             }
-            idx = (idx + 1) & (BN_DDTS - 1);
+            idx = (idx + 1) & (DDTS - 1);
         }
         atomicAdd(&wgt[idx], 1u);
     }
     __syncthreads();
     // compact the used cells into the CTA's list
-    constexpr int PER = BN_DDTS / BN_THREADS;
+    constexpr int PER = DDTS / TH;
     u32 used = 0, mask = 0;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         if (cell[tid * PER + i] != BN_EMPTY32) { mask |= 1u << i; ++used; }
     }
     u32 ex, d0, total, d1;
-    block_scan2(used, 0u, sm.wa, sm.wb, ex, d0, total, d1);
-    uint4 *outs = P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT * Q;
-    u32 *outm = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
+    block_scan2<TH>(used, 0u, sm.wa, sm.wb, ex, d0, total, d1);
+    uint4 *outs = P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT_MAX * Q;
+    u32 *outm = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT_MAX;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         if ((mask >> i) & 1) {
@@ -348,15 +361,15 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT> &sm, const BinParams &
     return total;
 }
 
-// One pass over the k-mers of the bin.  Warps take batches of 32 consecutive slots (ticket in shared memory): the
+// One pass over the k-mers of the bin.  Warps take batches of up to 32 consecutive slots (ticket in shared memory): the
 // lanes stage one slot each, a warp scan of the k-mers per slot and a bitmap of the slot starts map k-mer g of
 // the batch to (slot, offset) without a search, and round r gives k-mer 32r + lane to every lane — all lanes
 // work on every round but the last, whatever the supermer lengths are.
 //   PASS2 == false: insert + count.   PASS2 == true (EXTENSION): place (pos, rid) of the occurrences of kept k-mers.
-template <int NW, bool EXT, bool PASS2>
-__device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &P, int k, int padbits, u32 S)
+template <bool PASS2, int NW, bool EXT, int TH>
+__device__ __forceinline__ void walk_bin(BinSmem<NW, EXT, TH> &sm, const BinParams &P, int k, int padbits, u32 S)
 {
-    using Cfg = BinCfg<NW, EXT>;
+    using Cfg = BinCfg<NW, EXT, TH>;
     constexpr int SW = Cfg::SW, PW = Cfg::PW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *stg4 = sm.stg(warp);
@@ -376,7 +389,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
         if (lane == 0) bt = atomicAdd(&sm.next_batch, 1u);
         j0 = __shfl_sync(0xFFFFFFFFu, bt, 0) * BS;
         if ((u32)lane < BS && j0 + lane < S) {
-            const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, P, j0 + lane, SW));
+            const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, j0 + lane, SW));
             if (mult) {
 #pragma unroll
                 for (int x = 0; x < SW / 4; ++x) pre[x] = __ldcg(sp + x);
@@ -434,7 +447,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
             kmer_canonical<NW>(key, k);
             if (!PASS2) {
                 u32 slot = (u32)Cfg::TS;
-                if (act) slot = table_find<NW, EXT, true>(sm, key);
+                if (act) slot = table_find<true>(sm, key);
                 __syncwarp();   // the probe loop diverges; everything after it runs once per warp
                 const u32 m1 = mult ? __shfl_sync(0xFFFFFFFFu, my_m, s & 31) : 1u;   // copies of the k-mer's slot
                 if (act) {
@@ -449,7 +462,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT> &sm, const BinParams &
                 }
             } else {
                 u32 slot = (u32)Cfg::TS;
-                if (act) slot = table_find<NW, EXT, false>(sm, key);
+                if (act) slot = table_find<false>(sm, key);
                 __syncwarp();
                 if (slot < (u32)Cfg::TS && *reinterpret_cast<volatile u32 *>(&sm.cnt[slot]) != BN_NOTKEPT) {
                     const u64 p = sm.base_o + atomicAdd(&sm.cnt[slot], 1u);
@@ -498,71 +511,10 @@ __device__ __forceinline__ u64 lookback(volatile u64 *st, u32 lb)
     return sum;
 }
 
-// Bitonic sort of BN_THREADS * EPT elements spread over the CTA (element e = tid * EPT + r): partners inside a
-// thread are exchanged in registers, inside a warp by shuffles, further away through the exchange buffers.
-template <int NW, int EPT, int CAP>
-__device__ __forceinline__ void block_sort(u64 (&key)[EPT][NW], u32 (&pay)[EPT], u32 n2, u64 *xkey, u32 *xpay)
-{
-    const u32 tid = threadIdx.x;
-    // warps whose elements all lie beyond the network only keep the barriers company.  Keys are distinct except for
-    // the padding (all ones, payload 0), so one comparison decides an exchange: "the partner is smaller" == "I keep
-    // the smaller one".
-    const bool active = tid * EPT < max(n2, 32u * EPT);
-    for (u32 size = 2; size <= n2; size <<= 1) {
-        for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
-            if (EPT == 2 && stride == 1) {
-                const bool asc = ((tid * 2) & size) == 0;
-                if (active && key_less<NW>(key[EPT - 1], key[0]) == asc) {
-#pragma unroll
-                    for (int l = 0; l < NW; ++l) { const u64 t = key[0][l]; key[0][l] = key[EPT - 1][l]; key[EPT - 1][l] = t; }
-                    const u32 t = pay[0]; pay[0] = pay[EPT - 1]; pay[EPT - 1] = t;
-                }
-                continue;
-            }
-            const u32 ts = stride / EPT;   // partner thread distance
-            if (ts >= 32) {
-                __syncthreads();
-                if (active) {
-#pragma unroll
-                    for (int r = 0; r < EPT; ++r) {
-                        const u32 e = tid * EPT + r;
-#pragma unroll
-                        for (int l = 0; l < NW; ++l) xkey[(size_t)l * CAP + e] = key[r][l];
-                        xpay[e] = pay[r];
-                    }
-                }
-                __syncthreads();
-            }
-            if (!active) continue;
-#pragma unroll
-            for (int r = 0; r < EPT; ++r) {
-                const u32 e = tid * EPT + r;
-                u64 pk[NW];
-                u32 pp;
-                if (ts >= 32) {
-                    const u32 j = e ^ stride;
-#pragma unroll
-                    for (int l = 0; l < NW; ++l) pk[l] = xkey[(size_t)l * CAP + j];
-                    pp = xpay[j];
-                } else {
-#pragma unroll
-                    for (int l = 0; l < NW; ++l) pk[l] = __shfl_xor_sync(0xFFFFFFFFu, key[r][l], ts);
-                    pp = __shfl_xor_sync(0xFFFFFFFFu, pay[r], ts);
-                }
-                const bool want_min = ((e & size) == 0) == ((e & stride) == 0);
-                if (key_less<NW>(pk, key[r]) == want_min) {
-#pragma unroll
-                    for (int l = 0; l < NW; ++l) key[r][l] = pk[l];
-                    pay[r] = pp;
-                }
-            }
-        }
-    }
-}
-
-// look-back of one bin (warp 0): arena position -> sm.base_k / sm.base_o, inclusive prefix published
-template <int NW, bool EXT>
-__device__ __forceinline__ void resolve_position(BinSmem<NW, EXT> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
+// look-back of one bin (warp 0): arena position -> sm.base_k / sm.base_o, inclusive prefix published.  A bin that
+// would run past the arena is not written (sm.skip_out) and the call fails (P.err).
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ void resolve_position(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
 {
     if (threadIdx.x < 32) {
         volatile u64 *lbk = P.lb_state, *lbo = P.lb_state + P.nbins;
@@ -572,6 +524,9 @@ __device__ __forceinline__ void resolve_position(BinSmem<NW, EXT> &sm, const Bin
             lbk[lb] = LB_INC | (exk + tk);
             if (EXT) lbo[lb] = LB_INC | (exo + to);
             sm.base_k = exk; sm.base_o = exo;
+            const bool over = exk + tk > P.arena_cap || (EXT && exo + to > P.occ_cap);
+            sm.skip_out = over ? 1u : 0u;
+            if (over) atomicOr(P.err, 1u);
             const u32 g = lb / P.group_bins;
             if (lb + 1 == P.nbins || (lb + 1) % P.group_bins == 0) { P.grp_end[2 * g] = exk + tk; P.grp_end[2 * g + 1] = exo + to; }
             if (lb + 1 == P.nbins) { P.cursor[0] = exk + tk; P.cursor[1] = exo + to; }
@@ -580,56 +535,124 @@ __device__ __forceinline__ void resolve_position(BinSmem<NW, EXT> &sm, const Bin
     __syncthreads();
 }
 
-// The kept k-mers of a bin (slot list in sm.klist(), tk <= BN_THREADS * EPT): sort them, give every one its place
-// in the arena and write (k-mer, count[, occurrence offset]); EXTENSION leaves the occurrence cursors in sm.cnt.
-template <int NW, bool EXT, int EPT>
-__device__ __forceinline__ void sort_emit(BinSmem<NW, EXT> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
+// ---- the sort of a bin: the kept k-mers in ascending order ------------------------------------------------
+// The kept slots of the bin are listed in sm.cand[0 .. tk), tk <= SORTCAP.  Their k-mers are distinct, so the place of a
+// k-mer in the sorted bin is the number of smaller ones.  One counting pass over the most significant byte in which
+// the k-mers differ at all (first word) splits them into 256 buckets in ascending order; inside its bucket (a handful
+// of k-mers) every k-mer counts the smaller ones directly.  Six barriers and ~tk / 256 comparisons per k-mer, against
+// the 45 compare-exchange stages of a bitonic network over 512 elements.
+// Then every one gets its place in the arena: (k-mer, count[, occurrence offset]) are written in order; EXTENSION leaves
+// the occurrence cursors in sm.cnt.
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ void sort_emit(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
 {
-    const u32 tid = threadIdx.x;
-    if (tk == 0) { resolve_position<NW, EXT>(sm, P, lb, 0u, 0u); return; }
+    using Cfg = BinCfg<NW, EXT, TH>;
+    constexpr int EPT = Cfg::EPT, CAP = Cfg::SORTCAP;
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    if (tk == 0) { resolve_position(sm, P, lb, 0u, 0u); return; }
+    u32 *bh = sm.bh();
+    u64 *xkey = sm.xkey();
+    u32 *ypay = sm.ypay();
+    for (u32 i = tid; i < 257; i += TH) bh[i] = 0;
     u64 key[EPT][NW];
     u32 pay[EPT];   // slot << 16 | count (count <= UPPER <= 65535)
+    const u32 s0 = sm.cand[0];
+    const u64 k0 = NW == 1 ? sm.fp[s0] : sm.kw[0][s0];
+    u64 x = 0;
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
-        const u32 e = tid * EPT + r;
+        const u32 e = tid + r * TH;
         if (e < tk) {
-            const u32 slot = sm.klist()[e];
+            const u32 slot = sm.cand[e];
 #pragma unroll
             for (int l = 0; l < NW; ++l) key[r][l] = NW == 1 ? sm.fp[slot] : sm.kw[l][slot];
             pay[r] = (slot << 16) | sm.cnt[slot];
-        } else {
-#pragma unroll
-            for (int l = 0; l < NW; ++l) key[r][l] = ~0ull;
-            pay[r] = 0;
+            x |= key[r][0] ^ k0;
         }
     }
-    u32 n2 = 2;
-    while (n2 < tk) n2 <<= 1;
-    __syncthreads();   // the slot list has been read: the scratch becomes the exchange buffer
-    block_sort<NW, EPT, BinCfg<NW, EXT>::SORTCAP>(key, pay, n2, sm.xkey(), sm.xpay());
+    {
+        const u32 xh = __reduce_or_sync(0xFFFFFFFFu, (u32)(x >> 32)), xl = __reduce_or_sync(0xFFFFFFFFu, (u32)x);
+        if (lane == 0) { if (xh) atomicOr(&sm.xor_hi, xh); if (xl) atomicOr(&sm.xor_lo, xl); }
+    }
+    __syncthreads();
+    const u64 diff = ((u64)sm.xor_hi << 32) | sm.xor_lo;
+    const int top = diff ? 63 - __clzll((long long)diff) : 7;   // highest bit in which two of the k-mers differ
+    const int shift = top > 7 ? top - 7 : 0;
+    u32 bp[EPT];
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        if (tid + r * TH < tk) bp[r] = atomicAdd(&bh[(u32)(key[r][0] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the 256 bucket sizes; bh[256] = tk
+        u32 v[8], s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = bh[tid * 8 + i]; s += v[i]; }
+        u32 inc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        u32 ex = inc - s;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { bh[tid * 8 + i] = ex; ex += v[i]; }
+        if (tid == 31) bh[256] = ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        if (tid + r * TH < tk) {
+            const u32 idx = bh[(u32)(key[r][0] >> shift) & 255u] + bp[r];
+#pragma unroll
+            for (int l = 0; l < NW; ++l) xkey[(size_t)l * CAP + idx] = key[r][l];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        if (tid + r * TH < tk) {
+            const u32 b = (u32)(key[r][0] >> shift) & 255u;
+            const u32 lo = bh[b], hi = bh[b + 1];
+            u32 rank = lo;
+            for (u32 j = lo; j < hi; ++j) {
+                u64 o[NW];
+#pragma unroll
+                for (int l = 0; l < NW; ++l) o[l] = xkey[(size_t)l * CAP + j];
+                rank += key_less<NW>(o, key[r]) ? 1u : 0u;
+            }
+            ypay[rank] = pay[r];
+        }
+    }
+    __syncthreads();
+    // from here on a thread handles the sorted positions tid, tid + TH, ...
     u32 off[EPT];
     if (EXT) {
         // occurrence lists follow the sorted order: offsets inside the bin, left in the slots' counters as cursors
-        u32 mine = 0;
-#pragma unroll
-        for (int r = 0; r < EPT; ++r) { off[r] = mine; mine += pay[r] & 0xFFFFu; }
-        u32 ex, d0, t0, t1;
-        block_scan2(mine, 0u, sm.wa, sm.wb, ex, d0, t0, t1);
+        u32 carry = 0;
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
-            off[r] += ex;
-            if (tid * EPT + r < tk) sm.cnt[pay[r] >> 16] = off[r];
+            if ((u32)(r * TH) < tk) {
+                const u32 e = tid + r * TH;
+                const u32 c = e < tk ? (ypay[e] & 0xFFFFu) : 0u;
+                u32 ex, d0, t0, t1;
+                block_scan2<TH>(c, 0u, sm.wa, sm.wb, ex, d0, t0, t1);
+                off[r] = carry + ex;
+                carry += t0;
+                if (e < tk) sm.cnt[ypay[e] >> 16] = off[r];
+            }
         }
     }
-    resolve_position<NW, EXT>(sm, P, lb, tk, to);
+    resolve_position(sm, P, lb, tk, to);
+    if (sm.skip_out) return;
     const u64 bk = sm.base_k, bo = sm.base_o;
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
-        const u32 e = tid * EPT + r;
+        const u32 e = tid + r * TH;
         if (e < tk) {
-            const u32 c = pay[r] & 0xFFFFu;
+            const u32 p = ypay[e], slot = p >> 16, c = p & 0xFFFFu;
 #pragma unroll
-            for (int l = 0; l < NW; ++l) P.out_words[(bk + e) * NW + l] = key[r][l];
+            for (int l = 0; l < NW; ++l) P.out_words[(bk + e) * NW + l] = NW == 1 ? sm.fp[slot] : sm.kw[l][slot];
             P.out_cnt[bk + e] = c;
             if (EXT) P.out_occ_off[bk + e] = bo + off[r];
             if (c < (u32)BN_HCAP) atomicAdd(&sm.hist[c], 1u); else atomicAdd(&P.histogram[c], 1ull);
@@ -639,24 +662,27 @@ __device__ __forceinline__ void sort_emit(BinSmem<NW, EXT> &sm, const BinParams 
 
 // One CTA per bin, bins taken in index order through a ticket; a bin of any size is handled as long as its distinct
 // k-mers fit the table (anything else is listed for the HBM path).
-template <int NW, bool EXT>
-__global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count(BinParams P)
+template <int NW, bool EXT, int TH>
+__global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(BinParams P)
 {
-    using Cfg = BinCfg<NW, EXT>;
+    using Cfg = BinCfg<NW, EXT, TH>;
     constexpr int SW = Cfg::SW;
     constexpr bool DEDUP = (NW <= 2) && !EXT;
-    static_assert(!DEDUP || (2 * BN_DDTS <= Cfg::TS && BN_DDTS % BN_THREADS == 0 && BN_DDLIMIT < BN_DDTS && BN_DDLIMIT % BN_THREADS == 0), "supermer table fits the k-mer table");
+    static_assert(!DEDUP || 2 * Cfg::DDTS <= Cfg::TS, "supermer table fits the k-mer table");
     extern __shared__ __align__(16) unsigned char smraw[];
-    BinSmem<NW, EXT> &sm = *reinterpret_cast<BinSmem<NW, EXT> *>(smraw);
+    BinSmem<NW, EXT, TH> &sm = *reinterpret_cast<BinSmem<NW, EXT, TH> *>(smraw);
     const int tid = threadIdx.x;
     const int k = P.k;
     const int padbits = 2 * (32 * NW - k);
 
-    for (int i = tid; i < BN_HCAP; i += BN_THREADS) sm.hist[i] = 0;
+    for (int i = tid; i < BN_HCAP; i += TH) sm.hist[i] = 0;
 
     while (true) {
         __syncthreads();   // end of the previous bin: shared memory is free again
-        if (tid == 0) { sm.bin = atomicAdd(P.ticket, 1u); sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; }
+        if (tid == 0) {
+            sm.bin = atomicAdd(P.ticket, 1u);
+            sm.bail = 0; sm.next_batch = 0; sm.seen = 0; sm.ncand = 0; sm.skip_out = 0; sm.xor_hi = 0; sm.xor_lo = 0;
+        }
         __syncthreads();
         const u32 lb = sm.bin;
         if (lb >= P.nbins) break;
@@ -672,7 +698,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
             u64 s = 0;
             for (int i = 0; i < P.nsrc; ++i) { sm.src_sbase[i] = (u32)min(s, (u64)0xFFFFFFFFu); s += sm.src_n[i]; }
             sm.src_sbase[P.nsrc] = (u32)min(s, (u64)0xFFFFFFFFu);
-            const u64 nk = P.bin_kmers[lb] & ((1ull << 40) - 1);
+            const u64 nk = bt_kmers(P.bin_kmers[lb]);
             sm.nk = (u32)min(nk, (u64)0xFFFFFFFFu);
             sm.S = (u32)min(s, (u64)0xFFFFFFFFu);
             if (nk >= 0xFFFFFFFFull || s >= 0xFFFFFFFFull) sm.bail = 1;   // 32-bit counters
@@ -681,33 +707,35 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         __syncthreads();
         const u32 nk = sm.nk;
         u32 S = sm.S;
-        const bool dd = DEDUP && !sm.bail && S > 0 && S <= (u32)BN_DDLIMIT && P.dd_slots != nullptr;
-        uint4 ddv[BN_DDPT][SW / 4];
-        if constexpr (DEDUP) { if (dd) dedup_fetch<NW, EXT>(sm, P, S, ddv); }
+        const bool dd = DEDUP && !sm.bail && S > 0 && S <= (u32)Cfg::DDLIMIT && P.dd_slots != nullptr;
+        uint4 ddv[Cfg::DDPT][SW / 4];
+        if constexpr (DEDUP) { if (dd) dedup_fetch<NW, EXT, TH>(sm, S, ddv); }
 
         // ---- empty table (the slots of a de-duplicated bin are on their way meanwhile)
         {
             const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
-            if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
-            else { for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp32)[i] = ones; }
+            if (NW == 1) { for (int i = tid; i < Cfg::TS / 2; i += TH) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
+            else { for (int i = tid; i < Cfg::TS / 4; i += TH) reinterpret_cast<uint4 *>(sm.fp32)[i] = ones; }
             // de-duplication first uses the counters as its cells (empty = all ones) and weights
-            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS)
-                reinterpret_cast<uint4 *>(sm.cnt)[i] = (dd && i < BN_DDTS / 4) ? ones : zero;
+            for (int i = tid; i < Cfg::TS / 4; i += TH)
+                reinterpret_cast<uint4 *>(sm.cnt)[i] = (dd && i < Cfg::DDTS / 4) ? ones : zero;
         }
         __syncthreads();
         if constexpr (DEDUP) {
             if (dd) {
-                const u32 Sd = dedup_bin<NW, EXT>(sm, P, S, ddv);
+                const u32 Sd = dedup_bin<NW, EXT, TH>(sm, P, S, ddv);
                 __syncthreads();   // the list is complete; the table memory goes back to the k-mers
                 {
                     const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
-                    if (NW == 1) { for (int i = tid; i < BN_DDTS; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
-                    for (int i = tid; i < 2 * BN_DDTS / 4; i += BN_THREADS) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
+                    // the supermer keys overlaid the first DDTS * SW * 4 bytes of the k-mer cells (K <= 32 only: for K > 32
+                    // they lie in the key words, which need no clearing)
+                    if (NW == 1) { for (int i = tid; i < Cfg::DDTS * (SW / 4); i += TH) reinterpret_cast<uint4 *>(sm.fp)[i] = ones; }
+                    for (int i = tid; i < 2 * Cfg::DDTS / 4; i += TH) reinterpret_cast<uint4 *>(sm.cnt)[i] = zero;
                 }
                 if (tid == 0) {
                     sm.nsrc = 1;
-                    sm.src_ptr[0] = reinterpret_cast<const u32 *>(P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT * (SW / 4));
-                    sm.mult = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT;
+                    sm.src_ptr[0] = reinterpret_cast<const u32 *>(P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT_MAX * (SW / 4));
+                    sm.mult = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT_MAX;
                 }
                 S = Sd;
                 __syncthreads();
@@ -716,48 +744,67 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
 
         // ---- expand + insert + count.  About two batches per warp, so that the warps finish together
         if (tid == 0) {
-            u32 bs = (S + 2 * BN_WARPS - 1) / (2 * BN_WARPS);
+            u32 bs = (S + 2 * Cfg::WARPS - 1) / (2 * Cfg::WARPS);
             sm.batch_slots = min((u32)Cfg::BATCH, max(8u, bs));
         }
         __syncthreads();
-        if (!sm.bail) walk_bin<NW, EXT, false>(sm, P, k, padbits, S);
+        if (!sm.bail) walk_bin<false>(sm, P, k, padbits, S);
         __syncthreads();
         if (!sm.bail && sm.seen != nk && tid == 0) sm.bail = 2;   // inconsistent totals: never count from a corrupt table
         __syncthreads();
-        const bool bailed = sm.bail != 0;   // the bin goes to the HBM path; it still takes its (empty) place in the chain
+        bool bailed = sm.bail != 0;   // the bin goes to the HBM path; it still takes its (empty) place in the chain
 
         // ---- filter.  Usually the candidate list (slots that reached LOWER) names the few slots to look at; a bin
         //      with more candidates than the list holds (LOWER == 1, mostly) scans its whole table.
         const u32 ncand = sm.ncand;
         const bool listed = ncand <= (u32)BN_CAND;
-        const u32 per_thread = bailed ? 0u : (listed ? (ncand + BN_THREADS - 1) / BN_THREADS : (u32)Cfg::SLOTS_PT);
+        constexpr int LPT = BN_CAND / TH;   // listed candidates per thread, at most
+        const u32 per_thread = bailed ? 0u : (listed ? (ncand + TH - 1) / TH : (u32)Cfg::SLOTS_PT);
         u32 kept = 0, occ = 0, keepmask = 0;
-        for (u32 i = 0; i < per_thread; ++i) {
-            u32 slot = tid * per_thread + i;
-            bool in = true;
-            if (listed) { in = slot < ncand; slot = in ? sm.cand[slot] : 0u; }
-            const u32 c = sm.cnt[slot];
-            if (in && c >= P.lower && c <= P.upper) { keepmask |= 1u << i; ++kept; occ += c; }
+        u32 myslot[LPT];
+        if (listed) {
+#pragma unroll
+            for (int i = 0; i < LPT; ++i) {
+                const u32 idx = tid * per_thread + i;
+                const bool in = (u32)i < per_thread && idx < ncand;
+                const u32 slot = in ? sm.cand[idx] : 0u;
+                myslot[i] = slot;
+                const u32 c = sm.cnt[slot];
+                if (in && c >= P.lower && c <= P.upper) { keepmask |= 1u << i; ++kept; occ += c; }
+            }
+        } else if (!bailed) {
+#pragma unroll
+            for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
+                const u32 c = sm.cnt[tid * Cfg::SLOTS_PT + i];
+                if (c >= P.lower && c <= P.upper) { keepmask |= 1u << i; ++kept; occ += c; }
+            }
         }
         u32 ek, eo, tk, to;
-        block_scan2(kept, occ, sm.wa, sm.wb, ek, eo, tk, to);
+        block_scan2<TH>(kept, occ, sm.wa, sm.wb, ek, eo, tk, to);   // (its barriers: every candidate has been read)
         if (!EXT) to = 0;
-        const bool big = tk > (u32)Cfg::SORTCAP;   // too many kept k-mers to sort here: staging area + big gather
+        const bool big = tk > (u32)Cfg::SORTCAP;   // too many kept k-mers to sort here (never a listed bin): staging area + big gather
+        if (big) {
+            // room in the staging area?  Otherwise the bin goes through the HBM path like an overflowing one.
+            if (tid == 0) {
+                const u64 sk = atomicAdd(P.stage_cursor, (u64)tk);
+                const u64 so = (EXT && to) ? atomicAdd(P.stage_cursor + 1, (u64)to) : 0;
+                if (sk + tk > P.stage_cap || (EXT && so + to > P.stage_occ_cap)) sm.bail = 32;
+                sm.base_k = sk; sm.base_o = so;
+            }
+            __syncthreads();
+            if (sm.bail) { bailed = true; tk = 0; to = 0; }
+        }
         if (tid == 0) {
             volatile u64 *lbs = P.lb_state;
             lbs[lb] = LB_AGG | tk;
             if (EXT) lbs[P.nbins + lb] = LB_AGG | to;
             sm.next_batch = 0;
             if (bailed) P.ovf_list[atomicAdd(P.ovf_count, 1u)] = lb;
-            if (big) {
-                sm.base_k = atomicAdd(P.stage_cursor, (u64)tk);
-                sm.base_o = (EXT && to) ? atomicAdd(P.stage_cursor + 1, (u64)to) : 0;
-            }
         }
-        if (EXT && !bailed && (listed || !big)) {
+        if (EXT && !bailed && !big) {
             // slots that are not kept: the occurrence pass tells by the mark (kept slots get their cursor below)
             __syncthreads();
-            for (int i = tid; i < Cfg::TS / 4; i += BN_THREADS) {
+            for (int i = tid; i < Cfg::TS / 4; i += TH) {
                 uint4 v = reinterpret_cast<uint4 *>(sm.cnt)[i];
                 if (v.x < P.lower || v.x > P.upper) v.x = BN_NOTKEPT;
                 if (v.y < P.lower || v.y > P.upper) v.y = BN_NOTKEPT;
@@ -767,28 +814,31 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
             }
         }
         __syncthreads();
-        if (!big) {
-            // compacted list of the kept slots, then sort + emit straight into the arena
+        if (bailed) {
+            resolve_position(sm, P, lb, 0u, 0u);
+        } else if (!big) {
+            // compacted list of the kept slots (in place of the candidates, all of which have been read), then sort +
+            // emit straight into the arena
             u32 g = ek;
-            for (u32 i = 0; i < per_thread; ++i) {
-                if ((keepmask >> i) & 1) {
-                    u32 slot = tid * per_thread + i;
-                    if (listed) slot = sm.cand[slot];
-                    sm.klist()[g++] = (u16)slot;
-                }
+            if (listed) {
+#pragma unroll
+                for (int i = 0; i < LPT; ++i) if ((keepmask >> i) & 1) sm.cand[g++] = (u16)myslot[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < Cfg::SLOTS_PT; ++i) if ((keepmask >> i) & 1) sm.cand[g++] = (u16)(tid * Cfg::SLOTS_PT + i);
             }
             __syncthreads();
-            if (Cfg::SORTCAP <= BN_THREADS || tk <= (u32)BN_THREADS) sort_emit<NW, EXT, 1>(sm, P, lb, tk, to);
-            else sort_emit<NW, EXT, 2>(sm, P, lb, tk, to);
+            sort_emit<NW, EXT, TH>(sm, P, lb, tk, to);
             if (EXT && tid == 0) { sm.occ_pos = P.out_pos; sm.occ_rid = P.out_rid; }
         } else {
-            // unsorted into the staging area; the big gather sorts and moves the bin to its place in the arena
+            // unsorted into the staging area (the whole table was scanned); the big gather sorts and moves the bin to its
+            // place in the arena
             const u64 sk = sm.base_k, so = sm.base_o;
             u64 g = sk + ek;
             u32 lo = eo;   // occurrence offset inside the bin
-            for (u32 i = 0; i < per_thread; ++i) {
-                u32 slot = tid * per_thread + i;
-                if (listed) slot = slot < ncand ? sm.cand[slot] : 0u;
+#pragma unroll
+            for (int i = 0; i < Cfg::SLOTS_PT; ++i) {
+                const u32 slot = tid * Cfg::SLOTS_PT + i;
                 u32 mark = BN_NOTKEPT;
                 if ((keepmask >> i) & 1) {
                     const u32 c = sm.cnt[slot];
@@ -803,12 +853,12 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
                     lo += c;
                     ++g;
                 }
-                if (EXT && (!listed || ((keepmask >> i) & 1))) sm.cnt[slot] = mark;
+                if (EXT) sm.cnt[slot] = mark;
             }
             __syncthreads();
-            resolve_position<NW, EXT>(sm, P, lb, tk, to);   // sm.base_k / base_o: now the place in the arena
+            resolve_position(sm, P, lb, tk, to);   // sm.base_k / base_o: now the place in the arena
             if (tid == 0) {
-                P.bin_rec[4 * (size_t)lb + 0] = sk; P.bin_rec[4 * (size_t)lb + 1] = tk;
+                P.bin_rec[4 * (size_t)lb + 0] = sk; P.bin_rec[4 * (size_t)lb + 1] = sm.skip_out ? 0 : tk;
                 P.bin_rec[4 * (size_t)lb + 2] = so; P.bin_rec[4 * (size_t)lb + 3] = to;
                 P.fin[2 * (size_t)lb] = sm.base_k; P.fin[2 * (size_t)lb + 1] = sm.base_o;
                 P.big_list[atomicAdd(P.big_count, 1u)] = lb;
@@ -820,7 +870,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
         if (EXT) {
             // ---- occurrences: (pos, rid) of every occurrence of a kept k-mer, grouped per k-mer
             __syncthreads();
-            if (to) walk_bin<NW, EXT, true>(sm, P, k, padbits, S);
+            if (to && !bailed && !sm.skip_out) walk_bin<true>(sm, P, k, padbits, S);
         }
 
         // ---- the bin is in the arena: group bookkeeping for the host that streams the result out
@@ -840,7 +890,7 @@ __global__ void __launch_bounds__(BN_THREADS, BinCfg<NW, EXT>::CTAS) k_bin_count
     }
 
     __syncthreads();
-    for (int i = tid; i < BN_HCAP; i += BN_THREADS)
+    for (int i = tid; i < BN_HCAP; i += TH)
         if (sm.hist[i]) atomicAdd(&P.histogram[i], (u64)sm.hist[i]);
 }
 
@@ -960,7 +1010,7 @@ __global__ void __launch_bounds__(THREADS) k_bin_gather(BinParams P)
 }
 
 // ---- multi-rank bookkeeping from the all-gathered bin totals -----------------------------------------
-// alltot[src][b] = (slots << 40 | k-mers) of bin b as extracted by rank src.  Rank r owns bins [r*tg, (r+1)*tg) and
+// alltot[src][b] = bt_pack(slots, k-mers) of bin b as extracted by rank src.  Rank r owns bins [r*tg, (r+1)*tg) and
 // receives them in one buffer: one region per source rank (in rank order), bins in index order inside a region.
 
 // block-wide exclusive scan helper for one u64 per thread (1024 threads), with a running carry
@@ -1004,7 +1054,7 @@ __global__ void __launch_bounds__(1024) k_seg_scan(const u64 *__restrict__ allto
     const u64 *row0 = alltot + (size_t)src * T;
     u64 before = 0;
     if (absolute) {
-        for (u32 b = threadIdx.x; b < b_lo; b += 1024) before += row0[b] >> 40;
+        for (u32 b = threadIdx.x; b < b_lo; b += 1024) before += bt_slots(row0[b]);
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
     }
@@ -1020,7 +1070,7 @@ __global__ void __launch_bounds__(1024) k_seg_scan(const u64 *__restrict__ allto
     u64 *os = seg_start + (size_t)src * (tg + 1);
     for (u32 base = 0; base < tg; base += 1024) {
         const u32 b = base + threadIdx.x;
-        const u64 ex = scan1024(b < tg ? (row[b] >> 40) : 0, s_c, carry);
+        const u64 ex = scan1024(b < tg ? bt_slots(row[b]) : 0, s_c, carry);
         if (b < tg) os[b] = ex;
     }
     if (threadIdx.x == 0) { os[tg] = carry; meta[src] = carry - first; }
@@ -1033,7 +1083,7 @@ __global__ void __launch_bounds__(256) k_sum_kmers(const u64 *__restrict__ allto
     const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     u64 s = 0;
     if (b < tg) {
-        for (int src = 0; src < nranks; ++src) s += alltot[(size_t)src * T + b_lo + b] & ((1ull << 40) - 1);
+        for (int src = 0; src < nranks; ++src) s += bt_kmers(alltot[(size_t)src * T + b_lo + b]);
         bin_kmers[b] = s;
     }
 #pragma unroll
@@ -1051,31 +1101,32 @@ cudaError_t launch_seg_scan(const u64 *alltot, u32 T, int me, u32 tg, int nranks
 }
 
 // 228 KB of shared memory per SM, 1 KB reserved per CTA
-static_assert(sizeof(BinSmem<1, false>) <= (233472 - 2 * 1024) / 2, "K <= 32: two CTAs per SM");
-static_assert(sizeof(BinSmem<1, true>) <= (233472 - 3 * 1024) / 3, "K <= 32 with EXTENSION: three CTAs per SM");
-static_assert(sizeof(BinSmem<2, false>) <= 232448 && sizeof(BinSmem<2, true>) <= 232448 && sizeof(BinSmem<3, true>) <= 232448, "K > 32: one CTA per SM");
+static_assert(sizeof(BinSmem<1, false, 512>) <= (233472 - 2 * 1024) / 2, "K <= 32: two CTAs per SM");
+static_assert(sizeof(BinSmem<1, true, 512>) <= (233472 - 3 * 1024) / 3, "K <= 32 with EXTENSION: three CTAs per SM");
+static_assert(sizeof(BinSmem<2, false, 512>) <= 232448 && sizeof(BinSmem<2, true, 512>) <= 232448 && sizeof(BinSmem<3, true, 512>) <= 232448, "K > 32: one CTA per SM");
+static_assert(sizeof(BinSmem<2, false, 1024>) <= 232448, "K in 33..64: one CTA of 1024 threads per SM");
 constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers than a CTA sorts itself
 
-template <int NW, bool EXT>
+template <int NW, bool EXT, int TH>
 static cudaError_t launch_bins_t(const BinParams &P, int sm_count, cudaStream_t s)
 {
-    const size_t smem = sizeof(BinSmem<NW, EXT>);
-    cudaError_t e = cudaFuncSetAttribute(k_bin_count<NW, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(BinSmem<NW, EXT, TH>);
+    cudaError_t e = cudaFuncSetAttribute(k_bin_count<NW, EXT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_count<NW, EXT>, BN_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_count<NW, EXT, TH>, TH, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     // every CTA must be resident: the look-back chain waits on bins that other CTAs hold
     const u32 grid = (u32)std::min<u64>((u64)sm_count * per_sm, std::max<u32>(P.nbins, 1u));
-    k_bin_count<NW, EXT><<<grid, BN_THREADS, smem, s>>>(P);
+    k_bin_count<NW, EXT, TH><<<grid, TH, smem, s>>>(P);
     return cudaGetLastError();
 }
 
 template <int NW, bool EXT>
 static cudaError_t launch_big_t(const BinParams &P, int sm_count, cudaStream_t s)
 {
-    constexpr int GL_CAP = BinCfg<NW, EXT>::TS;   // a bin keeps at most one entry per table slot
+    constexpr int GL_CAP = BinCfg<NW, EXT, 512>::TS;   // a bin keeps at most one entry per table slot
     const size_t smem_l = ((size_t)8 * NW + 8) * GL_CAP;
     cudaError_t e = cudaFuncSetAttribute(k_bin_gather<NW, EXT, GL_CAP, GL_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
     if (e != cudaSuccess) return e;
@@ -1083,23 +1134,31 @@ static cudaError_t launch_big_t(const BinParams &P, int sm_count, cudaStream_t s
     return cudaGetLastError();
 }
 
+// threads per CTA of the K in 33..64 kernel: 1024 (one CTA per SM either way; HSK_BIN_THREADS=512 selects the 16-warp variant)
+static int k2_threads()
+{
+    static int v = [] { const char *e = getenv("HSK_BIN_THREADS"); const int t = e ? atoi(e) : 1024; return t == 512 ? 512 : 1024; }();
+    return v;
+}
+
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
 {
     if (P.nbins == 0) return cudaSuccess;
-    if (nwords == 1) return ext ? launch_bins_t<1, true>(P, sm_count, s) : launch_bins_t<1, false>(P, sm_count, s);
-    if (nwords == 2) return ext ? launch_bins_t<2, true>(P, sm_count, s) : launch_bins_t<2, false>(P, sm_count, s);
-    return ext ? launch_bins_t<3, true>(P, sm_count, s) : launch_bins_t<3, false>(P, sm_count, s);
+    if (nwords == 1) return ext ? launch_bins_t<1, true, 512>(P, sm_count, s) : launch_bins_t<1, false, 512>(P, sm_count, s);
+    if (nwords == 2) {
+        if (ext) return launch_bins_t<2, true, 512>(P, sm_count, s);
+        return k2_threads() == 1024 ? launch_bins_t<2, false, 1024>(P, sm_count, s) : launch_bins_t<2, false, 512>(P, sm_count, s);
+    }
+    return ext ? launch_bins_t<3, true, 512>(P, sm_count, s) : launch_bins_t<3, false, 512>(P, sm_count, s);
 }
 
-} // namespace hsk
-
-namespace hsk {
-// sorts + moves the bins listed in P.big_list (more kept k-mers than the small gather takes); launched only when
-// the group's big_count is not zero
+// sorts + moves the bins listed in P.big_list (more kept k-mers than a CTA of k_bin_count sorts itself); launched only
+// when the list is not empty
 cudaError_t launch_bin_gather_big(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
 {
     if (nwords == 1) return ext ? launch_big_t<1, true>(P, sm_count, s) : launch_big_t<1, false>(P, sm_count, s);
     if (nwords == 2) return ext ? launch_big_t<2, true>(P, sm_count, s) : launch_big_t<2, false>(P, sm_count, s);
     return ext ? launch_big_t<3, true>(P, sm_count, s) : launch_big_t<3, false>(P, sm_count, s);
 }
+
 } // namespace hsk

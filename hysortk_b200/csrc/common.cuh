@@ -122,6 +122,16 @@ __host__ __device__ constexpr int xt_out_lanes(int w) { return 32 - xt_halo_lane
 __host__ __device__ constexpr int xt_out_slots(int w) { return xt_out_lanes(w) * XT_R; }
 constexpr u32 MAX_BINS = 1u << 26;
 
+// ---- per-bin totals ---------------------------------------------------------------------------
+// One 64-bit word per bin and rank, accumulated with one reduction per run: supermer slots in the upper 28 bits,
+// k-mers in the lower 36.  Pass A also keeps independent grand totals; the bin scan compares them with the sums of the
+// two fields, so a bin that outgrows a field is reported instead of corrupting the stream (engine.cu: extract_count).
+constexpr int BT_KBITS = 36;
+constexpr u64 BT_KMASK = (1ull << BT_KBITS) - 1;
+__host__ __device__ __forceinline__ u64 bt_pack(u64 slots, u64 kmers) { return (slots << BT_KBITS) | kmers; }
+__host__ __device__ __forceinline__ u64 bt_slots(u64 v) { return v >> BT_KBITS; }
+__host__ __device__ __forceinline__ u64 bt_kmers(u64 v) { return v & BT_KMASK; }
+
 // ---- supermer slots ---------------------------------------------------------------------------
 // A supermer is stored in one fixed-size slot of SW 32-bit words (16-byte multiples, so a slot is
 // written and read with 128-bit accesses and addressed by its index alone):

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(CT_THREADS) k_count_tiles(CountParams P, u64 *
 }
 
 // exclusive scan of the tile totals starting at the arena cursor; advances the cursor (one block)
-__global__ void __launch_bounds__(1024) k_count_scan(u64 *__restrict__ tile_counts, u64 ntiles, u64 *__restrict__ cursor)
+__global__ void __launch_bounds__(1024) k_count_scan(u64 *__restrict__ tile_counts, u64 ntiles, u64 *__restrict__ cursor,
+                                                     u64 arena_cap, u64 occ_cap, u32 *__restrict__ err)
 {
     __shared__ u64 s_a[32], s_b[32];
     __shared__ u64 carry_a, carry_b;
@@ -143,7 +144,10 @@ __global__ void __launch_bounds__(1024) k_count_scan(u64 *__restrict__ tile_coun
         if (threadIdx.x == 1023) { carry_a = ea + a; carry_b = eb + b; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { cursor[0] = carry_a; cursor[1] = carry_b; }
+    if (threadIdx.x == 0) {
+        cursor[0] = carry_a; cursor[1] = carry_b;
+        if (carry_a > arena_cap || carry_b > occ_cap) atomicOr(err, 1u);
+    }
 }
 
 template <int NW, bool EXT>
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(CT_THREADS) k_count_emit(CountParams P, const 
         if ((keep >> b) & 1) {
             const u64 g = tbase + (u64)(tid * CT_IPT + b);
             const u32 len = lens[b];
+            if (e >= P.arena_cap || (EXT && oc + len > P.occ_cap)) { ++e; oc += len; continue; }   // reported by k_count_scan
 #pragma unroll
             for (int l = 0; l < NW; ++l) P.out_words[e * NW + l] = P.keys.p[l][g];
             P.out_cnt[e] = len;
@@ -225,7 +230,7 @@ cudaError_t launch_count_filter(const CountParams &P, void *scratch, cudaStream_
     if (P.nwords == 1) k_count_tiles<1><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(P, tiles);
     else if (P.nwords == 2) k_count_tiles<2><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(P, tiles);
     else k_count_tiles<3><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(P, tiles);
-    k_count_scan<<<1, 1024, 0, s>>>(tiles, ntiles, P.cursor);
+    k_count_scan<<<1, 1024, 0, s>>>(tiles, ntiles, P.cursor, P.arena_cap, P.occ_cap, P.err);
 #define HSK_CT(NW_, EXT_) k_count_emit<NW_, EXT_><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(P, tiles)
     if (P.nwords == 1) { if (ext) HSK_CT(1, true); else HSK_CT(1, false); }
     else if (P.nwords == 2) { if (ext) HSK_CT(2, true); else HSK_CT(2, false); }

@@ -17,12 +17,17 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <unistd.h>
 #include <string>
 #include <thread>
@@ -162,6 +167,125 @@ struct HostBuf {   // page-locked
 
 struct EvPair { cudaEvent_t a, b; };
 
+// A few host threads of the context: copy a pageable DnaBuffer into the page-locked staging ring, fill caller memory from
+// the result arrays.  parallel_for splits [0, n) into one contiguous piece per thread (the caller takes the first).
+class HostPool {
+public:
+    explicit HostPool(unsigned nthreads) : n_(std::max(1u, nthreads))
+    {
+        for (unsigned t = 1; t < n_; ++t) workers_.emplace_back([this, t] { run(t); });
+    }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+    }
+    void parallel_for(u64 n, const std::function<void(u64, u64)> &fn)
+    {
+        if (n_ == 1 || n < 2) { if (n) fn(0, n); return; }
+        {
+            std::lock_guard<std::mutex> l(m_);
+            fn_ = &fn; total_ = n; left_ = n_ - 1; ++gen_;
+        }
+        cv_.notify_all();
+        fn(0, n / n_);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return left_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void run(unsigned t)
+    {
+        u64 seen = 0;
+        while (true) {
+            const std::function<void(u64, u64)> *fn;
+            u64 n;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_; n = total_;
+            }
+            (*fn)(n * t / n_, n * (t + 1) / n_);
+            { std::lock_guard<std::mutex> l(m_); if (--left_ == 0) done_.notify_one(); }
+        }
+    }
+    unsigned n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(u64, u64)> *fn_ = nullptr;
+    u64 total_ = 0, gen_ = 0;
+    unsigned left_ = 0;
+    bool stop_ = false;
+};
+
+// hsk_count_stream: parts of the result that have reached the page-locked host arrays are handed to the caller's sink by
+// one thread of the context, in order, while the GPU works on the rest.
+struct SinkPart { u64 first, n, first_occ, n_occ, hint; cudaEvent_t ready; };
+class SinkWorker {
+public:
+    SinkWorker() : th_([this] { run(); }) {}
+    ~SinkWorker()
+    {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        th_.join();
+    }
+    void begin(hsk_sink_fn fn, void *user, const hsk_result *view, int device)
+    {
+        std::lock_guard<std::mutex> l(m_);
+        fn_ = fn; user_ = user; view_ = view; device_ = device; rc_ = 0; busy_ = 0;
+    }
+    void push(const SinkPart &p)
+    {
+        { std::lock_guard<std::mutex> l(m_); q_.push_back(p); ++busy_; }
+        cv_.notify_all();
+    }
+    // waits until every pushed part has been delivered; returns the first non-zero sink status
+    int drain()
+    {
+        std::unique_lock<std::mutex> l(m_);
+        idle_.wait(l, [this] { return busy_ == 0; });
+        return rc_;
+    }
+private:
+    void run()
+    {
+        bool dev_set = false;
+        while (true) {
+            SinkPart p;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                p = q_.front(); q_.pop_front();
+            }
+            if (!dev_set) { cudaSetDevice(device_); dev_set = true; }
+            int rc = 0;
+            if (p.ready && cudaEventSynchronize(p.ready) != cudaSuccess) rc = 2;
+            if (!rc && rc_ == 0 && fn_) rc = fn_(user_, view_, p.first, p.n, p.first_occ, p.n_occ, p.hint);
+            {
+                std::lock_guard<std::mutex> l(m_);
+                if (rc && !rc_) rc_ = rc;
+                if (--busy_ == 0) idle_.notify_all();
+            }
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, idle_;
+    std::deque<SinkPart> q_;
+    hsk_sink_fn fn_ = nullptr;
+    void *user_ = nullptr;
+    const hsk_result *view_ = nullptr;
+    int device_ = 0, rc_ = 0;
+    unsigned busy_ = 0;
+    bool stop_ = false;
+    std::thread th_;
+};
+
 } // namespace
 
 struct hsk_ctx {
@@ -177,7 +301,7 @@ struct hsk_ctx {
     // input staging (hsk_count)
     DevBuf d_packed, d_read_off, d_read_len, d_len64, d_rtscratch;
     // host pipeline of hsk_count: chunks of the packed reads in flight (tile bound + event), result streaming
-    struct InChunk { u64 tile_end; cudaEvent_t ready; };
+    struct InChunk { u64 tile_end; cudaEvent_t ready; u64 off, n; };
     std::vector<InChunk> in_chunks;
     bool stream_result = false;          // hsk_count: results go to the host buffers group by group
     u32 *d_in_flags = nullptr;           // hsk_count: read table checks (reads.cu), looked at after the first sync
@@ -196,6 +320,20 @@ struct hsk_ctx {
     struct PeerMap { unsigned char info[128]; void *mapped = nullptr; bool ipc = false; bool valid = false; };
     PeerMap peers[BN_MAX_SRC];
     bool use_p2p = true;
+    std::vector<DevBuf> retired;         // former supermer buffers that peers may still have mapped (freed one call later)
+    // host side of hsk_count_stream
+    std::unique_ptr<HostPool> pool;
+    std::unique_ptr<SinkWorker> sink;
+    hsk_sink_fn sink_fn = nullptr;
+    void *sink_user = nullptr;
+    hsk_result sink_view;
+    // pageable input: chunks are copied into a ring of page-locked buffers by the pool, then sent
+    static constexpr int RING = 3;
+    HostBuf h_ring[RING], h_len;
+    cudaEvent_t ring_free[RING] = {nullptr, nullptr, nullptr};
+    const u8 *in_host = nullptr;
+    bool in_pageable = false;
+    size_t in_staged = 0;
     // extraction state between the count pass and the scatter pass
     ExtractParams xp;
     u32 x_nctas = 0;
@@ -305,7 +443,15 @@ int hsk_create(hsk_ctx **out, const hsk_config *cfg)
         if (r != ncclSuccess) { delete c; return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
     }
     memset(&c->stats, 0, sizeof(c->stats));
+    memset(&c->sink_view, 0, sizeof(c->sink_view));
     if (const char *ev = getenv("HSK_EXCHANGE")) c->use_p2p = strcmp(ev, "nccl") != 0;
+    {
+        // host threads of the context (staging of pageable input, hsk_fill_entries): the ranks of a node share its cores
+        unsigned nt = std::max(1u, std::thread::hardware_concurrency() / (unsigned)cfg->nranks);
+        nt = std::min(nt, 8u);
+        if (const char *ev = getenv("HSK_HOST_THREADS")) { const int v = atoi(ev); if (v >= 1 && v <= 64) nt = (unsigned)v; }
+        c->pool.reset(new HostPool(nt));
+    }
     *out = c;
     return 0;
 }
@@ -316,14 +462,32 @@ void hsk_destroy(hsk_ctx *c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    c->sink.reset();
+    c->pool.reset();
+    // Collective when the context spans several ranks: nobody may still be reading a peer's supermers when they are
+    // freed, and an exported buffer is only freed after every peer has closed its mapping of it.
+    const bool fence = c->comm && c->use_p2p && c->d_cursor.p && !getenv("HSK_NO_DESTROY_BARRIER");
+    auto barrier = [&]() {
+        if (!fence) return;
+        u64 *w = c->d_cursor.as<u64>() + 8;
+        if (g_nccl.AllReduce(w, w + 1, 1, ncclUint64, ncclSum, c->comm, c->stream) == ncclSuccess) cudaStreamSynchronize(c->stream);
+    };
+    barrier();
+    for (int p = 0; p < BN_MAX_SRC; ++p) {
+        if (c->peers[p].valid && c->peers[p].ipc && c->peers[p].mapped) cudaIpcCloseMemHandle(c->peers[p].mapped);
+        c->peers[p].valid = false;
+    }
+    barrier();
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    for (auto &r : c->retired) r.release();
+    for (int r = 0; r < hsk_ctx::RING; ++r) { c->h_ring[r].release(); if (c->ring_free[r]) cudaEventDestroy(c->ring_free[r]); }
+    c->h_len.release();
     DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_len64, &c->d_rtscratch, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bscratch, &c->d_bucket, &c->d_slots,
                     &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_peerinfo, &c->d_dd, &c->d_grp, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
     for (int h = 0; h < 2; ++h) for (int w = 0; w < MAX_WORDS; ++w) c->d_keys[h][w].release();
-    for (int p = 0; p < BN_MAX_SRC; ++p) if (c->peers[p].valid && c->peers[p].ipc && c->peers[p].mapped) cudaIpcCloseMemHandle(c->peers[p].mapped);
     HostBuf *hb[] = {&c->h_peerinfo, &c->h_bucket, &c->h_alltot, &c->h_meta, &c->h_cursor, &c->h_owords, &c->h_ocnt,
                      &c->h_oocc_off, &c->h_opos, &c->h_orid, &c->h_hist};
     for (auto *b : hb) b->release();
@@ -342,14 +506,15 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
     if (c->cfg.buckets_per_rank > 0) return 0;
     u64 mx = nbytes;
     if (c->cfg.nranks > 1) {
-        CK(c->d_cursor.ensure(64));
-        CK(c->h_cursor.ensure(64));
-        c->h_cursor.as<u64>()[4] = nbytes;
-        CK(cudaMemcpyAsync(c->d_cursor.as<u64>() + 4, c->h_cursor.as<u64>() + 4, 8, cudaMemcpyHostToDevice, c->stream));
-        NK(g_nccl.AllReduce(c->d_cursor.as<u64>() + 4, c->d_cursor.as<u64>() + 5, 1, ncclUint64, ncclMax, c->comm, c->stream));
-        CK(cudaMemcpyAsync(c->h_cursor.as<u64>() + 5, c->d_cursor.as<u64>() + 5, 8, cudaMemcpyDeviceToHost, c->stream));
+        // words 10 / 11 of the cursor block: not shared with anything the kernels of this call use
+        CK(c->d_cursor.ensure(128));
+        CK(c->h_cursor.ensure(128));
+        c->h_cursor.as<u64>()[10] = nbytes;
+        CK(cudaMemcpyAsync(c->d_cursor.as<u64>() + 10, c->h_cursor.as<u64>() + 10, 8, cudaMemcpyHostToDevice, c->stream));
+        NK(g_nccl.AllReduce(c->d_cursor.as<u64>() + 10, c->d_cursor.as<u64>() + 11, 1, ncclUint64, ncclMax, c->comm, c->stream));
+        CK(cudaMemcpyAsync(c->h_cursor.as<u64>() + 11, c->d_cursor.as<u64>() + 11, 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        mx = c->h_cursor.as<u64>()[5];
+        mx = c->h_cursor.as<u64>()[11];
     }
     // average occurrences per bin: sized so that the distinct k-mers of a bin fill about a third of its table
     u64 target = (u64)bin_target_kmers(c->nwords, c->cfg.ext != 0);
@@ -362,12 +527,16 @@ static int choose_bins(hsk_ctx *c, u64 nbytes)
     return 0;
 }
 
-// Device layout of d_bucket (u64 units): [bin_tot T][start T+1][run_cursor][kmers_total][cursor T]
-// bin_tot = slots << 40 | k-mers.  Host (h_meta): S, run cursor, local k-mer total.  With full_d2h bin_tot and
+// Device layout of d_bucket (u64 units): [bin_tot T][start T+1][meta 8: run_cursor, kmers_total, check_slots,
+// check_kmers, -][cursor T].  bin_tot = bt_pack(slots, k-mers).  Host (h_meta): S, -, run cursor, k-mer total, the two
+// independent totals of pass A (common.cuh: a bin that outgrew a field of its total is an error, not a corrupt stream).  With full_d2h bin_tot and
 // start are also copied to h_bucket (debug entry point).  d_slots receives the bin-major supermer slots.
 // extract_count: tile table, pass A (per-bin totals + run list), bin scan; `before_sync` may queue more work that
 // only needs the totals (multi-rank bookkeeping) before the one host synchronisation.  extract_scatter: pass B into
 // c->xp.out_base with the cursors in `d_cur`.
+static int stage_chunk(hsk_ctx *c, size_t ci);
+static void end_input(hsk_ctx *c);
+
 static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_padded, const u64 *d_read_off,
                          const u32 *d_read_len, u64 nreads, int readid_base, const std::function<int()> &before_sync)
 {
@@ -392,7 +561,7 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
     P.slot_ninv = (u32)(((1ull << 32) + P.slot_nmax - 1) / P.slot_nmax);
 
     const size_t host_u64 = (size_t)T + ((size_t)T + 1);
-    const size_t dev_u64 = host_u64 + 2 + (size_t)T;
+    const size_t dev_u64 = host_u64 + XT_META + (size_t)T;
     CK(c->d_bucket.ensure(dev_u64 * 8));
     CK(c->h_meta.ensure(128 * 8));
     CK(c->d_tile_hdr.ensure((P.ntiles + 1) * sizeof(ulonglong2)));
@@ -401,16 +570,17 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
     P.tile_read = c->d_tile_read.as<u32>();
     u64 *d_tot = c->d_bucket.as<u64>();
     u64 *d_start = d_tot + T, *d_runcur = d_start + T + 1, *d_ktot = d_runcur + 1;
-    u64 *d_cur = d_ktot + 1;
+    u64 *d_cur = d_runcur + XT_META;
     u64 *hm = c->h_meta.as<u64>();
 
-    u64 run_cap = nslots / 3 + 1024;
+    // the run list: about one entry per 8 k-mers on reads; sized for one per 6 slots, with a retry at the worst case
+    u64 run_cap = nslots / 6 + 1024;
     c->begin(c->ev_extract);
     CK(launch_tile_reads(P, c->d_tile_read.as<u32>(), s));
     c->stats.n_launches += 1;
     for (int attempt = 0;; ++attempt) {
         CK(c->d_run_list.ensure(run_cap * 8));
-        CK(cudaMemsetAsync(d_tot, 0, (host_u64 + 2) * 8, s));
+        CK(cudaMemsetAsync(d_tot, 0, (host_u64 + XT_META) * 8, s));
         // pass A over the tiles whose bytes have arrived (hsk_count uploads the reads in chunks); a retry and
         // hsk_count_device see the whole buffer at once
         u64 tb = 0;
@@ -418,6 +588,7 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
         for (size_t ci = 0; ci <= nchunks; ++ci) {
             u64 te = P.ntiles;
             if (ci < nchunks) {
+                if (stage_chunk(c, ci)) return 1;   // pageable input: copied to the staging ring and sent now
                 CK(cudaStreamWaitEvent(s, c->in_chunks[ci].ready, 0));
                 te = std::min<u64>(c->in_chunks[ci].tile_end, P.ntiles);
                 if (ci + 1 == nchunks) te = P.ntiles;
@@ -433,17 +604,23 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
         c->end(c->ev_extract);
         if (before_sync && before_sync()) return 1;
         CK(cudaMemcpyAsync(hm + 0, d_start + T, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(hm + 2, d_runcur, 16, cudaMemcpyDeviceToHost, s));   // run cursor, k-mer total
-        hm[5] = 0;
-        if (c->d_in_flags) CK(cudaMemcpyAsync(hm + 5, c->d_in_flags, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hm + 2, d_runcur, 32, cudaMemcpyDeviceToHost, s));   // run cursor, k-mer total, check totals
+        hm[6] = 0;
+        if (c->d_in_flags) CK(cudaMemcpyAsync(hm + 6, c->d_in_flags, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         c->stats.n_launches += 3;
         g_trace.mark("pass A + bin scan done (host sync)");
-        if (hm[5] & 1) return fail("a read is longer than 2^32-1 bases");
-        if (hm[5] & 2) return fail("DnaBuffer size %llu does not match the read lengths", (unsigned long long)nbytes);
-        if (hm[2] <= run_cap) break;
+        if (hm[6] & 1) return fail("a read is longer than 2^32-1 bases");
+        if (hm[6] & 2) return fail("DnaBuffer size %llu does not match the read lengths", (unsigned long long)nbytes);
+        if (hm[2] <= run_cap) {
+            if (hm[0] != hm[4] || hm[3] != hm[5])
+                return fail("a minimizer bin holds more than 2^%d supermers or 2^%d k-mers of this rank's reads (totals %llu / %llu, summed "
+                            "per bin %llu / %llu)", 64 - BT_KBITS, BT_KBITS, (unsigned long long)hm[4], (unsigned long long)hm[5],
+                            (unsigned long long)hm[0], (unsigned long long)hm[3]);
+            break;
+        }
         if (attempt) return fail("internal: run list overflow after resize");
-        run_cap = nslots + 1024;   // pathological input (runs shorter than 3 k-mers on average): worst-case list
+        run_cap = nslots + 1024;   // pathological input (runs shorter than 6 k-mers on average): worst-case list
         c->begin(c->ev_extract);
     }
     P.tile_begin = 0; P.tile_end = P.ntiles;
@@ -484,7 +661,7 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
     const u64 S = c->stats.n_supermers;
     CK(c->d_slots.ensure((S + 4) * (size_t)SW * 4));
     c->xp.out_stream = c->d_slots.as<u32>();
-    u64 *d_cur = c->d_bucket.as<u64>() + (size_t)T + (T + 1) + 2;
+    u64 *d_cur = c->d_bucket.as<u64>() + (size_t)T + (T + 1) + XT_META;
     if (extract_scatter(c, d_cur)) return 1;
     if (full_d2h) {
         const size_t host_u64 = (size_t)T + ((size_t)T + 1);
@@ -496,9 +673,11 @@ static int run_extract(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_pa
 }
 
 // ---- HBM path for the bins the on-chip path left over (skewed bins): expand -> radix sort -> count ------
-struct OvfSeg { int src; u64 i0, nslots, kmers; };
+struct OvfSeg { int src; u32 bin; u64 i0, nslots, kmers; };
+struct CountLimits { u64 arena_cap, occ_cap; u32 *err; };
 
-static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
+// segs: the segments of the overflow bins, all sources of a bin next to each other; a batch holds whole bins
+static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs, const CountLimits &lim)
 {
     cudaStream_t s = c->stream;
     const int NW = c->nwords;
@@ -506,13 +685,15 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
     u64 cap = c->cfg.batch_kmers ? c->cfg.batch_kmers : (1ull << 28);
     cap = std::min<u64>(cap, (1ull << 29) - 1);
     size_t first = 0;
-    while (first < segs.size()) {   // batches of whole segments
+    while (first < segs.size()) {   // batches of whole bins
         size_t last = first;
         u64 n = 0, max_sup = 0;
-        while (last < segs.size() && (n == 0 || n + segs[last].kmers <= cap)) {
-            n += segs[last].kmers;
-            max_sup = std::max(max_sup, segs[last].nslots);
-            ++last;
+        while (last < segs.size()) {
+            size_t e = last;
+            u64 nb = 0, ms = 0;
+            while (e < segs.size() && segs[e].bin == segs[last].bin) { nb += segs[e].kmers; ms = std::max(ms, segs[e].nslots); ++e; }
+            if (n != 0 && n + nb > cap) break;
+            n += nb; max_sup = std::max(max_sup, ms); last = e;
         }
         if (n > (1ull << 29) - 1)
             return fail("a minimizer bin holds %llu k-mers (> 2^29-1); raise buckets_per_rank", (unsigned long long)n);
@@ -566,6 +747,7 @@ static int run_hbm_path(hsk_ctx *c, const std::vector<OvfSeg> &segs)
         CP.out_words = c->d_owords.as<u64>(); CP.out_cnt = c->d_ocnt.as<u32>();
         CP.out_occ_off = c->d_oocc_off.as<u64>(); CP.out_pos = c->d_opos.as<u32>(); CP.out_rid = c->d_orid.as<int>();
         CP.histogram = c->d_hist.as<u64>(); CP.cursor = c->d_cursor.as<u64>();
+        CP.arena_cap = lim.arena_cap; CP.occ_cap = lim.occ_cap; CP.err = lim.err;
         CK(launch_count_filter(CP, c->d_cscratch.p, s));
         c->end(c->ev_count);
         c->stats.n_launches += 3;
@@ -595,7 +777,8 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     CK(cudaEventRecord(ev_t0, s));
 
     // ---- small device state of this call:
-    //      [cursor 2][owned total 1][ticket, ovf_count (u32 x2)][stage cursor 2][big_count (u32)][barrier word]
+    //      [cursor 2][owned total 1][ticket, ovf_count (u32 x2)][stage cursor 2][big_count (u32)][error flags (u32)]
+    //      [barrier words 2][choose_bins words 2]
     CK(c->d_cursor.ensure(128));
     CK(c->h_cursor.ensure(128));
     CK(cudaMemsetAsync(c->d_cursor.p, 0, 128, s));
@@ -604,6 +787,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     u32 *d_ticket = reinterpret_cast<u32 *>(d_cursor + 3), *d_ovfc = d_ticket + 1;
     u64 *d_stagecur = d_cursor + 4;
     u32 *d_bigc = reinterpret_cast<u32 *>(d_cursor + 6);
+    u32 *d_err = reinterpret_cast<u32 *>(d_cursor + 7);
 
     BinParams BP;
     memset(&BP, 0, sizeof(BP));
@@ -657,9 +841,22 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         if (extract_count(c, d_packed, nbytes, nbytes_padded, d_read_off, d_read_len, nreads, readid_base, bookkeeping)) return 1;
         owned = hm[7];
         const u64 *rtot = hm + 8, *bounds = hm + 8 + (size_t)G;
-        u64 *d_cur = d_start + T + 1 + 2;
+        u64 *d_cur = d_start + T + 1 + XT_META;
         const u64 S = c->stats.n_supermers;
-        CK(c->d_slots.ensure((S + S / 8 + 64) * (size_t)SW * 4));
+        // Every rank has passed the all-gather above, so every rank has finished its previous call: supermer buffers of
+        // mine that peers had mapped then and that were replaced since are no longer mapped anywhere.
+        for (auto &r : c->retired) r.release();
+        c->retired.clear();
+        {
+            const size_t want = (S + S / 8 + 64) * (size_t)SW * 4;
+            if (want > c->d_slots.cap && c->d_slots.p && c->use_p2p) {
+                // peers still have the old buffer mapped (CUDA IPC) until they have seen the new record: keep it until
+                // the next call instead of freeing it under them
+                c->retired.push_back(c->d_slots);
+                c->d_slots = DevBuf();
+            }
+            CK(c->d_slots.ensure(want));
+        }
         c->xp.out_stream = c->d_slots.as<u32>();
         for (int peer = 0; peer < G; ++peer) {
             if (peer == me) continue;
@@ -756,25 +953,59 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     for (int src = 0; src < G; ++src) c->src_slots[src] = BP.slots[src];
     c->stats.n_kmers_owned = owned;
 
-    // ---- result arena, staging area, per-bin records
-    const u64 arena = owned / (u64)c->cfg.lower + 8;
-    CK(c->d_owords.ensure(arena * NW * 8));
-    CK(c->d_ocnt.ensure(arena * 4));
-    CK(c->d_swords.ensure(arena * NW * 8));
-    CK(c->d_scnt.ensure(arena * 4));
+    // ---- result arena, staging area, per-bin records.  No more than owned / LOWER entries can be kept; when arena +
+    //      staging area of that size do not fit the free memory, the run list (dead once the scatter pass has run) is
+    //      given back and both are cut to what there is: the kernels check the limits (arena full: the call fails;
+    //      staging area full: the bin takes the HBM path).
+    const u64 bound = owned / (u64)c->cfg.lower + 8;
+    u64 arena_cap = bound, stage_cap = bound, occ_cap = owned + 8, stage_occ_cap = owned + 8;
+    {
+        const size_t ent_b = (size_t)NW * 8 + 4 + (ext ? 8 : 0);
+        const size_t need = 2 * (size_t)bound * ent_b + (ext ? 2 * (size_t)(owned + 8) * 8 : 0);
+        const size_t have = c->d_owords.cap + c->d_ocnt.cap + c->d_swords.cap + c->d_scnt.cap + c->d_oocc_off.cap + c->d_opos.cap +
+                            c->d_orid.cap + c->d_spos.cap + c->d_srid.cap;
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        u64 budget = 0;
+        if (const char *ev = getenv("HSK_ARENA_BUDGET_MB")) budget = strtoull(ev, nullptr, 10) << 20;   // tests
+        if (budget || (need > have && (double)(need + need / 16) > 0.92 * (double)(free_b + have))) {
+            CK(cudaStreamSynchronize(s));
+            DevBuf *rel[] = {&c->d_run_list, &c->d_tile_hdr, &c->d_owords, &c->d_ocnt, &c->d_swords, &c->d_scnt, &c->d_oocc_off,
+                             &c->d_opos, &c->d_orid, &c->d_spos, &c->d_srid};
+            for (auto *r : rel) r->release();
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            if (!budget) budget = (u64)(0.85 * (double)free_b);
+            if (!ext) {
+                arena_cap = std::min<u64>(bound, budget / 9 * 8 / ent_b);
+                stage_cap = std::min<u64>(bound, budget / 9 / ent_b);
+            } else {
+                arena_cap = std::min<u64>(bound, budget / 100 * 40 / ent_b);
+                stage_cap = std::min<u64>(bound, budget / 100 * 10 / ent_b);
+                occ_cap = std::min<u64>(owned + 8, budget / 100 * 40 / 8);
+                stage_occ_cap = std::min<u64>(owned + 8, budget / 100 * 10 / 8);
+            }
+            g_trace.mark("memory is short: run list released, arena capped");
+        }
+    }
+    // exact sizes when capped (DevBuf::ensure adds slack)
+    CK(c->d_owords.ensure(arena_cap * NW * 8));
+    CK(c->d_ocnt.ensure(arena_cap * 4));
+    CK(c->d_swords.ensure(stage_cap * NW * 8));
+    CK(c->d_scnt.ensure(stage_cap * 4));
     if (ext) {
-        CK(c->d_oocc_off.ensure((arena + 1) * 8));
-        CK(c->d_opos.ensure((owned + 8) * 4));
-        CK(c->d_orid.ensure((owned + 8) * 4));
-        CK(c->d_spos.ensure((owned + 8) * 4));
-        CK(c->d_srid.ensure((owned + 8) * 4));
+        CK(c->d_oocc_off.ensure((arena_cap + 1) * 8));
+        CK(c->d_opos.ensure(occ_cap * 4));
+        CK(c->d_orid.ensure(occ_cap * 4));
+        CK(c->d_spos.ensure(stage_occ_cap * 4));
+        CK(c->d_srid.ensure(stage_occ_cap * 4));
     }
     const size_t hist_bins = (size_t)c->cfg.upper + 1;
     CK(c->d_hist.ensure(hist_bins * 8));
     CK(cudaMemsetAsync(c->d_hist.p, 0, hist_bins * 8, s));
     // per-bin records: look-back cells (zeroed), staging records of the big bins, overflow / big lists
-    int NG = (c->stream_result && TG >= 2048) ? 32 : 1;
-    if (const char *ev = getenv("HSK_GROUPS")) { const int v = atoi(ev); if (v >= 1 && v <= 64 && c->stream_result) NG = v; }
+    const bool streaming = c->stream_result;
+    int NG = (streaming && TG >= 2048) ? 32 : 1;
+    if (const char *ev = getenv("HSK_GROUPS")) { const int v = atoi(ev); if (v >= 1 && v <= 64 && streaming) NG = v; }
     const u32 group_bins = (TG + (u32)NG - 1) / (u32)NG;
     NG = group_bins ? (int)((TG + group_bins - 1) / group_bins) : 1;
     CK(c->d_lb.ensure(((size_t)8 * TG + 16) * 8 + ((size_t)2 * TG + 16) * 4));
@@ -787,9 +1018,11 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     BP.st_words = c->d_swords.as<u64>(); BP.st_cnt = c->d_scnt.as<u32>();
     BP.st_pos = c->d_spos.as<u32>(); BP.st_rid = c->d_srid.as<int>();
     BP.stage_cursor = d_stagecur;
+    BP.stage_cap = stage_cap; BP.stage_occ_cap = stage_occ_cap;
     BP.out_words = c->d_owords.as<u64>(); BP.out_cnt = c->d_ocnt.as<u32>();
     BP.out_occ_off = c->d_oocc_off.as<u64>(); BP.out_pos = c->d_opos.as<u32>(); BP.out_rid = c->d_orid.as<int>();
     BP.histogram = c->d_hist.as<u64>(); BP.cursor = d_cursor;
+    BP.arena_cap = arena_cap; BP.occ_cap = occ_cap; BP.err = d_err;
     BP.ticket = d_ticket; BP.ovf_count = d_ovfc;
     BP.ovf_list = reinterpret_cast<u32 *>(BP.fin + (size_t)2 * TG + 8);
     BP.big_list = BP.ovf_list + TG + 4; BP.big_count = d_bigc;
@@ -799,13 +1032,13 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         if (NW <= 2 && !ext && !(ev && *ev == '0')) {
             CK(c->d_dd.ensure(bin_dedup_scratch_bytes(c->sm_count, SW)));
             BP.dd_slots = c->d_dd.as<uint4>();
-            BP.dd_mult = reinterpret_cast<u32 *>(BP.dd_slots + (size_t)c->sm_count * 2 * BN_DDLIMIT * (SW / 4));
+            BP.dd_mult = reinterpret_cast<u32 *>(BP.dd_slots + (size_t)c->sm_count * 2 * BN_DDLIMIT_MAX * (SW / 4));
         }
     }
     BP.grp_end = c->d_grp.as<u64>();
     BP.grp_done = reinterpret_cast<u32 *>(BP.grp_end + (size_t)2 * NG); BP.grp_big = BP.grp_done + NG;
     volatile u64 *snap = c->h_grp.as<u64>();
-    BP.snap = c->stream_result ? c->h_grp.as<u64>() : nullptr;
+    BP.snap = streaming ? c->h_grp.as<u64>() : nullptr;
     for (int i = 0; i < 4 * NG; ++i) snap[i] = 0;
 
     // ---- stages 4+5 on chip: one persistent launch over all bins.  hsk_count streams the arena to the host group by
@@ -813,21 +1046,39 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     const size_t hist_bytes = hist_bins * 8;
     u64 sent_kept = 0, sent_occ = 0;
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
-    if (c->stream_result) { ev_d0 = c->ev(); ev_d1 = c->ev(); CK(cudaEventRecord(ev_d0, c->copy_stream)); }
-    // copy arena entries [sent_kept, kept_end) / occurrences [sent_occ, occ_end) (after `ready`, if given)
-    auto send_result = [&](u64 kept_end, u64 occ_end, u64 kept_total_hint, cudaEvent_t ready) -> int {
+    if (streaming) { ev_d0 = c->ev(); ev_d1 = c->ev(); CK(cudaEventRecord(ev_d0, c->copy_stream)); }
+    const bool sinking = streaming && c->sink_fn != nullptr;
+    auto refresh_view = [&]() {
+        hsk_result &v = c->sink_view;
+        v.nwords = NW;
+        v.kmer_words = c->h_owords.as<uint64_t>(); v.cnt = c->h_ocnt.as<u32>();
+        v.occ_off = ext ? c->h_oocc_off.as<uint64_t>() : nullptr;
+        v.pos = ext ? c->h_opos.as<u32>() : nullptr; v.rid = ext ? c->h_orid.as<int32_t>() : nullptr;
+        v.histogram = c->h_hist.as<uint64_t>();
+    };
+    if (sinking) { refresh_view(); c->sink->begin(c->sink_fn, c->sink_user, &c->sink_view, c->cfg.device); }
+    int sink_rc = 0;
+    // copy arena entries [sent_kept, kept_end) / occurrences [sent_occ, occ_end) (after `ready`, if given) and hand them
+    // to the sink
+    auto send_result = [&](u64 kept_end, u64 occ_end, u64 kept_total_hint, cudaEvent_t ready, bool last) -> int {
         const u64 want = std::max<u64>(kept_end, kept_total_hint) + 1;
-        if (want * NW * 8 > c->h_owords.cap || want * 4 > c->h_ocnt.cap || (ext && (want + 1) * 8 > c->h_oocc_off.cap)) {
+        const bool grow_k = want * NW * 8 > c->h_owords.cap || want * 4 > c->h_ocnt.cap || (ext && (want + 1) * 8 > c->h_oocc_off.cap);
+        const bool grow_o = ext && ((occ_end + 1) * 4 > c->h_opos.cap);
+        if (grow_k || grow_o) {
+            // the arrays move: nobody may be reading or writing them
             CK(cudaStreamSynchronize(c->copy_stream));
-            CK(c->h_owords.ensure_keep(want * NW * 8, sent_kept * NW * 8));
-            CK(c->h_ocnt.ensure_keep(want * 4, sent_kept * 4));
-            if (ext) CK(c->h_oocc_off.ensure_keep((want + 1) * 8, sent_kept * 8));
-        }
-        if (ext && ((occ_end + 1) * 4 > c->h_opos.cap)) {
-            const u64 wo = occ_end + (kept_end ? (u64)((double)occ_end / (double)kept_end * (double)(want - kept_end)) : 0) + 1;
-            CK(cudaStreamSynchronize(c->copy_stream));
-            CK(c->h_opos.ensure_keep(wo * 4, sent_occ * 4));
-            CK(c->h_orid.ensure_keep(wo * 4, sent_occ * 4));
+            if (sinking) sink_rc |= c->sink->drain();
+            if (grow_k) {
+                CK(c->h_owords.ensure_keep(want * NW * 8, sent_kept * NW * 8));
+                CK(c->h_ocnt.ensure_keep(want * 4, sent_kept * 4));
+                if (ext) CK(c->h_oocc_off.ensure_keep((want + 1) * 8, sent_kept * 8));
+            }
+            if (grow_o) {
+                const u64 wo = occ_end + (kept_end ? (u64)((double)occ_end / (double)kept_end * (double)(want - kept_end)) : 0) + 1;
+                CK(c->h_opos.ensure_keep(wo * 4, sent_occ * 4));
+                CK(c->h_orid.ensure_keep(wo * 4, sent_occ * 4));
+            }
+            refresh_view();
         }
         cudaStream_t cs = c->copy_stream;
         if (ready) CK(cudaStreamWaitEvent(cs, ready, 0));
@@ -841,6 +1092,11 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
             CK(cudaMemcpyAsync(c->h_opos.as<u32>() + sent_occ, c->d_opos.as<u32>() + sent_occ, no * 4, cudaMemcpyDeviceToHost, cs));
             CK(cudaMemcpyAsync(c->h_orid.as<int>() + sent_occ, c->d_orid.as<int>() + sent_occ, no * 4, cudaMemcpyDeviceToHost, cs));
         }
+        if (sinking && (nk || last)) {
+            cudaEvent_t arrived = c->ev();
+            CK(cudaEventRecord(arrived, cs));
+            c->sink->push({sent_kept, nk, sent_occ, no, last ? kept_end : std::max<u64>(kept_end, kept_total_hint), arrived});
+        }
         sent_kept = kept_end; sent_occ = occ_end;
         return 0;
     };
@@ -850,7 +1106,7 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     c->stats.n_launches += 1;
     cudaEvent_t ev_bins_done = c->ev();
     CK(cudaEventRecord(ev_bins_done, s));
-    if (c->stream_result) {
+    if (streaming) {
         // follow the kernel: a finished group whose bins are all in place goes out at once; after the first group
         // that waits for the big gather the rest is sent at the end
         for (int g = 0; g < NG; ++g) {
@@ -860,13 +1116,20 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
             if (snap[4 * g + 3] == 0 || snap[4 * g + 2] != 0) break;
             g_trace.mark("bin group in the arena");
             const u64 kept_end = snap[4 * g], occ_end = snap[4 * g + 1];
+            if (kept_end > arena_cap || occ_end > occ_cap) break;   // the arena overflowed: reported below
             const u64 hint = (u64)((double)kept_end * (double)NG / (double)(g + 1) * 1.15) + 4096;
-            if (send_result(kept_end, occ_end, hint, nullptr)) return 1;
+            if (send_result(kept_end, occ_end, hint, nullptr, false)) return 1;
         }
     }
     c->stats.n_batches = 1;
     CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    const char *arena_msg = "the result (%llu entries) does not fit the memory of the GPU next to the reads and supermers (room for %llu): "
+                            "split the input over more ranks";
+    if (reinterpret_cast<u32 *>(c->h_cursor.as<u64>() + 7)[0] & 1u) {
+        if (sinking) c->sink->drain();
+        return fail(arena_msg, (unsigned long long)c->h_cursor.as<u64>()[0], (unsigned long long)arena_cap);
+    }
     const u32 novf = reinterpret_cast<u32 *>(c->h_cursor.as<u64>() + 3)[1];
     c->stats.n_overflow_bins = novf;
     if (*reinterpret_cast<u32 *>(c->h_cursor.as<u64>() + 6)) {   // bins that keep more k-mers than a CTA sorts
@@ -875,41 +1138,55 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     }
 
     if (novf) {
-        // ---- leftovers through HBM: fetch the tables of the overflow bins
+        // ---- leftovers through HBM: fetch the tables of the overflow bins.  Segments are listed bin by bin (all sources
+        //      of a bin next to each other), so that a batch never holds a part of a bin.
         std::vector<u32> ovf(novf);
         CK(cudaMemcpy(ovf.data(), BP.ovf_list, (size_t)novf * 4, cudaMemcpyDeviceToHost));
         std::sort(ovf.begin(), ovf.end());
-        std::vector<OvfSeg> segs;
-        // tables of all bins in one copy per source (only when something overflowed)
+        std::vector<OvfSeg> segs((size_t)novf * G);
         std::vector<u64> hs((size_t)TG + 1), hk((size_t)TG);
-        for (int src = 0; src < G; ++src) {
+        for (int src = 0; src < G; ++src) {   // tables of all bins in one copy per source (only when something overflowed)
             CK(cudaMemcpy(hs.data(), BP.seg_start[src], ((size_t)TG + 1) * 8, cudaMemcpyDeviceToHost));
             const u64 *kp = (G == 1) ? d_tot : c->d_alltot.as<u64>() + (size_t)src * T + b_lo;
             CK(cudaMemcpy(hk.data(), kp, (size_t)TG * 8, cudaMemcpyDeviceToHost));
-            for (u32 lb : ovf) segs.push_back({src, hs[lb], hs[lb + 1] - hs[lb], hk[lb] & ((1ull << 40) - 1)});
+            for (u32 i = 0; i < novf; ++i) {
+                const u32 lb = ovf[i];
+                segs[(size_t)i * G + src] = {src, lb, hs[lb], hs[lb + 1] - hs[lb], bt_kmers(hk[lb])};
+            }
         }
-        if (run_hbm_path(c, segs)) return 1;
-        CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 16, cudaMemcpyDeviceToHost, s));
+        CountLimits lim{arena_cap, occ_cap, d_err};
+        if (run_hbm_path(c, segs, lim)) { if (sinking) c->sink->drain(); return 1; }
+        CK(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 64, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ev_t1, s));
     CK(cudaStreamSynchronize(s));
+    if (reinterpret_cast<u32 *>(c->h_cursor.as<u64>() + 7)[0] & 1u) {
+        if (sinking) c->sink->drain();
+        return fail(arena_msg, (unsigned long long)c->h_cursor.as<u64>()[0], (unsigned long long)arena_cap);
+    }
     c->n_kept = c->h_cursor.as<u64>()[0];
     c->n_occ = c->h_cursor.as<u64>()[1];
     if (ext) {   // closing offset of the occurrence lists
         CK(cudaMemcpyAsync(c->d_oocc_off.as<u64>() + c->n_kept, c->h_cursor.as<u64>() + 1, 8, cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
     }
-    if (c->stream_result) {
+    if (streaming) {
         // what the HBM path appended, the histogram, and the end of the copies
-        if (send_result(c->n_kept, c->n_occ, c->n_kept, ev_t1)) return 1;
         CK(c->h_hist.ensure(hist_bytes));
+        if (sinking) refresh_view();
         CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, hist_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (send_result(c->n_kept, c->n_occ, c->n_kept, ev_t1, true)) return 1;
         CK(cudaEventRecord(ev_d1, c->copy_stream));
         g_trace.mark("last copies enqueued");
         CK(cudaStreamSynchronize(c->copy_stream));
         g_trace.mark("copies done");
         if (ext) c->h_oocc_off.as<u64>()[c->n_kept] = c->n_occ;
         CK(cudaEventElapsedTime(&c->stats.ms_d2h, ev_d0, ev_d1));
+        if (sinking) {
+            sink_rc |= c->sink->drain();
+            g_trace.mark("sink done");
+            if (sink_rc) return fail("hsk_count_stream: the sink failed (status %d)", sink_rc);
+        }
     }
     c->stats.ms_extract = hsk_ctx::sum_ms(c->ev_extract);
     c->stats.ms_exchange = hsk_ctx::sum_ms(c->ev_exchange);
@@ -944,8 +1221,7 @@ int hsk_count_device(hsk_ctx *c, const uint8_t *d_packed, uint64_t nbytes, const
     if (((uintptr_t)d_packed & 15) != 0) return fail("hsk_count_device: d_packed must be 16-byte aligned");
     c->stats.ms_h2d = 0;
     c->ev_used = 0;
-    c->in_chunks.clear();
-    c->d_in_flags = nullptr;
+    end_input(c);
     if (count_device(c, d_packed, nbytes, (nbytes + 15) & ~15ull, (const u64 *)d_read_off, d_read_len, nreads, readid_base)) return 1;
     fill_device_result(c, out);
     return 0;
@@ -1001,7 +1277,37 @@ int hsk_fetch_result(hsk_ctx *c, hsk_result *out)
 // host -> device staging of a DnaBuffer.  The 64-bit read lengths go up as they are and reads.cu turns them into
 // byte offsets + 32-bit lengths on the device; the packed bytes go up in chunks on the copy stream, every chunk
 // with an event and the number of extraction tiles it completes, so that pass A of the extraction starts on the
-// first chunk while the others are still on the bus.
+// first chunk while the others are still on the bus.  Page-locked input is sent from where it is; pageable input
+// (a DnaBuffer is a plain heap array) is copied chunk by chunk into a ring of page-locked buffers by the context's
+// host threads, each chunk right before the extraction waits for it (stage_chunk).
+static bool is_pageable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_chunk(hsk_ctx *c, size_t ci)
+{
+    if (!c->in_pageable || ci < c->in_staged) return 0;
+    for (; c->in_staged <= ci; ++c->in_staged) {
+        const hsk_ctx::InChunk &ch = c->in_chunks[c->in_staged];
+        const int slot = (int)(c->in_staged % hsk_ctx::RING);
+        if (c->in_staged >= (size_t)hsk_ctx::RING) CK(cudaEventSynchronize(c->ring_free[slot]));   // its previous chunk has left
+        u8 *dst = c->h_ring[slot].as<u8>();
+        const u8 *src = c->in_host + ch.off;
+        c->pool->parallel_for((ch.n + 4095) / 4096, [=](u64 lo, u64 hi) {
+            const u64 b0 = lo * 4096, b1 = std::min<u64>(hi * 4096, ch.n);
+            if (b1 > b0) memcpy(dst + b0, src + b0, b1 - b0);
+        });
+        CK(cudaMemcpyAsync(c->d_packed.as<u8>() + ch.off, dst, ch.n, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(ch.ready, c->copy_stream));
+        CK(cudaEventRecord(c->ring_free[slot], c->copy_stream));
+        if (c->in_staged + 1 == c->in_chunks.size()) CK(cudaEventRecord(c->ev_h2d[1], c->copy_stream));
+    }
+    return 0;
+}
+
 static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads)
 {
     CK(cudaSetDevice(c->cfg.device));
@@ -1014,8 +1320,23 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
     const size_t rts = read_table_scratch_bytes(nreads);
     CK(c->d_rtscratch.ensure(rts + 16));
     c->d_in_flags = reinterpret_cast<u32 *>(c->d_rtscratch.as<u8>() + rts);
+    c->in_pageable = nbytes > 0 && is_pageable(packed);
+    c->in_host = packed;
+    c->in_staged = 0;
     CK(cudaMemsetAsync(c->d_in_flags, 0, 16, s));
-    if (nreads) CK(cudaMemcpyAsync(c->d_len64.p, read_len, nreads * 8, cudaMemcpyHostToDevice, s));
+    if (nreads) {
+        const uint64_t *lens = read_len;
+        if (nreads >= 4096 && is_pageable(read_len)) {   // a large pageable array would be staged by the driver, one thread
+            CK(c->h_len.ensure(nreads * 8));
+            u64 *dst = c->h_len.as<u64>();
+            c->pool->parallel_for((nreads + 511) / 512, [=](u64 lo, u64 hi) {
+                const u64 i0 = lo * 512, i1 = std::min<u64>(hi * 512, nreads);
+                if (i1 > i0) memcpy(dst + i0, read_len + i0, (i1 - i0) * 8);
+            });
+            lens = reinterpret_cast<const uint64_t *>(dst);
+        }
+        CK(cudaMemcpyAsync(c->d_len64.p, lens, nreads * 8, cudaMemcpyHostToDevice, s));
+    }
     CK(launch_read_table(c->d_len64.as<u64>(), nreads, nbytes, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(),
                          c->d_rtscratch.as<u64>(), c->d_in_flags, s));
     c->stats.n_launches += 3;
@@ -1023,44 +1344,70 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
     const u32 OL = (u32)xt_out_lanes(c->cfg.k - c->m_eff + 1);
     c->in_chunks.clear();
     cudaEvent_t e0 = c->ev(), e1 = c->ev();
+    c->ev_h2d[0] = e0; c->ev_h2d[1] = e1;   // ms_h2d is read after the call has synchronised
     CK(cudaEventRecord(e0, cs));
     CK(cudaMemsetAsync(c->d_packed.as<u8>() + (nbytes & ~15ull), 0, padded - (nbytes & ~15ull), cs));
-    u64 chunk = std::min<u64>(std::max<u64>((nbytes / 8 + 4095) & ~4095ull, 2ull << 20), 256ull << 20);
+    u64 chunk = std::min<u64>(std::max<u64>((nbytes / 8 + 4095) & ~4095ull, 2ull << 20), c->in_pageable ? (16ull << 20) : (256ull << 20));
+    if (c->in_pageable) {
+        for (int r = 0; r < hsk_ctx::RING; ++r) {
+            CK(c->h_ring[r].ensure(std::min<u64>(chunk, nbytes)));
+            if (!c->ring_free[r]) CK(cudaEventCreateWithFlags(&c->ring_free[r], cudaEventDisableTiming));
+        }
+    }
     for (u64 o = 0; o < nbytes; o += chunk) {
         const u64 n = std::min<u64>(chunk, nbytes - o);
-        CK(cudaMemcpyAsync(c->d_packed.as<u8>() + o, packed + o, n, cudaMemcpyHostToDevice, cs));
         cudaEvent_t ev = c->ev();
-        CK(cudaEventRecord(ev, cs));
+        if (!c->in_pageable) {
+            CK(cudaMemcpyAsync(c->d_packed.as<u8>() + o, packed + o, n, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(ev, cs));
+        }
         const u64 words = (o + n) / 4;   // a tile reads 34 words from its first one
-        c->in_chunks.push_back({words >= 34 ? (words - 34) / OL + 1 : 0, ev});
+        c->in_chunks.push_back({words >= 34 ? (words - 34) / OL + 1 : 0, ev, o, n});
     }
-    CK(cudaEventRecord(e1, cs));
-    // ms_h2d is read after the call has synchronised
-    c->ev_h2d[0] = e0; c->ev_h2d[1] = e1;
+    if (!c->in_pageable || nbytes == 0) CK(cudaEventRecord(e1, cs));
     return 0;
 }
 
-int hsk_count(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
-              int32_t readid_base, hsk_result *out)
+static void end_input(hsk_ctx *c)
+{
+    c->in_chunks.clear();
+    c->d_in_flags = nullptr;
+    c->in_host = nullptr;
+    c->in_pageable = false;
+}
+
+int hsk_count_stream(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
+                     int32_t readid_base, hsk_sink_fn sink, void *user, hsk_result *out)
 {
     if (!c || !out) return fail("hsk_count: null argument");
     if (nreads && (!read_len)) return fail("hsk_count: null read_len");
+    if (nbytes && !packed) return fail("hsk_count: null packed buffer");
     c->ev_used = 0;
     hsk_stats keep;
     memset(&keep, 0, sizeof(keep));
     c->stats = keep;
     g_trace.start();
     g_trace.mark("hsk_count begin");
-    if (stage_input(c, packed, nbytes, read_len, nreads)) return 1;
+    if (stage_input(c, packed, nbytes, read_len, nreads)) { end_input(c); return 1; }
     g_trace.mark("input copies enqueued");
     const u64 staged_launches = c->stats.n_launches;
     c->stream_result = true;
+    c->sink_fn = sink; c->sink_user = user;
+    if (sink && !c->sink) c->sink.reset(new SinkWorker());
     const int rc = count_device(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(),
                                 c->d_read_len.as<u32>(), nreads, readid_base);
     c->stream_result = false;
-    c->in_chunks.clear();
-    c->d_in_flags = nullptr;
-    if (rc) { cudaStreamSynchronize(c->copy_stream); return 1; }
+    c->sink_fn = nullptr; c->sink_user = nullptr;
+    end_input(c);
+    if (rc) {
+        const std::string msg = g_err;   // the first error is the one to report
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        if (c->sink) c->sink->drain();
+        (void)cudaGetLastError();
+        g_err = msg;
+        return 1;
+    }
     g_trace.mark("hsk_count end");
     c->stats.n_launches += staged_launches;
     CK(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_h2d[0], c->ev_h2d[1]));
@@ -1076,6 +1423,12 @@ int hsk_count(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t
     out->histogram = c->h_hist.as<uint64_t>();
     out->stats = c->stats;
     return 0;
+}
+
+int hsk_count(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
+              int32_t readid_base, hsk_result *out)
+{
+    return hsk_count_stream(c, packed, nbytes, read_len, nreads, readid_base, nullptr, nullptr, out);
 }
 
 int hsk_allreduce_histogram(hsk_ctx *c, uint64_t *hist)
@@ -1107,21 +1460,16 @@ int hsk_fill_entries(hsk_ctx *c, void *entries, uint64_t capacity_entries)
     const u64 *w = c->h_owords.as<u64>();
     const u32 *cnt = c->h_ocnt.as<u32>();
     u64 *dst = reinterpret_cast<u64 *>(entries);
-    // SoA -> {TKmer kmer; uint64_t cnt;} entries (reference KmerListEntryS, include/kmer.hpp:368-407), a few host
-    // threads: the loop is memory-bound and the list has millions of entries
+    // SoA -> {TKmer kmer; uint64_t cnt;} entries (reference KmerListEntryS, include/kmer.hpp:368-407) by the context's
+    // host threads: the loop is memory-bound and the list has millions of entries
     const u64 n = c->n_kept;
-    auto fill = [=](u64 lo, u64 hi) {
-        for (u64 i = lo; i < hi; ++i) {
+    c->pool->parallel_for((n + 4095) / 4096, [=](u64 lo, u64 hi) {
+        const u64 i1 = std::min<u64>(hi * 4096, n);
+        for (u64 i = lo * 4096; i < i1; ++i) {
             for (int l = 0; l < NW; ++l) dst[i * (NW + 1) + l] = w[i * NW + l];
             dst[i * (NW + 1) + NW] = cnt[i];
         }
-    };
-    unsigned nt = std::min<unsigned>(8u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
-    if (n < (1u << 16)) nt = 1;
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t) th.emplace_back(fill, n * t / nt, n * (t + 1) / nt);
-    fill(0, n / nt);
-    for (auto &x : th) x.join();
+    });
     return 0;
 }
 
@@ -1159,17 +1507,16 @@ int hsk_debug_extract(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const 
     if (!c || !out) return fail("hsk_debug_extract: null argument");
     c->ev_used = 0;
     c->ev_extract.clear();
-    if (stage_input(c, packed, nbytes, read_len, nreads)) return 1;
+    if (stage_input(c, packed, nbytes, read_len, nreads)) { end_input(c); return 1; }
     if (run_extract(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(), c->d_read_len.as<u32>(), nreads,
-                    readid_base, true)) { c->in_chunks.clear(); c->d_in_flags = nullptr; cudaStreamSynchronize(c->copy_stream); return 1; }
-    c->in_chunks.clear();
-    c->d_in_flags = nullptr;
+                    readid_base, true)) { end_input(c); cudaStreamSynchronize(c->copy_stream); return 1; }
+    end_input(c);
     const u32 T = c->tt;
     const int SW = slot_words(c->nwords, c->cfg.ext != 0);
     const u64 *hb = c->h_bucket.as<u64>();
     const u64 S = hb[(size_t)T + T];
     c->h_dbg.resize(2 * (size_t)T);
-    for (u32 b = 0; b < T; ++b) { c->h_dbg[b] = hb[b] >> 40; c->h_dbg[T + b] = hb[b] & ((1ull << 40) - 1); }
+    for (u32 b = 0; b < T; ++b) { c->h_dbg[b] = bt_slots(hb[b]); c->h_dbg[T + b] = bt_kmers(hb[b]); }
     CK(c->h_owords.ensure((S + 1) * (size_t)SW * 4));
     if (S) CK(cudaMemcpyAsync(c->h_owords.p, c->d_slots.p, S * (size_t)SW * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

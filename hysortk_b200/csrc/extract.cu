@@ -118,7 +118,7 @@ __device__ __forceinline__ void load_lane_words(const u32 *__restrict__ packed32
 }
 
 // ---- pass A: per-bin totals + the run list of every tile ------------------------------------------
-// bin_tot[b] += (slots << 40) | k-mers per valid run.  Run list entry = (n << 48 | start << 32 | bin);
+// bin_tot[b] += bt_pack(slots, k-mers) per valid run.  Run list entry = (n << 48 | start << 32 | bin);
 // tile_hdr[tile] = (first entry, number of entries).
 template <int W>
 __global__ void __launch_bounds__(XT_THREADS, XT_CTAS_PER_SM) k_supermer_count(ExtractParams P, u64 *__restrict__ bin_tot,
@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(XT_THREADS, XT_CTAS_PER_SM) k_supermer_count(E
                                                                 ulonglong2 *__restrict__ tile_hdr,
                                                                 u64 *__restrict__ run_cursor, u64 run_capacity)
 {
+    // run_cursor[0] = entries of the run list; run_cursor[2], [3] = grand totals of slots / k-mers, kept apart from the
+    // per-bin words so that a field overflow there is noticed (common.cuh: bt_pack)
     constexpr int OL = xt_out_lanes(W), OUT = OL * XT_R;
+    u64 chk_slots = 0, chk_kmers = 0;
     __shared__ u32 s_st[XT_WARPS][OUT + 2];
     __shared__ u16 s_pos[XT_WARPS][OUT + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,7 +245,8 @@ __global__ void __launch_bounds__(XT_THREADS, XT_CTAS_PER_SM) k_supermer_count(E
             if (valid) {
                 const u32 b = hash_bucket(s, P.nbins);
                 const u32 pieces = __umulhi(n + P.slot_nmax - 1, P.slot_ninv);
-                atomicAdd(&bin_tot[b], ((u64)pieces << 40) | (u64)n);
+                atomicAdd(&bin_tot[b], bt_pack(pieces, n));
+                chk_slots += pieces; chk_kmers += n;
                 const u32 idx = base + __popc(bal & ((1u << lane) - 1));
                 if (fits) run_list[rb + idx] = ((u64)(start | (n << 16)) << 32) | b;
             }
@@ -250,6 +254,12 @@ __global__ void __launch_bounds__(XT_THREADS, XT_CTAS_PER_SM) k_supermer_count(E
         }
         __syncwarp();
     }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        chk_slots += __shfl_xor_sync(FULL, chk_slots, d);
+        chk_kmers += __shfl_xor_sync(FULL, chk_kmers, d);
+    }
+    if (lane == 0 && chk_kmers) { atomicAdd(run_cursor + 2, chk_slots); atomicAdd(run_cursor + 3, chk_kmers); }
 }
 
 // ---- bin scan: exclusive prefix over bins of the slot counts -> bin starts / cursors; k-mer total ---------
@@ -279,8 +289,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bin_tile_sums(const u64 *__restr
     for (int i = 0; i < BS_PER; ++i) {
         const u32 b = blockIdx.x * BS_TILE + threadIdx.x * BS_PER + i;
         const u64 v = b < nbins ? bin_tot[b] : 0;
-        slots += v >> 40;
-        kmers += v & ((1ull << 40) - 1);
+        slots += bt_slots(v);
+        kmers += bt_kmers(v);
     }
     slots = block_sum_1024(slots, s_c);
     kmers = block_sum_1024(kmers, s_c);
@@ -338,7 +348,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bin_starts(const u64 *__restrict
 #pragma unroll
     for (int i = 0; i < BS_PER; ++i) {
         const u32 b = blockIdx.x * BS_TILE + threadIdx.x * BS_PER + i;
-        c[i] = b < nbins ? (bin_tot[b] >> 40) : 0;
+        c[i] = b < nbins ? bt_slots(bin_tot[b]) : 0;
         tc += c[i];
     }
     u64 ic = tc;

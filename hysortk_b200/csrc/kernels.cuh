@@ -34,11 +34,12 @@ struct ExtractParams {
     u32 *out_stream;         // pass B destination: the bin-major supermer stream of this rank
 };
 
+constexpr int XT_META = 8;   // u64 words after the bin starts: run cursor, k-mer total, pass A's independent slot / k-mer totals
 // grid of the two extraction passes (persistent warps, contiguous tile ranges)
 u32 extract_grid(int w, int sm_count);
 // tile_read[t] = read holding byte t * out_slots / 4 (t = 0..ntiles)
 cudaError_t launch_tile_reads(const ExtractParams &P, u32 *tile_read, cudaStream_t s);
-// pass A: bin_tot[b] += (slots << 40 | k-mers) per run; run list + tile headers for pass B
+// pass A: bin_tot[b] += bt_pack(slots, k-mers) per run; run list + tile headers for pass B
 cudaError_t launch_supermer_count(const ExtractParams &P, u32 nctas, u64 *bin_tot, u64 *run_list, ulonglong2 *tile_hdr,
                                   u64 *run_cursor, u64 run_capacity, cudaStream_t s);
 // bin_start: nbins+1 exclusive prefix of the slot counts, bin_cursor[b] = bin_start[b]; *kmers_total += all k-mers
@@ -65,8 +66,7 @@ cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext,
                           Planes out_keys, u64 *out_val, cudaStream_t s);
 
 // ---- stages 4+5 on chip: bins.cu ---------------------------------------------------------------------
-constexpr int BN_THREADS = 512;
-constexpr int BN_DDLIMIT = 1536;     // bins with more supermer slots skip the de-duplication; entries per CTA list
+constexpr int BN_DDLIMIT_MAX = 2048;   // entries of a CTA's list of distinct supermers (bins with more slots skip the de-duplication)
 
 struct BinParams {
     int k;
@@ -75,17 +75,20 @@ struct BinParams {
     int nsrc;
     const u32 *slots[BN_MAX_SRC];        // supermer slot stream per source rank
     const u64 *seg_start[BN_MAX_SRC];    // nbins+1: first slot of every bin inside the source's stream
-    const u64 *bin_kmers;                // nbins: (slots << 40 | k-mers) per bin over all sources; low 40 bits used
+    const u64 *bin_kmers;                // nbins: bt_pack(slots, k-mers) per bin over all sources; the k-mer field is used
     // final arena (bins in index order, ascending k-mers inside a bin)
     u64 *out_words; u32 *out_cnt; u64 *out_occ_off; u32 *out_pos; int *out_rid;
     u64 *histogram;
     u64 *cursor;                         // [0] entries, [1] occurrences in the arena once every bin is done
+    u64 arena_cap, occ_cap;              // entries / occurrences the arena holds; a bin that would run past them sets *err
+    u32 *err;                            // zeroed; bit 0: the arena is too small for the result
     u64 *lb_state;                       // 2 x nbins, zeroed: look-back cells (entries, occurrences)
     u32 *ticket;                         // zeroed
     u32 *ovf_list, *ovf_count;           // bins left to the HBM path
     // bins that keep more k-mers than a CTA sorts itself: unsorted in the staging area, listed for the big gather
     u64 *st_words; u32 *st_cnt; u32 *st_pos; int *st_rid;
     u64 *stage_cursor;                   // [0] entries, [1] occurrences claimed so far (zeroed)
+    u64 stage_cap, stage_occ_cap;        // room in the staging area; a bin that finds none goes to the HBM path
     u64 *bin_rec;                        // nbins x {stage entry base, kept, stage occurrence base, occurrences}
     u64 *fin;                            // nbins x {final entry base, final occurrence base}
     u32 *big_list, *big_count;
@@ -141,6 +144,8 @@ struct CountParams {
     int *out_rid;            // ext: ReadId per occurrence
     u64 *histogram;          // upper+1 bins
     u64 *cursor;             // [0] = entries emitted so far, [1] = occurrences emitted so far
+    u64 arena_cap, occ_cap;  // room in the arena; what would run past it is not written and *err gets bit 0
+    u32 *err;
 };
 
 // scratch: 2 * (ceil(n/CT_TILE)+1) u64

@@ -24,12 +24,15 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <memory>
+#include <new>
+#include <type_traits>
 
 namespace hysortk {
 
 namespace {
 
-struct FaiRecord { size_t len, pos, bases; };
+struct FaiRecord { size_t len, pos, bases, width; };   /* .fai columns 2-5: length, offset, bases per line, bytes per line */
 
 int local_device_for(int rank)
 {
@@ -42,13 +45,122 @@ int local_device_for(int rank)
     return per > 0 ? rank % per : 0;
 }
 
-/* one engine context per process, re-created when the communicator shape changes */
+/* One engine context per process, re-created when the communicator shape changes.  It is NOT torn down by a static
+ * destructor: at that point MPI is finalised and the CUDA runtime may be gone, and with several ranks hsk_destroy is
+ * collective.  hysortk::release_gpu_engine() frees it explicitly; otherwise it lives until the process exits. */
 struct Engine {
     hsk_ctx *ctx = nullptr;
     int rank = -1, nranks = -1;
-    ~Engine() { if (ctx) hsk_destroy(ctx); }
 };
 Engine g_engine;
+
+/* Builds the KmerListS while the result is still arriving (sink of hsk_count_stream).  The entries are constructed in
+ * place in memory obtained from std::allocator<KmerListEntryS>, by the host threads, part by part; the finished array is
+ * then handed to a std::vector without the value-initialisation + copy that resize() + assignment would cost (the list
+ * has millions of entries; first touch of its pages is the expensive part and is spread over the threads). */
+struct ListBuilder {
+    static constexpr int NW = TKmer::NBYTES / 8;
+    std::allocator<KmerListEntryS> alloc;
+    KmerListEntryS *base = nullptr;
+    size_t cap = 0, filled = 0;
+    int nthreads = 1;   /* the caller's OpenMP team size: the sink runs on a thread of the engine, whose own default differs */
+    std::string error;
+
+    ~ListBuilder() { release(); }
+    void release()
+    {
+        if (!base) return;
+#if EXTENSION == 1
+        for (size_t i = 0; i < filled; ++i) base[i].~KmerListEntryS();
+#endif
+        alloc.deallocate(base, cap);
+        base = nullptr; cap = filled = 0;
+    }
+    void grow(size_t want)
+    {
+        const size_t ncap = want + want / 8 + 1024;
+        KmerListEntryS *nb = alloc.allocate(ncap);
+        if (filled) {
+#if EXTENSION == 1
+            #pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (size_t i = 0; i < filled; ++i) { new (nb + i) KmerListEntryS(std::move(base[i])); base[i].~KmerListEntryS(); }
+#else
+            const size_t n = filled;
+            #pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (size_t b = 0; b < (n + 65535) / 65536; ++b) {
+                const size_t lo = b * 65536, hi = std::min(n, lo + 65536);
+                std::memcpy(static_cast<void *>(nb + lo), static_cast<const void *>(base + lo), (hi - lo) * sizeof(KmerListEntryS));
+            }
+#endif
+        }
+        if (base) alloc.deallocate(base, cap);
+        base = nb; cap = ncap;
+    }
+    int take(const hsk_result *v, uint64_t first, uint64_t n, uint64_t first_occ, uint64_t n_occ, uint64_t hint)
+    {
+        try {
+            const size_t want = std::max<size_t>(first + n, hint);
+            if (want > cap) grow(want);
+            KmerListEntryS *dst = base;
+            const uint64_t *words = v->kmer_words;
+            const uint32_t *cnt = v->cnt;
+#if EXTENSION == 1
+            const uint64_t *off = v->occ_off;
+            const uint32_t *pos = v->pos;
+            const int32_t *rid = v->rid;
+            const uint64_t occ_end = first_occ + n_occ;
+            #pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (size_t i = first; i < first + n; ++i) {
+                KmerListEntryS *e = new (dst + i) KmerListEntryS();
+                e->kmer = TKmer(static_cast<const void *>(words + i * NW));
+                e->cnt = cnt[i];
+                const uint64_t o0 = off[i], o1 = (i + 1 < first + n) ? off[i + 1] : occ_end;
+                e->pos.assign(pos + o0, pos + o1);
+                e->rid.assign(rid + o0, rid + o1);
+            }
+#else
+            (void)first_occ; (void)n_occ;
+            static_assert(sizeof(KmerListEntryS) == 8 * (NW + 1), "entry layout: k-mer words followed by the 64-bit count");
+            uint64_t *raw = reinterpret_cast<uint64_t *>(dst);
+            #pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (size_t b = first / 4096; b < (first + n + 4095) / 4096; ++b) {
+                const size_t lo = std::max<size_t>(first, b * 4096), hi = std::min<size_t>(first + n, (b + 1) * 4096);
+                for (size_t i = lo; i < hi; ++i) {
+                    for (int l = 0; l < NW; ++l) raw[i * (NW + 1) + l] = words[i * NW + l];
+                    raw[i * (NW + 1) + NW] = cnt[i];
+                }
+            }
+#endif
+            filled = first + n;
+            return 0;
+        } catch (const std::exception& e) {
+            error = e.what();
+            return 1;
+        }
+    }
+    static int sink(void *user, const hsk_result *v, uint64_t first, uint64_t n, uint64_t first_occ, uint64_t n_occ, uint64_t hint)
+    {
+        return static_cast<ListBuilder *>(user)->take(v, first, n, first_occ, n_occ, hint);
+    }
+    /* the finished array becomes the storage of a std::vector */
+    std::unique_ptr<KmerListS> finish()
+    {
+        auto list = std::make_unique<KmerListS>();
+        if (!base || filled == 0) return list;
+#if defined(__GLIBCXX__) || defined(_LIBCPP_VERSION)
+        /* libstdc++ / libc++: a vector with the default allocator is three pointers (begin, end, end of storage) */
+        static_assert(sizeof(KmerListS) == 3 * sizeof(void *), "std::vector layout");
+        KmerListEntryS *triple[3] = {base, base + filled, base + cap};
+        std::memcpy(static_cast<void *>(list.get()), triple, sizeof(triple));
+        base = nullptr; cap = filled = 0;
+#else
+        list->reserve(filled);
+        for (size_t i = 0; i < filled; ++i) list->push_back(std::move(base[i]));
+        release();
+#endif
+        return list;
+    }
+};
 
 hsk_ctx *engine_for(MPI_Comm comm)
 {
@@ -94,7 +206,10 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
         while (std::getline(fai, line)) {
             if (line.empty()) continue;
             FaiRecord r{};
-            std::istringstream(line) >> name >> r.len >> r.pos >> r.bases;
+            std::istringstream ls(line);
+            ls >> name >> r.len >> r.pos >> r.bases;
+            if (!ls) throw std::runtime_error("malformed line in " + fasta_fname + ".fai: " + line);
+            if (!(ls >> r.width) || r.width <= r.bases) r.width = r.bases + 1;   /* the reference assumes 1-byte line ends (fastaindex.cpp:285) */
             rec.push_back(r);
         }
     }
@@ -132,7 +247,9 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
     if (hi > lo) {
         const size_t start = rec[lo].pos;
         const FaiRecord& last = rec[hi - 1];
-        const size_t end = last.pos + last.len + (last.bases ? last.len / last.bases : 0) + 1;
+        /* bytes of a record in the file: its bases + the line terminators between them */
+        auto extent = [](const FaiRecord& r) { return r.len + (r.bases ? (r.len - (r.len ? 1 : 0)) / r.bases * (r.width - r.bases) : 0); };
+        const size_t end = last.pos + extent(last);
         /* the rank's byte range: mapped read-only (the encoder threads read the page cache directly); a plain
          * read() into a string is the fallback */
         const char *text = nullptr;
@@ -142,10 +259,19 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
         const int fd = ::open(fasta_fname.c_str(), O_RDONLY);
         if (fd < 0) { delete[] buf; throw std::runtime_error("cannot open FASTA file " + fasta_fname); }
         struct stat st;
-        if (::fstat(fd, &st) == 0 && static_cast<size_t>(st.st_size) > start) {
+        if (::fstat(fd, &st) != 0) { ::close(fd); delete[] buf; throw std::runtime_error("cannot stat FASTA file " + fasta_fname); }
+        /* a stale or truncated index must not send the encoder threads past the end of the file */
+        for (size_t i = lo; i < hi; ++i) {
+            if (rec[i].pos + extent(rec[i]) > static_cast<size_t>(st.st_size)) {
+                ::close(fd); delete[] buf;
+                throw std::runtime_error("FASTA index " + fasta_fname + ".fai does not match the file: record " + std::to_string(i) +
+                                         " ends beyond its " + std::to_string(st.st_size) + " bytes");
+            }
+        }
+        if (end > start) {
             const size_t page = static_cast<size_t>(::sysconf(_SC_PAGESIZE));
             map_skew = start % page;
-            map_len = std::min(end, static_cast<size_t>(st.st_size)) - start + map_skew;
+            map_len = end - start + map_skew;
             map = ::mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, static_cast<off_t>(start - map_skew));
             if (map != MAP_FAILED) {
                 ::madvise(map, map_len, MADV_SEQUENTIAL);
@@ -154,8 +280,12 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
         }
         if (!text) {
             chunk.assign(end - start, '\n');
-            const ssize_t got = ::pread(fd, &chunk[0], chunk.size(), static_cast<off_t>(start));
-            (void)got;
+            size_t got = 0;
+            while (got < chunk.size()) {
+                const ssize_t r = ::pread(fd, &chunk[got], chunk.size() - got, static_cast<off_t>(start + got));
+                if (r <= 0) { ::close(fd); delete[] buf; throw std::runtime_error("short read from FASTA file " + fasta_fname); }
+                got += static_cast<size_t>(r);
+            }
             text = chunk.data();
         }
         ::close(fd);
@@ -166,11 +296,12 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
             const char *src = text + (r.pos - start);
             uint8_t *dst = buf + byteoff[ii];
             const size_t width = r.bases ? r.bases : r.len;   /* characters per FASTA line */
+            const size_t eol = r.bases ? r.width - r.bases : 0; /* bytes of the line terminator (2 for CRLF files) */
             size_t col = 0;
             for (size_t p = 0; p < r.len;) {
                 unsigned byte = 0;
                 for (int j = 0; j < 4 && p < r.len; ++j, ++p) {
-                    if (col == width) { ++src; col = 0; }   /* the newline after every `bases` characters */
+                    if (col == width) { src += eol; col = 0; }   /* the line end after every `bases` characters */
                     byte |= (static_cast<unsigned>(DnaSeq::getcharcode(*src++)) << (6 - 2 * j)) & 0xFFu;
                     ++col;
                 }
@@ -192,6 +323,11 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
     return dna;
 }
 
+void release_gpu_engine()
+{
+    if (g_engine.ctx) { hsk_destroy(g_engine.ctx); g_engine.ctx = nullptr; g_engine.rank = g_engine.nranks = -1; }
+}
+
 std::unique_ptr<KmerListS> kmer_count(const DnaBuffer& mydna, MPI_Comm comm)
 {
     int rank, nranks;
@@ -211,29 +347,20 @@ std::unique_ptr<KmerListS> kmer_count(const DnaBuffer& mydna, MPI_Comm comm)
 
     const size_t n = mydna.size();
     std::vector<uint64_t> lens(n);
+    #pragma omp parallel for schedule(static) if (n > 65536)
     for (size_t i = 0; i < n; ++i) lens[i] = mydna[i].size();
     const uint8_t *bytes = n ? mydna.getbufoffset(0) : nullptr;
     const size_t nbytes = n ? mydna.getrangebufsize(0, n) : 0;
 
+    /* the DnaBuffer bytes go to the GPU as they are (pageable memory: staged by the engine's host threads); the entries
+     * are built from the parts of the result as they arrive, while the GPU is still counting */
     hsk_result res;
-    if (hsk_count(ctx, bytes, nbytes, lens.data(), n, readoffset, &res)) throw std::runtime_error(hsk_last_error());
-
-    auto list = std::make_unique<KmerListS>();
-    list->resize(res.n_kept);
-    constexpr int NW = TKmer::NBYTES / 8;
-#if EXTENSION == 0
-    static_assert(sizeof(KmerListEntryS) == 8 * (NW + 1), "entry layout");
-    if (hsk_fill_entries(ctx, list->data(), res.n_kept)) throw std::runtime_error(hsk_last_error());
-#else
-    #pragma omp parallel for schedule(static)
-    for (size_t i = 0; i < (size_t)res.n_kept; ++i) {
-        KmerListEntryS& e = (*list)[i];
-        e.kmer = TKmer(static_cast<const void *>(res.kmer_words + i * NW));
-        e.cnt = res.cnt[i];
-        e.pos.assign(res.pos + res.occ_off[i], res.pos + res.occ_off[i + 1]);
-        e.rid.assign(res.rid + res.occ_off[i], res.rid + res.occ_off[i + 1]);
-    }
-#endif
+    ListBuilder builder;
+    builder.nthreads = std::max(1, omp_get_max_threads());
+    if (hsk_count_stream(ctx, bytes, nbytes, lens.data(), n, readoffset, &ListBuilder::sink, &builder, &res))
+        throw std::runtime_error(builder.error.empty() ? std::string(hsk_last_error()) : "kmer_count: " + builder.error);
+    if (builder.filled != res.n_kept) throw std::runtime_error("kmer_count: internal: result parts do not add up");
+    auto list = builder.finish();
 
 #if LOG_LEVEL >= 1
     MPI_Barrier(comm);

@@ -34,6 +34,7 @@ int main(int argc, char **argv)
         std::cerr << "hysortk: " << e.what() << std::endl;
         MPI_Abort(MPI_COMM_WORLD, 1);
     }
+    hysortk::release_gpu_engine();
     MPI_Finalize();
     return 0;
 }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HSK_VERSION 1
+#define HSK_VERSION 2
 #define HSK_NCCL_ID_BYTES 128
 #define HSK_MAX_KMER_WORDS 3 /* reference include/kmer.hpp:343-345: K<=32 -> 1, <=64 -> 2, <=95 -> 3 */
 
@@ -128,6 +128,21 @@ void hsk_destroy(hsk_ctx *ctx);
  * of the call. */
 int hsk_count(hsk_ctx *ctx, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
               int32_t readid_base, hsk_result *out);
+
+/* kmer_count on host buffers with the result handed over while it is being produced — what the C++ shim uses to build the
+ * reference's KmerListS (std::vector<KmerListEntryS>, include/kmer.hpp:368-410; reference kmerops.cpp:883-904 copies the
+ * task results into it at the end) while the GPU is still counting.  `sink` is called from one thread of the context, in
+ * entry order, with parts [first_entry, first_entry + n_entries) of the result that have reached the host: `view` has
+ * the hsk_result layout and is indexed with absolute entry / occurrence numbers (pointers valid during the call only);
+ * `total_hint` estimates the final number of entries (exact in the last call).  A non-zero return of the sink stops the
+ * deliveries and makes hsk_count_stream fail.  All calls of the sink have returned when hsk_count_stream returns; *out is
+ * filled as by hsk_count.  `packed` may be pageable memory (a DnaBuffer is a plain heap array, reference
+ * include/dnabuffer.hpp:40): it is then copied through a page-locked staging ring by the context's host threads
+ * (HSK_HOST_THREADS, default: the hardware threads divided by the ranks, at most 8), chunk by chunk under the extraction. */
+typedef int (*hsk_sink_fn)(void *user, const hsk_result *view, uint64_t first_entry, uint64_t n_entries, uint64_t first_occ,
+                           uint64_t n_occ, uint64_t total_hint);
+int hsk_count_stream(hsk_ctx *ctx, const uint8_t *packed, uint64_t nbytes, const uint64_t *read_len, uint64_t nreads,
+                     int32_t readid_base, hsk_sink_fn sink, void *user, hsk_result *out);
 
 /* Same with the reads already resident in HBM: d_packed (nbytes, 16-byte aligned, readable up to
  * nbytes rounded up to 16), d_read_off (nreads+1 byte offsets of the reads, uint64) and d_read_len

@@ -43,6 +43,11 @@ void print_kmer_histogram(const KmerListS& kmerlist, MPI_Comm comm);
 /* Writes "<k-mer>\t<count>" per entry to <output_dir>/<rank>.out.  reference src/hysortk.cpp:138-164 */
 void write_output_file(const KmerListS& kmerlist, const std::string& output_dir, MPI_Comm comm);
 
+/* hysortk_b200 addition (not in the reference): frees the GPU engine of this process — device memory, streams, NCCL
+ * communicator.  Collective over the communicator of the last kmer_count; call it before MPI_Finalize.  Optional: without
+ * it the engine lives until the process exits (it is never torn down from a static destructor). */
+void release_gpu_engine();
+
 } // namespace hysortk
 
 #endif

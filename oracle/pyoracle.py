@@ -247,3 +247,87 @@ def ref_kmer_count(packed: np.ndarray, readlens: np.ndarray, k: int, m: int, low
         return c
     finally:
         L.ref_free(h)
+
+
+# ------------------------------------------------------------- the real reference, several MPI ranks
+
+def _partition(readlens: np.ndarray, nranks: int) -> np.ndarray:
+    """first read of every rank: the reference's greedy contiguous partition by bases
+    (reference src/fastaindex.cpp:52-100)."""
+    lens = np.asarray(readlens, dtype=np.int64)
+    n = len(lens)
+    avg = float(lens.sum()) / nranks
+    first = np.full(nranks + 1, n, dtype=np.int64)
+    rid = 0
+    for p in range(nranks - 1):
+        first[p] = rid
+        sofar = 0
+        if rid < n:
+            while True:
+                sofar += int(lens[rid]); rid += 1
+                if not (rid < n and sofar + int(lens[rid]) < avg):
+                    break
+    first[nranks - 1] = rid
+    return first
+
+
+def ref_kmer_count_ranks(packed: np.ndarray, readlens: np.ndarray, k: int, m: int, lower: int, upper: int, ext: int = 0,
+                         nranks: int = 2, threads_per_rank: int | None = None, want_result: bool = True,
+                         repeats: int = 1, timeout: float = 1800.0):
+    """The reference's kmer_count as an MPI job of `nranks` processes of this node (the bundled multi-process MPI
+    stand-in, hysortk_b200/shim/mpi.h): every rank gets its contiguous share of the reads, like read_dna_buffer
+    would give it.  Returns (Counts of the union over ranks or None, list of per-repeat seconds = max over ranks)."""
+    import json
+    import sys
+    import uuid
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    rl = np.ascontiguousarray(readlens, dtype=np.uint64)
+    first = _partition(rl, nranks)
+    nb = (rl + np.uint64(3)) // np.uint64(4)
+    off = np.zeros(len(rl) + 1, dtype=np.uint64)
+    np.cumsum(nb, out=off[1:])
+    session = "ref" + uuid.uuid4().hex[:12]
+    threads = threads_per_rank or max(1, (os.cpu_count() or 1) // nranks)
+    with tempfile.TemporaryDirectory() as d:
+        procs = []
+        for r in range(nranks):
+            lo, hi = int(first[r]), int(first[r + 1])
+            np.savez(os.path.join(d, f"in{r}.npz"), packed=packed[int(off[lo]):int(off[hi])], readlens=rl[lo:hi])
+            env = dict(os.environ, HSK_MPI_SIZE=str(nranks), HSK_MPI_RANK=str(r), HSK_MPI_SESSION=session,
+                       OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="false", SLURM_TASKS_PER_NODE=str(nranks))
+            cmd = [sys.executable, os.path.join(HERE, "ref_worker.py"), os.path.join(d, f"in{r}.npz"),
+                   os.path.join(d, f"out{r}.npz"), str(k), str(m), str(lower), str(upper), str(ext), str(repeats),
+                   "1" if want_result else "0"]
+            procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = []
+        try:
+            for p in procs:
+                o, e = p.communicate(timeout=timeout)
+                if p.returncode != 0:
+                    raise RuntimeError(f"reference rank failed (rc {p.returncode}):\n{o[-2000:]}\n{e[-2000:]}")
+                outs.append(json.loads(o.strip().splitlines()[-1]))
+        finally:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            try:
+                os.unlink("/dev/shm/hsk_mpi_" + session)
+            except OSError:
+                pass
+        seconds = [max(o["seconds"][i] for o in outs) for i in range(repeats)]
+        if not want_result:
+            return None, seconds
+        nw = 1 if k <= 32 else (2 if k <= 64 else 3)
+        zs = [np.load(os.path.join(d, f"out{r}.npz")) for r in range(nranks)]
+        words = np.concatenate([z["words"].reshape(-1, nw) for z in zs])
+        cnt = np.concatenate([z["cnt"] for z in zs])
+        if ext:
+            offs, shift = [np.zeros(1, dtype=np.uint64)], 0
+            for z in zs:
+                offs.append(z["occ_off"][1:] + np.uint64(shift))
+                shift += int(z["occ_off"][-1])
+            c = canonicalize(k, words, cnt, np.concatenate(offs), np.concatenate([z["pos"] for z in zs]),
+                             np.concatenate([z["rid"] for z in zs]))
+        else:
+            c = canonicalize(k, words, cnt)
+        return c, seconds

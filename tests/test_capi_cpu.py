@@ -23,7 +23,7 @@ def test_library_builds_and_exports_all_symbols():
     assert set(syms) == set(capi.EXPORTS), (syms, capi.EXPORTS)
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in hsk_capi.h but not exported"
-    assert lib.hsk_version() == 1
+    assert lib.hsk_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

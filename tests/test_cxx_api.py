@@ -154,3 +154,26 @@ def test_standalone_cli_matches_reference_output(name, line_width, tmp_path):
     assert "Overall kmer counting (Excluding I/O)" in r.stdout
     lines = sorted(open(outdir / "0.out").read().splitlines())
     assert hashlib.md5("\n".join(lines).encode()).hexdigest() == g["sorted_output_md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["k31_e0_mixed", "k55_e0_mixed", "k31_e1_mixed"])
+def test_cxx_kmer_count_matches_reference_golden(name, tmp_path):
+    """hysortk::kmer_count itself (C++ API over the engine; C entry points hysortk_b200/cxx/bench_api.cpp): pageable
+    DnaBuffer in, std::vector<KmerListEntryS> out — entries incl. the per-entry pos / rid vectors of EXTENSION == 1, the
+    histogram text and the output file equal the unmodified reference's (tests/golden)."""
+    from conftest import load_golden
+    from hysortk_b200 import cxxapi
+    g = load_golden(name)
+    a = cxxapi.kmer_count(g["packed"], g["readlens"], g["k"], g["m"], g["lower"], g["upper"], g["ext"], want_text_dir=str(tmp_path))
+    got = po.canonicalize(g["k"], a["words"], a["cnt"], a.get("occ_off"), a.get("pos"), a.get("rid"))
+    po.assert_equal(got, g["expected"], "C++ API vs reference golden")
+    assert a["n"] == g["expected"].n
+    assert open(tmp_path / "hist.txt").read() == g["histogram_text"]
+    lines = sorted(open(tmp_path / "0.out").read().splitlines())
+    assert hashlib.md5("\n".join(lines).encode()).hexdigest() == g["sorted_output_md5"]
+    # a second call on the same engine, and a larger input (several result parts, list grown from the hint)
+    rs = synth.sample_fixed(500_000, 12.0, 2500, 0.01, seed=6)
+    exp = po.kmer_count(rs.packed, rs.readlens, g["k"], g["m"], g["lower"], g["upper"], g["ext"], via_supermers=False)
+    b = cxxapi.kmer_count(rs.packed, rs.readlens, g["k"], g["m"], g["lower"], g["upper"], g["ext"])
+    po.assert_equal(po.canonicalize(g["k"], b["words"], b["cnt"], b.get("occ_off"), b.get("pos"), b.get("rid")), exp, "C++ API vs oracle")

@@ -273,3 +273,99 @@ def test_read_table_many_short_and_empty_reads():
         c, raw = gpu_counts(ctx, rs.packed, rs.readlens)
         po.assert_equal(c, exp, "short and empty reads")
         assert raw["stats"]["n_kmers_local"] == rs.num_kmers(k)
+
+
+@pytest.mark.parametrize("k,m,ext", [(31, 17, 0), (31, 17, 1), (55, 23, 0)])
+def test_count_stream_parts_and_input_memory(k, m, ext, monkeypatch):
+    """hsk_count_stream hands the result to a sink part by part while the kernel runs: the parts are contiguous, in
+    order, their concatenation equals hsk_count's result and the oracle's; page-locked and pageable input (staged
+    through the ring of page-locked buffers by the context's host threads) give the same result."""
+    import torch
+    rs = synth.sample_fixed(800_000, 10.0, 3000, 0.01, seed=31 + k + ext)
+    exp = po.kmer_count(rs.packed, rs.readlens, k, m, 2, 50, ext, via_supermers=False)
+    monkeypatch.setenv("HSK_GROUPS", "9")
+    with capi.Context(k, m, 2, 50, ext) as ctx:
+        base = ctx.count(rs.packed, rs.readlens)                      # pageable numpy memory
+        s = ctx.count_stream(rs.packed, rs.readlens)
+        firsts = [p[0] for p in s["parts"]]
+        ns = [p[1] for p in s["parts"]]
+        assert firsts == list(np.cumsum([0] + ns[:-1])) and sum(ns) == base["n_kept"] and len(ns) >= 2
+        assert s["parts"][-1][2] == base["n_kept"]                   # the last hint is exact
+        assert np.array_equal(s["words"], base["words"]) and np.array_equal(s["cnt"], base["cnt"])
+        if ext:
+            assert np.array_equal(s["occ_off"], base["occ_off"])
+            assert np.array_equal(s["pos"], base["pos"]) and np.array_equal(s["rid"], base["rid"])
+        po.assert_equal(po.canonicalize(k, s["words"], s["cnt"], s.get("occ_off"), s.get("pos"), s.get("rid")), exp, "stream vs oracle")
+        # page-locked input goes up from where it is
+        hp = torch.from_numpy(rs.packed).pin_memory()
+        hl = torch.from_numpy(rs.readlens.view(np.int64)).pin_memory()
+        r = capi.Result()
+        capi._check(ctx.lib.hsk_count(ctx.handle, hp.data_ptr(), rs.packed.nbytes, hl.data_ptr(), rs.nreads, 0, capi.C.byref(r)))
+        pinned = ctx._unpack(r)
+        assert np.array_equal(pinned["words"], base["words"]) and np.array_equal(pinned["cnt"], base["cnt"])
+    # many small chunks through the staging ring: a 40 MB buffer is cut into 2 MB pieces
+    rs2 = synth.sample_fixed(4_000_000, 10.0, 10_000, 0.005, seed=77)
+    with capi.Context(31, 17, 2, 50, 0) as ctx:
+        a = ctx.count(rs2.packed, rs2.readlens)
+        hp = torch.from_numpy(rs2.packed).pin_memory()
+        hl = torch.from_numpy(rs2.readlens.view(np.int64)).pin_memory()
+        r = capi.Result()
+        capi._check(ctx.lib.hsk_count(ctx.handle, hp.data_ptr(), rs2.packed.nbytes, hl.data_ptr(), rs2.nreads, 0, capi.C.byref(r)))
+        b = ctx._unpack(r)
+        assert a["n_kept"] == b["n_kept"] and np.array_equal(a["words"], b["words"]) and np.array_equal(a["cnt"], b["cnt"])
+        assert int(a["stats"]["n_kmers_local"]) == rs2.num_kmers(31)
+
+
+def test_arena_limits(monkeypatch):
+    """Memory planning (engine.cu: count_device): when the arena is cut to what fits, a result that fits is unchanged, bins
+    that find no room in the staging area take the HBM path, and a result that does not fit is an error, not a
+    corrupted arena."""
+    k, m = 31, 17
+    rs = synth.sample_fixed(300_000, 12.0, 2000, 0.002, seed=8)
+    exp = po.kmer_count(rs.packed, rs.readlens, k, m, 1, 65535, 0, via_supermers=False)
+    # LOWER = 1 and few bins: every bin keeps more k-mers than a CTA sorts itself (staging area + big gather)
+    with capi.Context(k, m, 1, 65535, 0, buckets_per_rank=128) as ctx:
+        c, raw = gpu_counts(ctx, rs.packed, rs.readlens)
+        po.assert_equal(c, exp, "big bins, roomy arena")
+        assert raw["stats"]["n_overflow_bins"] == 0
+    # 8 MB: arena of ~590 K entries (the result has ~320 K), staging area of ~74 K entries: most bins find it full
+    monkeypatch.setenv("HSK_ARENA_BUDGET_MB", "8")
+    with capi.Context(k, m, 1, 65535, 0, buckets_per_rank=128) as ctx:
+        c, raw = gpu_counts(ctx, rs.packed, rs.readlens)
+        po.assert_equal(c, exp, "big bins, staging area exhausted -> HBM path")
+        assert raw["stats"]["n_overflow_bins"] > 0
+        c2, _ = gpu_counts(ctx, rs.packed, rs.readlens)
+        po.assert_equal(c2, exp, "second call")
+    # EXTENSION with a tight budget
+    exp1 = po.kmer_count(rs.packed, rs.readlens, k, m, 2, 50, 1, via_supermers=False)
+    monkeypatch.setenv("HSK_ARENA_BUDGET_MB", "64")
+    with capi.Context(k, m, 2, 50, 1) as ctx:
+        c, _ = gpu_counts(ctx, rs.packed, rs.readlens)
+        po.assert_equal(c, exp1, "EXT, capped arena")
+    # 1 MB: the arena cannot hold the result
+    monkeypatch.setenv("HSK_ARENA_BUDGET_MB", "1")
+    with capi.Context(k, m, 1, 65535, 0) as ctx:
+        with pytest.raises(capi.HskError, match="does not fit"):
+            ctx.count(rs.packed, rs.readlens)
+        monkeypatch.delenv("HSK_ARENA_BUDGET_MB")
+        c, _ = gpu_counts(ctx, rs.packed, rs.readlens)               # the context is usable afterwards
+        po.assert_equal(c, exp, "after the error")
+
+
+def test_heavy_bin_poly_a():
+    """One minimizer bin far above the others (the reference pre-counts such tasks, kmerops.cpp:1157-1199): 60 Mbp of
+    poly-A among ordinary reads.  The bin is counted on chip by one CTA (one distinct k-mer), its total exceeds 2^24
+    supermer slots only at larger sizes — here the per-bin totals are checked against pass A's independent totals."""
+    k, m = 31, 17
+    rs = synth.sample_fixed(200_000, 8.0, 2000, 0.01, seed=4)
+    polya = np.zeros((6000, 2500), dtype=np.uint8)   # 6000 reads x 10 000 A
+    reads_packed = np.concatenate([rs.packed, polya.reshape(-1)])
+    lens = np.concatenate([rs.readlens, np.full(6000, 10_000, dtype=np.uint64)])
+    with capi.Context(k, m, 2, 65535, 0) as ctx:
+        r = ctx.count(reads_packed, lens)
+        assert r["stats"]["n_kmers_local"] == rs.num_kmers(k) + 6000 * (10_000 - k + 1)
+        exp = po.kmer_count(rs.packed, rs.readlens, k, m, 2, 65535, 0, via_supermers=False)
+        got = po.canonicalize(k, r["words"], r["cnt"])
+        # AAAA...A occurs ~6e7 times: above UPPER, dropped; everything else as without the poly-A reads (a genomic
+        # poly-A k-mer would have been counted with them, a uniform 200 kbp genome has none)
+        po.assert_equal(got, exp, "poly-A poisoned input")
