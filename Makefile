@@ -39,8 +39,11 @@ endif
 CXXFLAGS=$(OPT) -std=c++17 -fPIC -fopenmp -pthread -Wall $(PARAMS) -I./include $(MPI_INC)
 NVFLAGS=-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 
+# the CUDA engine does not depend on K/M/L/U/EXT (they reach it at run time): CUOBJ=<dir> lets several configurations share
+# one set of engine objects
+CUOBJ?=$(OBJ)
 HOST_OBJ=$(OBJ)/hysortk.o $(OBJ)/dnaseq.o $(OBJ)/dnabuffer.o $(OBJ)/hashfuncs.o
-CUDA_OBJ=$(OBJ)/reads.o $(OBJ)/extract.o $(OBJ)/expand.o $(OBJ)/radix.o $(OBJ)/count.o $(OBJ)/bins.o $(OBJ)/engine.o
+CUDA_OBJ=$(CUOBJ)/reads.o $(CUOBJ)/extract.o $(CUOBJ)/expand.o $(CUOBJ)/radix.o $(CUOBJ)/count.o $(CUOBJ)/bins.o $(CUOBJ)/engine.o
 
 all: print lib
 
@@ -57,8 +60,8 @@ $(OBJ)/%.o: hysortk_b200/cxx/%.cpp include/*.hpp include/*.h
 	@mkdir -p $(OBJ)
 	$(CXX) $(CXXFLAGS) -c -o $@ $<
 
-$(OBJ)/%.o: hysortk_b200/csrc/%.cu hysortk_b200/csrc/*.cuh include/hsk_capi.h
-	@mkdir -p $(OBJ)
+$(CUOBJ)/%.o: hysortk_b200/csrc/%.cu hysortk_b200/csrc/*.cuh include/hsk_capi.h
+	@mkdir -p $(CUOBJ)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
 standalone: all

@@ -173,43 +173,46 @@ class Context:
 
     def count_stream(self, packed: np.ndarray, readlens: np.ndarray, readid_base: int = 0) -> dict:
         """hsk_count_stream: the result is collected part by part by a sink (a Python callback, called from the
-        context's delivery thread) while the GPU is still counting; returns the concatenated parts like count()
-        plus `parts` = the (first_entry, n_entries, total_hint) of every delivery."""
+        context's delivery threads, in any order) while the GPU is still counting; returns the parts put together like
+        count() plus `parts` = the (first_entry, n_entries, total_hint) of every delivery, in arrival order."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         readlens = np.ascontiguousarray(readlens, dtype=np.uint64)
         nw = self.nwords
-        got = dict(words=[], cnt=[], occ_n=[], pos=[], rid=[], parts=[])
+        got = []
+        order = []
 
         def sink(user, view, first, n, first_occ, n_occ, hint):
             v = view.contents
-            got["parts"].append((int(first), int(n), int(hint)))
+            order.append((int(first), int(n), int(hint)))
             if n:
+                part = dict(first=int(first))
                 w = np.ctypeslib.as_array(v.kmer_words, shape=(int(first + n) * nw,))[int(first) * nw:].copy()
-                got["words"].append(w.reshape(int(n), nw))
-                got["cnt"].append(np.ctypeslib.as_array(v.cnt, shape=(int(first + n),))[int(first):].copy())
+                part["words"] = w.reshape(int(n), nw)
+                part["cnt"] = np.ctypeslib.as_array(v.cnt, shape=(int(first + n),))[int(first):].copy()
                 if self.ext:
                     off = np.ctypeslib.as_array(v.occ_off, shape=(int(first + n),))[int(first):].astype(np.uint64)
                     ends = np.concatenate([off[1:], np.array([first_occ + n_occ], dtype=np.uint64)])
-                    got["occ_n"].append(ends - off)
-                    if n_occ:
-                        got["pos"].append(np.ctypeslib.as_array(v.pos, shape=(int(first_occ + n_occ),))[int(first_occ):].copy())
-                        got["rid"].append(np.ctypeslib.as_array(v.rid, shape=(int(first_occ + n_occ),))[int(first_occ):].copy())
+                    part["occ_n"] = ends - off
+                    part["pos"] = np.ctypeslib.as_array(v.pos, shape=(int(first_occ + n_occ),))[int(first_occ):].copy() if n_occ else np.zeros(0, np.uint32)
+                    part["rid"] = np.ctypeslib.as_array(v.rid, shape=(int(first_occ + n_occ),))[int(first_occ):].copy() if n_occ else np.zeros(0, np.int32)
+                got.append(part)
             return 0
 
         cb = SINK_FN(sink)
         r = Result()
         _check(self.lib.hsk_count_stream(self.handle, packed.ctypes.data, packed.nbytes, readlens.ctypes.data, len(readlens),
                                          readid_base, C.cast(cb, C.c_void_p), None, C.byref(r)))
+        got.sort(key=lambda p: p["first"])
         n = int(r.n_kept)
-        out = dict(nwords=nw, n_kept=n, n_occ=int(r.n_occ), parts=got["parts"],
-                   words=np.concatenate(got["words"]) if got["words"] else np.zeros((0, nw), np.uint64),
-                   cnt=np.concatenate(got["cnt"]) if got["cnt"] else np.zeros(0, np.uint32),
+        out = dict(nwords=nw, n_kept=n, n_occ=int(r.n_occ), parts=order,
+                   words=np.concatenate([p["words"] for p in got]) if got else np.zeros((0, nw), np.uint64),
+                   cnt=np.concatenate([p["cnt"] for p in got]) if got else np.zeros(0, np.uint32),
                    histogram=_arr(r.histogram, self.upper + 1, np.uint64), stats=r.stats.as_dict())
         if self.ext:
-            occ_n = np.concatenate(got["occ_n"]) if got["occ_n"] else np.zeros(0, np.uint64)
+            occ_n = np.concatenate([p["occ_n"] for p in got]) if got else np.zeros(0, np.uint64)
             out["occ_off"] = np.concatenate([np.zeros(1, np.uint64), np.cumsum(occ_n, dtype=np.uint64)])
-            out["pos"] = np.concatenate(got["pos"]) if got["pos"] else np.zeros(0, np.uint32)
-            out["rid"] = np.concatenate(got["rid"]) if got["rid"] else np.zeros(0, np.int32)
+            out["pos"] = np.concatenate([p["pos"] for p in got]) if got else np.zeros(0, np.uint32)
+            out["rid"] = np.concatenate([p["rid"] for p in got]) if got else np.zeros(0, np.int32)
         return out
 
     def count_device(self, d_packed: int, nbytes: int, d_read_off: int, d_read_len: int, nreads: int,

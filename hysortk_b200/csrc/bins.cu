@@ -59,32 +59,43 @@ struct BinCfg {
     static constexpr int SW = (NW == 1 ? 4 : 8) + (EXT ? 4 : 0);
     static constexpr int PW = SW - (EXT ? 2 : 0);
     // table slots: K <= 32: 8192 (two CTAs per SM), with EXTENSION 4096 (three CTAs); K > 32: one CTA per SM
-    static constexpr int TS_BITS = NW == 1 ? (EXT ? 12 : 13) : (NW == 2 && !EXT ? 13 : 12);
+    static constexpr int TS_BITS = NW == 1 ? (EXT || TH < 512 ? 12 : 13) : (NW == 2 && !EXT ? 13 : 12);
     static constexpr int TS = 1 << TS_BITS;
     static constexpr int SLOTS_PT = TS / TH;
-    static constexpr int CTAS = NW == 1 ? (EXT ? 3 : 2) : 1;
+    static constexpr int CTAS = NW == 1 ? (EXT ? 3 : (TH < 512 ? 4 : 2)) : 1;
     // most k-mers one slot can hold (smallest K of the word count) = rounds of 32 k-mers a batch of 32 slots can need
     static constexpr int NMAX = 16 * (PW - 1) + 12 - (NW == 1 ? 3 : (NW == 2 ? 33 : 65)) + 1;
     // slots per walk batch (a warp stages them) and kept k-mers a CTA sorts itself; a bin that keeps more goes through
     // the staging area + big gather
-    static constexpr int BATCH = TH > 512 ? 16 : 32;
-    static constexpr int SORTCAP = 1024;
+    static constexpr int BATCH = TH != 512 ? 16 : 32;
+    static constexpr int SORTCAP = TH < 512 ? BN_SORTCAP / 2 : BN_SORTCAP;
     static constexpr int EPT = SORTCAP / TH;   // kept k-mers per thread in the sort
     static constexpr int HEADW = ((BATCH * NMAX + 31) / 32 + 3) / 4 * 4;   // rounds of 32 k-mers a batch can need
-    static constexpr int TARGET = NW == 1 ? (EXT ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
+    static constexpr int TARGET = NW == 1 ? (EXT || TH < 512 ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
     // de-duplication of the supermers of a bin (K <= 64 without EXTENSION): cells of the supermer table, most slots of
     // a bin that goes through it (a multiple of TH, below the number of cells)
     static constexpr int DDTS = TH > 512 ? 4096 : 2048;
     static constexpr int DDLIMIT = TH > 512 ? 2048 : 1536;
     static constexpr int DDPT = DDLIMIT / TH;
     static_assert(DDLIMIT <= BN_DDLIMIT_MAX && DDLIMIT % TH == 0 && DDLIMIT < DDTS && DDTS % TH == 0, "supermer table geometry");
-    static_assert(SORTCAP % TH == 0 && SORTCAP <= BN_CAND, "sort geometry");
+    static_assert(SORTCAP % TH == 0 && SORTCAP <= TS, "sort geometry");
 };
 
-size_t bin_dedup_scratch_bytes(int sm_count, int slot_words) { return (size_t)sm_count * 2 * BN_DDLIMIT_MAX * ((size_t)slot_words * 4 + sizeof(u32)); }
+size_t bin_pending_scratch_bytes(int sm_count, int nwords) { return (size_t)sm_count * BN_MAX_CTAS * BN_SORTCAP * ((size_t)nwords * 8 + 4); }
+size_t bin_dedup_scratch_bytes(int sm_count, int slot_words) { return (size_t)sm_count * BN_MAX_CTAS * BN_DDLIMIT_MAX * ((size_t)slot_words * 4 + sizeof(u32)); }
+
+// threads per CTA of the kernels that come in two shapes (HSK_BIN_THREADS): K <= 32 without EXTENSION: 512 (two CTAs per SM,
+// 8192-slot tables) or 256 (four CTAs, 4096-slot tables, bins half as large); K in 33..64: 1024 or 512 (one CTA per SM)
+static int bin_threads_env(int dflt, int other)
+{
+    const char *e = getenv("HSK_BIN_THREADS");
+    const int t = e ? atoi(e) : dflt;
+    return t == other ? other : dflt;
+}
 
 int bin_target_kmers(int nwords, bool ext)
 {
+    if (nwords == 1 && !ext && bin_threads_env(512, 256) == 256) return BinCfg<1, false, 256>::TARGET;
     if (nwords == 1) return ext ? BinCfg<1, true, 512>::TARGET : BinCfg<1, false, 512>::TARGET;
     if (nwords == 2) return ext ? BinCfg<2, true, 512>::TARGET : BinCfg<2, false, 512>::TARGET;
     return BinCfg<3, false, 512>::TARGET;
@@ -97,7 +108,7 @@ struct BinScratchCfg {
     using Cfg = BinCfg<NW, EXT, TH>;
     static constexpr int STG_U4 = Cfg::BATCH * Cfg::SW / 4 + 2;                       // uint4 per warp (+ pad)
     static constexpr size_t WALK = (size_t)Cfg::WARPS * (STG_U4 * 16 + 32 * 2 + Cfg::HEADW * 4);
-    static constexpr size_t SORT = (size_t)Cfg::SORTCAP * (8 * NW + 4) + 264 * 4;
+    static constexpr size_t SORT = (size_t)Cfg::SORTCAP * 4 + 264 * 4;
     static constexpr size_t BYTES = ((WALK > SORT ? WALK : SORT) + 15) / 16 * 16;
 };
 
@@ -111,13 +122,14 @@ struct BinSmem {
     alignas(16) u32 cnt[Cfg::TS];                           // occurrences per slot; EXT pass 2: next occurrence offset
     alignas(16) unsigned char scratch[Scr::BYTES];
     u32 hist[BN_HCAP];
-    u16 cand[BN_CAND];                                      // slots whose counter reached LOWER; then the kept slots
+    u16 cand[BN_CAND];                                      // slots whose counter reached LOWER
     const u32 *src_ptr[BN_MAX_SRC];                         // first slot of the bin in every source stream
     u32 src_n[BN_MAX_SRC], src_sbase[BN_MAX_SRC + 1];
     u32 wa[Cfg::WARPS], wb[Cfg::WARPS];
     u64 base_k, base_o;                                     // where the bin's entries / occurrences go
     u32 *occ_pos; int *occ_rid;                             // EXT pass 2 target arrays (arena, or staging for big bins)
     u32 bin, nk, S, bail, next_batch, seen, ncand, skip_out;
+    u32 pend_valid, pend_lb, pend_tk;                       // a sorted bin waiting in the CTA's global scratch for its place in the arena
     u32 xor_hi, xor_lo;                                     // bits in which the kept k-mers' first words differ
     u32 batch_slots;                                        // slots per walk batch: 32, fewer when the bin has few slots
     int nsrc;                                               // sources of the walk: P.nsrc, or 1 when the bin was de-duplicated
@@ -130,10 +142,10 @@ struct BinSmem {
     {
         return reinterpret_cast<u32 *>(scratch + (size_t)Cfg::WARPS * (Scr::STG_U4 * 16 + 64)) + (size_t)warp * Cfg::HEADW;
     }
-    // sort layout
-    __device__ u64 *xkey() { return reinterpret_cast<u64 *>(scratch); }                                   // [NW][SORTCAP]
-    __device__ u32 *ypay() { return reinterpret_cast<u32 *>(scratch + (size_t)Cfg::SORTCAP * 8 * NW); }   // [SORTCAP]
-    __device__ u32 *bh() { return ypay() + Cfg::SORTCAP; }                                                // [257]
+    // sort layout: kept slots (then the same slots in sorted order), slots in bucket order, bucket starts
+    __device__ u16 *klist() { return reinterpret_cast<u16 *>(scratch); }                                   // [SORTCAP]
+    __device__ u16 *xslot() { return reinterpret_cast<u16 *>(scratch) + Cfg::SORTCAP; }                    // [SORTCAP]
+    __device__ u32 *bh() { return reinterpret_cast<u32 *>(scratch + (size_t)Cfg::SORTCAP * 4); }           // [257]
 };
 
 // block-wide exclusive scan of two u32 values (TH threads); returns exclusive prefixes and totals
@@ -536,65 +548,60 @@ __device__ __forceinline__ void resolve_position(BinSmem<NW, EXT, TH> &sm, const
 }
 
 // ---- the sort of a bin: the kept k-mers in ascending order ------------------------------------------------
-// The kept slots of the bin are listed in sm.cand[0 .. tk), tk <= SORTCAP.  Their k-mers are distinct, so the place of a
-// k-mer in the sorted bin is the number of smaller ones.  One counting pass over the most significant byte in which
+// The kept slots of the bin are listed in sm.klist()[0 .. tk), tk <= SORTCAP.  Their k-mers are distinct, so the place of
+// a k-mer in the sorted bin is the number of smaller ones.  One counting pass over the most significant byte in which
 // the k-mers differ at all (first word) splits them into 256 buckets in ascending order; inside its bucket (a handful
-// of k-mers) every k-mer counts the smaller ones directly.  Six barriers and ~tk / 256 comparisons per k-mer, against
-// the 45 compare-exchange stages of a bitonic network over 512 elements.
-// Then every one gets its place in the arena: (k-mer, count[, occurrence offset]) are written in order; EXTENSION leaves
-// the occurrence cursors in sm.cnt.
+// of k-mers) every k-mer counts the smaller ones directly.  Five barriers and ~tk / 256 comparisons per k-mer, against
+// the 45 compare-exchange stages of a bitonic network over 512 elements.  Only slot numbers move: the k-mers stay in
+// the table.  Result: sm.klist()[e] = slot of the e-th smallest kept k-mer.
 template <int NW, bool EXT, int TH>
-__device__ __forceinline__ void sort_emit(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
+__device__ __forceinline__ u64 slot_key0(const BinSmem<NW, EXT, TH> &sm, u32 slot) { return NW == 1 ? sm.fp[slot] : sm.kw[0][slot]; }
+
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ void sort_bin(BinSmem<NW, EXT, TH> &sm, u32 tk)
 {
     using Cfg = BinCfg<NW, EXT, TH>;
-    constexpr int EPT = Cfg::EPT, CAP = Cfg::SORTCAP;
+    constexpr int EPT = Cfg::EPT;
     const u32 tid = threadIdx.x, lane = tid & 31;
-    if (tk == 0) { resolve_position(sm, P, lb, 0u, 0u); return; }
     u32 *bh = sm.bh();
-    u64 *xkey = sm.xkey();
-    u32 *ypay = sm.ypay();
+    u16 *klist = sm.klist(), *xslot = sm.xslot();
     for (u32 i = tid; i < 257; i += TH) bh[i] = 0;
-    u64 key[EPT][NW];
-    u32 pay[EPT];   // slot << 16 | count (count <= UPPER <= 65535)
-    const u32 s0 = sm.cand[0];
-    const u64 k0 = NW == 1 ? sm.fp[s0] : sm.kw[0][s0];
+    u32 slot[EPT];
+    const u64 k0 = slot_key0(sm, klist[0]);
     u64 x = 0;
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
         const u32 e = tid + r * TH;
-        if (e < tk) {
-            const u32 slot = sm.cand[e];
-#pragma unroll
-            for (int l = 0; l < NW; ++l) key[r][l] = NW == 1 ? sm.fp[slot] : sm.kw[l][slot];
-            pay[r] = (slot << 16) | sm.cnt[slot];
-            x |= key[r][0] ^ k0;
-        }
+        slot[r] = e < tk ? klist[e] : 0u;
+        if (e < tk) x |= slot_key0(sm, slot[r]) ^ k0;
     }
     {
         const u32 xh = __reduce_or_sync(0xFFFFFFFFu, (u32)(x >> 32)), xl = __reduce_or_sync(0xFFFFFFFFu, (u32)x);
         if (lane == 0) { if (xh) atomicOr(&sm.xor_hi, xh); if (xl) atomicOr(&sm.xor_lo, xl); }
     }
-    __syncthreads();
+    __syncthreads();   // the slot list has been read, the bucket counters are zero
     const u64 diff = ((u64)sm.xor_hi << 32) | sm.xor_lo;
     const int top = diff ? 63 - __clzll((long long)diff) : 7;   // highest bit in which two of the k-mers differ
     const int shift = top > 7 ? top - 7 : 0;
-    u32 bp[EPT];
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
-        if (tid + r * TH < tk) bp[r] = atomicAdd(&bh[(u32)(key[r][0] >> shift) & 255u], 1u);
+        if (tid + r * TH < tk) {
+            const u32 b = (u32)(slot_key0(sm, slot[r]) >> shift) & 255u;
+            slot[r] |= atomicAdd(&bh[b], 1u) << 16;   // place inside the bucket (< SORTCAP <= 65535)
+        }
     }
     __syncthreads();
     if (tid < 32) {   // exclusive scan of the 256 bucket sizes; bh[256] = tk
-        u32 v[8], s = 0;
+        u32 v[8], sum = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { v[i] = bh[tid * 8 + i]; s += v[i]; }
-        u32 inc = s;
+        for (int i = 0; i < 8; ++i) { v[i] = bh[tid * 8 + i]; sum += v[i]; }
+        u32 inc = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
             if (lane >= d) inc += t;
         }
-        u32 ex = inc - s;
+        u32 ex = inc - sum;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { bh[tid * 8 + i] = ex; ex += v[i]; }
         if (tid == 31) bh[256] = ex;
@@ -603,30 +610,46 @@ __device__ __forceinline__ void sort_emit(BinSmem<NW, EXT, TH> &sm, const BinPar
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
         if (tid + r * TH < tk) {
-            const u32 idx = bh[(u32)(key[r][0] >> shift) & 255u] + bp[r];
-#pragma unroll
-            for (int l = 0; l < NW; ++l) xkey[(size_t)l * CAP + idx] = key[r][l];
+            const u32 sl = slot[r] & 0xFFFFu;
+            const u32 b = (u32)(slot_key0(sm, sl) >> shift) & 255u;
+            xslot[bh[b] + (slot[r] >> 16)] = (u16)sl;
         }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
         if (tid + r * TH < tk) {
-            const u32 b = (u32)(key[r][0] >> shift) & 255u;
+            const u32 sl = slot[r] & 0xFFFFu;
+            u64 key[NW];
+#pragma unroll
+            for (int l = 0; l < NW; ++l) key[l] = NW == 1 ? sm.fp[sl] : sm.kw[l][sl];
+            const u32 b = (u32)(key[0] >> shift) & 255u;
             const u32 lo = bh[b], hi = bh[b + 1];
             u32 rank = lo;
             for (u32 j = lo; j < hi; ++j) {
+                const u32 os = xslot[j];
                 u64 o[NW];
 #pragma unroll
-                for (int l = 0; l < NW; ++l) o[l] = xkey[(size_t)l * CAP + j];
-                rank += key_less<NW>(o, key[r]) ? 1u : 0u;
+                for (int l = 0; l < NW; ++l) o[l] = NW == 1 ? sm.fp[os] : sm.kw[l][os];
+                rank += key_less<NW>(o, key) ? 1u : 0u;
             }
-            ypay[rank] = pay[r];
+            klist[rank] = (u16)sl;
         }
     }
     __syncthreads();
-    // from here on a thread handles the sorted positions tid, tid + TH, ...
-    u32 off[EPT];
+}
+
+// Sorted bin -> arena, at once (EXTENSION, where the occurrence pass needs the table of this bin: the look-back over the
+// bins before it may have to wait for them): every entry gets its place, (k-mer, count, occurrence offset) are written in
+// order and the occurrence cursors are left in sm.cnt.
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ void emit_now(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 lb, u32 tk, u32 to)
+{
+    using Cfg = BinCfg<NW, EXT, TH>;
+    constexpr int EPT = Cfg::EPT;
+    const u32 tid = threadIdx.x;
+    const u16 *klist = sm.klist();
+    u32 off[EPT], cnt[EPT];
     if (EXT) {
         // occurrence lists follow the sorted order: offsets inside the bin, left in the slots' counters as cursors
         u32 carry = 0;
@@ -634,14 +657,22 @@ __device__ __forceinline__ void sort_emit(BinSmem<NW, EXT, TH> &sm, const BinPar
         for (int r = 0; r < EPT; ++r) {
             if ((u32)(r * TH) < tk) {
                 const u32 e = tid + r * TH;
-                const u32 c = e < tk ? (ypay[e] & 0xFFFFu) : 0u;
+                cnt[r] = e < tk ? sm.cnt[klist[e]] : 0u;
                 u32 ex, d0, t0, t1;
-                block_scan2<TH>(c, 0u, sm.wa, sm.wb, ex, d0, t0, t1);
+                block_scan2<TH>(cnt[r], 0u, sm.wa, sm.wb, ex, d0, t0, t1);
                 off[r] = carry + ex;
                 carry += t0;
-                if (e < tk) sm.cnt[ypay[e] >> 16] = off[r];
             }
         }
+        __syncthreads();   // every count has been read: the counters become cursors
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const u32 e = tid + r * TH;
+            if (e < tk) sm.cnt[klist[e]] = off[r];
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) { const u32 e = tid + r * TH; cnt[r] = e < tk ? sm.cnt[klist[e]] : 0u; }
     }
     resolve_position(sm, P, lb, tk, to);
     if (sm.skip_out) return;
@@ -650,7 +681,7 @@ __device__ __forceinline__ void sort_emit(BinSmem<NW, EXT, TH> &sm, const BinPar
     for (int r = 0; r < EPT; ++r) {
         const u32 e = tid + r * TH;
         if (e < tk) {
-            const u32 p = ypay[e], slot = p >> 16, c = p & 0xFFFFu;
+            const u32 slot = klist[e], c = cnt[r];
 #pragma unroll
             for (int l = 0; l < NW; ++l) P.out_words[(bk + e) * NW + l] = NW == 1 ? sm.fp[slot] : sm.kw[l][slot];
             P.out_cnt[bk + e] = c;
@@ -658,6 +689,62 @@ __device__ __forceinline__ void sort_emit(BinSmem<NW, EXT, TH> &sm, const BinPar
             if (c < (u32)BN_HCAP) atomicAdd(&sm.hist[c], 1u); else atomicAdd(&P.histogram[c], 1ull);
         }
     }
+}
+
+// Sorted bin -> the CTA's scratch in global memory (L2).  Its place in the arena is resolved while the CTA works on its
+// next bin (flush_pending): by then the bins before it have published how many entries they keep, so the look-back finds
+// every one of them without waiting — emitting at once makes every CTA wait for the slowest of the bins in flight.
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ void stash_bin(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 lb, u32 tk)
+{
+    using Cfg = BinCfg<NW, EXT, TH>;
+    const u32 tid = threadIdx.x;
+    const u16 *klist = sm.klist();
+    u64 *pw = P.pend_words + (size_t)blockIdx.x * BN_SORTCAP * NW;
+    u32 *pc = P.pend_cnt + (size_t)blockIdx.x * BN_SORTCAP;
+    for (u32 e = tid; e < tk; e += TH) {
+        const u32 slot = klist[e], c = sm.cnt[slot];
+#pragma unroll
+        for (int l = 0; l < NW; ++l) __stcg(&pw[(size_t)e * NW + l], NW == 1 ? sm.fp[slot] : sm.kw[l][slot]);
+        __stcg(&pc[e], c);
+        if (c < (u32)BN_HCAP) atomicAdd(&sm.hist[c], 1u); else atomicAdd(&P.histogram[c], 1ull);
+    }
+    if (tid == 0) { sm.pend_valid = 1; sm.pend_lb = lb; sm.pend_tk = tk; }
+}
+
+// "bin lb is in the arena": group bookkeeping for the host that streams the result out (one thread)
+__device__ __forceinline__ void bin_done(const BinParams &P, u32 lb)
+{
+    __threadfence();
+    const u32 g = lb / P.group_bins;
+    const u32 gsize = min(P.group_bins, P.nbins - g * P.group_bins);
+    if (atomicAdd(&P.grp_done[g], 1u) + 1 == gsize && P.snap) {
+        __threadfence();
+        volatile u64 *sn = P.snap + 4 * (size_t)g;
+        sn[0] = P.grp_end[2 * g]; sn[1] = P.grp_end[2 * g + 1]; sn[2] = P.grp_big[g];
+        __threadfence_system();
+        sn[3] = 1;
+    }
+}
+
+// the stashed bin of this CTA, if any: look-back, copy to the arena, bookkeeping.  Called by all threads between two
+// barriers of the bin loop (sm.base_k / base_o / skip_out are not in use there).
+template <int NW, bool EXT, int TH>
+__device__ __forceinline__ void flush_pending(BinSmem<NW, EXT, TH> &sm, const BinParams &P)
+{
+    using Cfg = BinCfg<NW, EXT, TH>;
+    if (!sm.pend_valid) return;
+    const u32 tid = threadIdx.x, lb = sm.pend_lb, tk = sm.pend_tk;
+    resolve_position(sm, P, lb, tk, 0u);
+    if (!sm.skip_out) {
+        const u64 bk = sm.base_k;
+        const u64 *pw = P.pend_words + (size_t)blockIdx.x * BN_SORTCAP * NW;
+        const u32 *pc = P.pend_cnt + (size_t)blockIdx.x * BN_SORTCAP;
+        for (u32 i = tid; i < tk * NW; i += TH) P.out_words[bk * NW + i] = __ldcg(pw + i);
+        for (u32 e = tid; e < tk; e += TH) P.out_cnt[bk + e] = __ldcg(pc + e);
+    }
+    __syncthreads();
+    if (tid == 0) { sm.pend_valid = 0; bin_done(P, lb); }
 }
 
 // One CTA per bin, bins taken in index order through a ticket; a bin of any size is handled as long as its distinct
@@ -676,6 +763,7 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
     const int padbits = 2 * (32 * NW - k);
 
     for (int i = tid; i < BN_HCAP; i += TH) sm.hist[i] = 0;
+    if (tid == 0) sm.pend_valid = 0;
 
     while (true) {
         __syncthreads();   // end of the previous bin: shared memory is free again
@@ -686,6 +774,7 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
         __syncthreads();
         const u32 lb = sm.bin;
         if (lb >= P.nbins) break;
+        bool deferred = false;   // this bin's "in the arena" bookkeeping happens when its stash is flushed
 
         // ---- bin descriptor: one segment of slots per source rank
         if (tid < P.nsrc) {
@@ -744,8 +833,9 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
 
         // ---- expand + insert + count.  About two batches per warp, so that the warps finish together
         if (tid == 0) {
-            u32 bs = (S + 2 * Cfg::WARPS - 1) / (2 * Cfg::WARPS);
-            sm.batch_slots = min((u32)Cfg::BATCH, max(8u, bs));
+            const u32 parts = P.walk_split * Cfg::WARPS;
+            u32 bs = (S + parts - 1) / parts;
+            sm.batch_slots = min((u32)Cfg::BATCH, max(P.walk_min, bs));
         }
         __syncthreads();
         if (!sm.bail) walk_bin<false>(sm, P, k, padbits, S);
@@ -783,6 +873,7 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
         block_scan2<TH>(kept, occ, sm.wa, sm.wb, ek, eo, tk, to);   // (its barriers: every candidate has been read)
         if (!EXT) to = 0;
         const bool big = tk > (u32)Cfg::SORTCAP;   // too many kept k-mers to sort here (never a listed bin): staging area + big gather
+        u64 stage_k = 0, stage_o = 0;
         if (big) {
             // room in the staging area?  Otherwise the bin goes through the HBM path like an overflowing one.
             if (tid == 0) {
@@ -793,6 +884,7 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
             }
             __syncthreads();
             if (sm.bail) { bailed = true; tk = 0; to = 0; }
+            stage_k = sm.base_k; stage_o = sm.base_o;
         }
         if (tid == 0) {
             volatile u64 *lbs = P.lb_state;
@@ -801,6 +893,8 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
             sm.next_batch = 0;
             if (bailed) P.ovf_list[atomicAdd(P.ovf_count, 1u)] = lb;
         }
+        // the bin this CTA finished before this one goes to the arena now: every bin before it has long published its total
+        if (!EXT) { __syncthreads(); flush_pending<NW, EXT, TH>(sm, P); }
         if (EXT && !bailed && !big) {
             // slots that are not kept: the occurrence pass tells by the mark (kept slots get their cursor below)
             __syncthreads();
@@ -817,23 +911,29 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
         if (bailed) {
             resolve_position(sm, P, lb, 0u, 0u);
         } else if (!big) {
-            // compacted list of the kept slots (in place of the candidates, all of which have been read), then sort +
-            // emit straight into the arena
+            // compacted list of the kept slots (the walk's scratch is free), then the sort; the sorted bin goes to the
+            // CTA's scratch (its place in the arena is resolved later) or, with EXTENSION, straight into the arena
             u32 g = ek;
             if (listed) {
 #pragma unroll
-                for (int i = 0; i < LPT; ++i) if ((keepmask >> i) & 1) sm.cand[g++] = (u16)myslot[i];
+                for (int i = 0; i < LPT; ++i) if ((keepmask >> i) & 1) sm.klist()[g++] = (u16)myslot[i];
             } else {
 #pragma unroll
-                for (int i = 0; i < Cfg::SLOTS_PT; ++i) if ((keepmask >> i) & 1) sm.cand[g++] = (u16)(tid * Cfg::SLOTS_PT + i);
+                for (int i = 0; i < Cfg::SLOTS_PT; ++i) if ((keepmask >> i) & 1) sm.klist()[g++] = (u16)(tid * Cfg::SLOTS_PT + i);
             }
             __syncthreads();
-            sort_emit<NW, EXT, TH>(sm, P, lb, tk, to);
-            if (EXT && tid == 0) { sm.occ_pos = P.out_pos; sm.occ_rid = P.out_rid; }
+            if (tk) sort_bin<NW, EXT, TH>(sm, tk);
+            if (EXT) {
+                emit_now<NW, EXT, TH>(sm, P, lb, tk, to);
+                if (tid == 0) { sm.occ_pos = P.out_pos; sm.occ_rid = P.out_rid; }
+            } else {
+                stash_bin<NW, EXT, TH>(sm, P, lb, tk);
+                deferred = true;
+            }
         } else {
             // unsorted into the staging area (the whole table was scanned); the big gather sorts and moves the bin to its
             // place in the arena
-            const u64 sk = sm.base_k, so = sm.base_o;
+            const u64 sk = stage_k, so = stage_o;
             u64 g = sk + ek;
             u32 lo = eo;   // occurrence offset inside the bin
 #pragma unroll
@@ -873,23 +973,13 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
             if (to && !bailed && !sm.skip_out) walk_bin<true>(sm, P, k, padbits, S);
         }
 
-        // ---- the bin is in the arena: group bookkeeping for the host that streams the result out
+        // ---- the bin is in the arena (unless it waits in the stash): group bookkeeping for the host that streams the result out
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            const u32 g = lb / P.group_bins;
-            const u32 gsize = min(P.group_bins, P.nbins - g * P.group_bins);
-            if (atomicAdd(&P.grp_done[g], 1u) + 1 == gsize && P.snap) {
-                __threadfence();
-                volatile u64 *sn = P.snap + 4 * (size_t)g;
-                sn[0] = P.grp_end[2 * g]; sn[1] = P.grp_end[2 * g + 1]; sn[2] = P.grp_big[g];
-                __threadfence_system();
-                sn[3] = 1;
-            }
-        }
+        if (tid == 0 && !deferred) bin_done(P, lb);
     }
 
     __syncthreads();
+    if (!EXT) { flush_pending<NW, EXT, TH>(sm, P); __syncthreads(); }
     for (int i = tid; i < BN_HCAP; i += TH)
         if (sm.hist[i]) atomicAdd(&P.histogram[i], (u64)sm.hist[i]);
 }
@@ -1105,6 +1195,7 @@ static_assert(sizeof(BinSmem<1, false, 512>) <= (233472 - 2 * 1024) / 2, "K <= 3
 static_assert(sizeof(BinSmem<1, true, 512>) <= (233472 - 3 * 1024) / 3, "K <= 32 with EXTENSION: three CTAs per SM");
 static_assert(sizeof(BinSmem<2, false, 512>) <= 232448 && sizeof(BinSmem<2, true, 512>) <= 232448 && sizeof(BinSmem<3, true, 512>) <= 232448, "K > 32: one CTA per SM");
 static_assert(sizeof(BinSmem<2, false, 1024>) <= 232448, "K in 33..64: one CTA of 1024 threads per SM");
+static_assert(sizeof(BinSmem<1, false, 256>) <= (233472 - 4 * 1024) / 4, "K <= 32: four CTAs of 256 threads per SM");
 constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers than a CTA sorts itself
 
 template <int NW, bool EXT, int TH>
@@ -1134,20 +1225,16 @@ static cudaError_t launch_big_t(const BinParams &P, int sm_count, cudaStream_t s
     return cudaGetLastError();
 }
 
-// threads per CTA of the K in 33..64 kernel: 1024 (one CTA per SM either way; HSK_BIN_THREADS=512 selects the 16-warp variant)
-static int k2_threads()
-{
-    static int v = [] { const char *e = getenv("HSK_BIN_THREADS"); const int t = e ? atoi(e) : 1024; return t == 512 ? 512 : 1024; }();
-    return v;
-}
-
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s)
 {
     if (P.nbins == 0) return cudaSuccess;
-    if (nwords == 1) return ext ? launch_bins_t<1, true, 512>(P, sm_count, s) : launch_bins_t<1, false, 512>(P, sm_count, s);
+    if (nwords == 1) {
+        if (ext) return launch_bins_t<1, true, 512>(P, sm_count, s);
+        return bin_threads_env(512, 256) == 256 ? launch_bins_t<1, false, 256>(P, sm_count, s) : launch_bins_t<1, false, 512>(P, sm_count, s);
+    }
     if (nwords == 2) {
         if (ext) return launch_bins_t<2, true, 512>(P, sm_count, s);
-        return k2_threads() == 1024 ? launch_bins_t<2, false, 1024>(P, sm_count, s) : launch_bins_t<2, false, 512>(P, sm_count, s);
+        return bin_threads_env(1024, 512) == 1024 ? launch_bins_t<2, false, 1024>(P, sm_count, s) : launch_bins_t<2, false, 512>(P, sm_count, s);
     }
     return ext ? launch_bins_t<3, true, 512>(P, sm_count, s) : launch_bins_t<3, false, 512>(P, sm_count, s);
 }

@@ -223,16 +223,19 @@ private:
 };
 
 // hsk_count_stream: parts of the result that have reached the page-locked host arrays are handed to the caller's sink by
-// one thread of the context, in order, while the GPU works on the rest.
+// a few threads of the context (one part per thread at a time) while the GPU works on the rest.
 struct SinkPart { u64 first, n, first_occ, n_occ, hint; cudaEvent_t ready; };
-class SinkWorker {
+class SinkPool {
 public:
-    SinkWorker() : th_([this] { run(); }) {}
-    ~SinkWorker()
+    explicit SinkPool(unsigned nthreads)
+    {
+        for (unsigned t = 0; t < std::max(1u, nthreads); ++t) th_.emplace_back([this] { run(); });
+    }
+    ~SinkPool()
     {
         { std::lock_guard<std::mutex> l(m_); stop_ = true; }
         cv_.notify_all();
-        th_.join();
+        for (auto &t : th_) t.join();
     }
     void begin(hsk_sink_fn fn, void *user, const hsk_result *view, int device)
     {
@@ -242,7 +245,7 @@ public:
     void push(const SinkPart &p)
     {
         { std::lock_guard<std::mutex> l(m_); q_.push_back(p); ++busy_; }
-        cv_.notify_all();
+        cv_.notify_one();
     }
     // waits until every pushed part has been delivered; returns the first non-zero sink status
     int drain()
@@ -254,19 +257,21 @@ public:
 private:
     void run()
     {
-        bool dev_set = false;
+        int dev_set = -1;
         while (true) {
             SinkPart p;
+            hsk_sink_fn fn; void *user; const hsk_result *view; int device; bool skip;
             {
                 std::unique_lock<std::mutex> l(m_);
                 cv_.wait(l, [this] { return stop_ || !q_.empty(); });
                 if (q_.empty()) return;
                 p = q_.front(); q_.pop_front();
+                fn = fn_; user = user_; view = view_; device = device_; skip = rc_ != 0;
             }
-            if (!dev_set) { cudaSetDevice(device_); dev_set = true; }
+            if (dev_set != device) { cudaSetDevice(device); dev_set = device; }
             int rc = 0;
             if (p.ready && cudaEventSynchronize(p.ready) != cudaSuccess) rc = 2;
-            if (!rc && rc_ == 0 && fn_) rc = fn_(user_, view_, p.first, p.n, p.first_occ, p.n_occ, p.hint);
+            if (!rc && !skip && fn) rc = fn(user, view, p.first, p.n, p.first_occ, p.n_occ, p.hint);
             {
                 std::lock_guard<std::mutex> l(m_);
                 if (rc && !rc_) rc_ = rc;
@@ -283,7 +288,7 @@ private:
     int device_ = 0, rc_ = 0;
     unsigned busy_ = 0;
     bool stop_ = false;
-    std::thread th_;
+    std::vector<std::thread> th_;
 };
 
 } // namespace
@@ -306,6 +311,7 @@ struct hsk_ctx {
     bool stream_result = false;          // hsk_count: results go to the host buffers group by group
     u32 *d_in_flags = nullptr;           // hsk_count: read table checks (reads.cu), looked at after the first sync
     DevBuf d_dd;                         // per-CTA lists of distinct supermers (bins.cu: dedup_bin)
+    DevBuf d_pend;                       // per-CTA stash of the last sorted bin (bins.cu: stash_bin)
     DevBuf d_grp;                        // per bin group: ticket, big-bin counter
     HostBuf h_grp;                       // per bin group: arena cursor after the group
     // extraction
@@ -323,7 +329,8 @@ struct hsk_ctx {
     std::vector<DevBuf> retired;         // former supermer buffers that peers may still have mapped (freed one call later)
     // host side of hsk_count_stream
     std::unique_ptr<HostPool> pool;
-    std::unique_ptr<SinkWorker> sink;
+    std::unique_ptr<SinkPool> sink;
+    unsigned host_threads = 1;
     hsk_sink_fn sink_fn = nullptr;
     void *sink_user = nullptr;
     hsk_result sink_view;
@@ -448,8 +455,9 @@ int hsk_create(hsk_ctx **out, const hsk_config *cfg)
     {
         // host threads of the context (staging of pageable input, hsk_fill_entries): the ranks of a node share its cores
         unsigned nt = std::max(1u, std::thread::hardware_concurrency() / (unsigned)cfg->nranks);
-        nt = std::min(nt, 8u);
+        nt = std::min(nt, 16u);
         if (const char *ev = getenv("HSK_HOST_THREADS")) { const int v = atoi(ev); if (v >= 1 && v <= 64) nt = (unsigned)v; }
+        c->host_threads = nt;
         c->pool.reset(new HostPool(nt));
     }
     *out = c;
@@ -483,7 +491,7 @@ void hsk_destroy(hsk_ctx *c)
     for (int r = 0; r < hsk_ctx::RING; ++r) { c->h_ring[r].release(); if (c->ring_free[r]) cudaEventDestroy(c->ring_free[r]); }
     c->h_len.release();
     DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_len64, &c->d_rtscratch, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bscratch, &c->d_bucket, &c->d_slots,
-                    &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_peerinfo, &c->d_dd, &c->d_grp, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
+                    &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_peerinfo, &c->d_dd, &c->d_pend, &c->d_grp, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
                     &c->d_cscratch, &c->d_tsum, &c->d_tbase, &c->d_swords, &c->d_scnt, &c->d_spos, &c->d_srid, &c->d_owords, &c->d_ocnt, &c->d_oocc_off, &c->d_opos, &c->d_orid,
                     &c->d_hist, &c->d_cursor};
     for (auto *b : db) b->release();
@@ -965,9 +973,9 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         const size_t have = c->d_owords.cap + c->d_ocnt.cap + c->d_swords.cap + c->d_scnt.cap + c->d_oocc_off.cap + c->d_opos.cap +
                             c->d_orid.cap + c->d_spos.cap + c->d_srid.cap;
         size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
         u64 budget = 0;
         if (const char *ev = getenv("HSK_ARENA_BUDGET_MB")) budget = strtoull(ev, nullptr, 10) << 20;   // tests
+        if (need > have && !budget) CK(cudaMemGetInfo(&free_b, &total_b));   // (a slow driver call: only when something has to grow)
         if (budget || (need > have && (double)(need + need / 16) > 0.92 * (double)(free_b + have))) {
             CK(cudaStreamSynchronize(s));
             DevBuf *rel[] = {&c->d_run_list, &c->d_tile_hdr, &c->d_owords, &c->d_ocnt, &c->d_swords, &c->d_scnt, &c->d_oocc_off,
@@ -1032,9 +1040,17 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         if (NW <= 2 && !ext && !(ev && *ev == '0')) {
             CK(c->d_dd.ensure(bin_dedup_scratch_bytes(c->sm_count, SW)));
             BP.dd_slots = c->d_dd.as<uint4>();
-            BP.dd_mult = reinterpret_cast<u32 *>(BP.dd_slots + (size_t)c->sm_count * 2 * BN_DDLIMIT_MAX * (SW / 4));
+            BP.dd_mult = reinterpret_cast<u32 *>(BP.dd_slots + (size_t)c->sm_count * BN_MAX_CTAS * BN_DDLIMIT_MAX * (SW / 4));
         }
     }
+    if (!ext) {
+        CK(c->d_pend.ensure(bin_pending_scratch_bytes(c->sm_count, NW)));
+        BP.pend_words = c->d_pend.as<u64>();
+        BP.pend_cnt = reinterpret_cast<u32 *>(BP.pend_words + (size_t)c->sm_count * BN_MAX_CTAS * BN_SORTCAP * NW);
+    }
+    BP.walk_split = 1; BP.walk_min = 8;
+    if (const char *ev = getenv("HSK_WALK_SPLIT")) { const int v = atoi(ev); if (v >= 1 && v <= 16) BP.walk_split = (u32)v; }
+    if (const char *ev = getenv("HSK_WALK_MIN")) { const int v = atoi(ev); if (v >= 1 && v <= 32) BP.walk_min = (u32)v; }
     BP.grp_end = c->d_grp.as<u64>();
     BP.grp_done = reinterpret_cast<u32 *>(BP.grp_end + (size_t)2 * NG); BP.grp_big = BP.grp_done + NG;
     volatile u64 *snap = c->h_grp.as<u64>();
@@ -1393,7 +1409,7 @@ int hsk_count_stream(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const u
     const u64 staged_launches = c->stats.n_launches;
     c->stream_result = true;
     c->sink_fn = sink; c->sink_user = user;
-    if (sink && !c->sink) c->sink.reset(new SinkWorker());
+    if (sink && !c->sink) c->sink.reset(new SinkPool(c->host_threads));
     const int rc = count_device(c, c->d_packed.as<u8>(), nbytes, ((nbytes + 15) & ~15ull) + 64, c->d_read_off.as<u64>(),
                                 c->d_read_len.as<u32>(), nreads, readid_base);
     c->stream_result = false;

@@ -66,6 +66,8 @@ cudaError_t launch_expand(const ExpandSegment &seg, int k, int nwords, bool ext,
                           Planes out_keys, u64 *out_val, cudaStream_t s);
 
 // ---- stages 4+5 on chip: bins.cu ---------------------------------------------------------------------
+constexpr int BN_MAX_CTAS = 4;          // CTAs of k_bin_count per SM, at most
+constexpr int BN_SORTCAP = 2048;       // most kept k-mers of a bin that the CTA sorts itself
 constexpr int BN_DDLIMIT_MAX = 2048;   // entries of a CTA's list of distinct supermers (bins with more slots skip the de-duplication)
 
 struct BinParams {
@@ -99,9 +101,14 @@ struct BinParams {
     u64 *snap;                           // page-locked host memory or null: per group {entries, occurrences, big bins, ready}
     // per CTA: list of the distinct supermer slots of the bin it works on and their weights (K <= 64 without EXTENSION)
     uint4 *dd_slots; u32 *dd_mult;
+    // per CTA: the sorted (k-mer, count) entries of the bin it finished last, until their place in the arena is resolved
+    // (without EXTENSION): BN_SORTCAP entries each
+    u64 *pend_words; u32 *pend_cnt;
+    u32 walk_split, walk_min;            // the walk cuts a bin into about walk_split batches per warp, of at least walk_min slots
 };
 
 size_t bin_dedup_scratch_bytes(int sm_count, int slot_words);   // dd_slots + dd_mult of every resident CTA
+size_t bin_pending_scratch_bytes(int sm_count, int nwords);    // pend_words + pend_cnt of every resident CTA (3 per SM at most)
 int bin_target_kmers(int nwords, bool ext);  // k-mer occurrences per bin the on-chip path is sized for
 // k_bin_count: every bin counted, sorted and written to the arena (or listed for the big gather / the HBM path)
 cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_count, cudaStream_t s);

@@ -25,7 +25,10 @@
 #include <sstream>
 #include <stdexcept>
 #include <memory>
+#include <mutex>
 #include <new>
+#include <utility>
+#include <vector>
 #include <type_traits>
 
 namespace hysortk {
@@ -55,85 +58,94 @@ struct Engine {
 Engine g_engine;
 
 /* Builds the KmerListS while the result is still arriving (sink of hsk_count_stream).  The entries are constructed in
- * place in memory obtained from std::allocator<KmerListEntryS>, by the host threads, part by part; the finished array is
- * then handed to a std::vector without the value-initialisation + copy that resize() + assignment would cost (the list
- * has millions of entries; first touch of its pages is the expensive part and is spread over the threads). */
+ * place in memory obtained from std::allocator<KmerListEntryS>: the host threads of the engine deliver disjoint parts of
+ * the result concurrently and each fills its part; the finished array is then handed to a std::vector without the
+ * value-initialisation + copy that resize() + assignment would cost (the list has millions of entries; first touch of
+ * its pages is the expensive part and is spread over the threads).  The array is allocated when the first part arrives,
+ * from the engine's estimate of the total; should a part not fit after all, it is left out and the list is rebuilt
+ * from the complete result after the call (complete()). */
 struct ListBuilder {
     static constexpr int NW = TKmer::NBYTES / 8;
     std::allocator<KmerListEntryS> alloc;
     KmerListEntryS *base = nullptr;
-    size_t cap = 0, filled = 0;
-    int nthreads = 1;   /* the caller's OpenMP team size: the sink runs on a thread of the engine, whose own default differs */
+    size_t cap = 0;
+    std::mutex mu;
+    std::vector<std::pair<uint64_t, uint64_t>> done;   /* parts constructed so far: (first, n) */
+    bool overflow = false;
+    int nthreads = 1;   /* the caller's OpenMP team size (complete() only) */
+    double fill_seconds = 0.0;
     std::string error;
 
     ~ListBuilder() { release(); }
+    void destroy_entries()
+    {
+#if EXTENSION == 1
+        for (auto& r : done)
+            for (uint64_t i = r.first; i < r.first + r.second; ++i) base[i].~KmerListEntryS();
+#endif
+        done.clear();
+    }
     void release()
     {
         if (!base) return;
-#if EXTENSION == 1
-        for (size_t i = 0; i < filled; ++i) base[i].~KmerListEntryS();
-#endif
+        destroy_entries();
         alloc.deallocate(base, cap);
-        base = nullptr; cap = filled = 0;
+        base = nullptr; cap = 0;
     }
-    void grow(size_t want)
+    void allocate(size_t want)
     {
-        const size_t ncap = want + want / 8 + 1024;
-        KmerListEntryS *nb = alloc.allocate(ncap);
-        if (filled) {
-#if EXTENSION == 1
-            #pragma omp parallel for schedule(static) num_threads(nthreads)
-            for (size_t i = 0; i < filled; ++i) { new (nb + i) KmerListEntryS(std::move(base[i])); base[i].~KmerListEntryS(); }
-#else
-            const size_t n = filled;
-            #pragma omp parallel for schedule(static) num_threads(nthreads)
-            for (size_t b = 0; b < (n + 65535) / 65536; ++b) {
-                const size_t lo = b * 65536, hi = std::min(n, lo + 65536);
-                std::memcpy(static_cast<void *>(nb + lo), static_cast<const void *>(base + lo), (hi - lo) * sizeof(KmerListEntryS));
-            }
+        cap = want + 64;
+        base = alloc.allocate(cap);
+#ifdef MADV_HUGEPAGE
+        /* millions of entries: with 4 KiB pages the first touch of the array costs more than filling it; ask for
+         * transparent huge pages on the 2 MiB-aligned interior (a no-op where they are disabled) */
+        const uintptr_t huge = uintptr_t(2) << 20;
+        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(base) + huge - 1) & ~(huge - 1);
+        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(base) + cap * sizeof(KmerListEntryS)) & ~(huge - 1);
+        if (a1 > a0) (void)::madvise(reinterpret_cast<void *>(a0), a1 - a0, MADV_HUGEPAGE);
 #endif
+    }
+    /* entries [first, first + n) from the result arrays */
+    void fill(const hsk_result *v, uint64_t first, uint64_t n, uint64_t occ_end)
+    {
+        const uint64_t *words = v->kmer_words;
+        const uint32_t *cnt = v->cnt;
+#if EXTENSION == 1
+        for (uint64_t i = first; i < first + n; ++i) {
+            KmerListEntryS *e = new (base + i) KmerListEntryS();
+            e->kmer = TKmer(static_cast<const void *>(words + i * NW));
+            e->cnt = cnt[i];
+            const uint64_t o0 = v->occ_off[i], o1 = (i + 1 < first + n) ? v->occ_off[i + 1] : occ_end;
+            e->pos.assign(v->pos + o0, v->pos + o1);
+            e->rid.assign(v->rid + o0, v->rid + o1);
         }
-        if (base) alloc.deallocate(base, cap);
-        base = nb; cap = ncap;
+#else
+        (void)occ_end;
+        static_assert(sizeof(KmerListEntryS) == 8 * (NW + 1), "entry layout: k-mer words followed by the 64-bit count");
+        uint64_t *raw = reinterpret_cast<uint64_t *>(base);
+        for (uint64_t i = first; i < first + n; ++i) {
+            for (int l = 0; l < NW; ++l) raw[i * (NW + 1) + l] = words[i * NW + l];
+            raw[i * (NW + 1) + NW] = cnt[i];
+        }
+#endif
     }
     int take(const hsk_result *v, uint64_t first, uint64_t n, uint64_t first_occ, uint64_t n_occ, uint64_t hint)
     {
+        const auto t_in = std::chrono::steady_clock::now();
         try {
-            const size_t want = std::max<size_t>(first + n, hint);
-            if (want > cap) grow(want);
-            KmerListEntryS *dst = base;
-            const uint64_t *words = v->kmer_words;
-            const uint32_t *cnt = v->cnt;
-#if EXTENSION == 1
-            const uint64_t *off = v->occ_off;
-            const uint32_t *pos = v->pos;
-            const int32_t *rid = v->rid;
-            const uint64_t occ_end = first_occ + n_occ;
-            #pragma omp parallel for schedule(static) num_threads(nthreads)
-            for (size_t i = first; i < first + n; ++i) {
-                KmerListEntryS *e = new (dst + i) KmerListEntryS();
-                e->kmer = TKmer(static_cast<const void *>(words + i * NW));
-                e->cnt = cnt[i];
-                const uint64_t o0 = off[i], o1 = (i + 1 < first + n) ? off[i + 1] : occ_end;
-                e->pos.assign(pos + o0, pos + o1);
-                e->rid.assign(rid + o0, rid + o1);
+            {
+                std::lock_guard<std::mutex> l(mu);
+                if (!base) allocate(std::max<size_t>(first + n, hint));
+                if (first + n > cap) { overflow = true; return 0; }
+                if (n) done.emplace_back(first, n);
             }
-#else
-            (void)first_occ; (void)n_occ;
-            static_assert(sizeof(KmerListEntryS) == 8 * (NW + 1), "entry layout: k-mer words followed by the 64-bit count");
-            uint64_t *raw = reinterpret_cast<uint64_t *>(dst);
-            #pragma omp parallel for schedule(static) num_threads(nthreads)
-            for (size_t b = first / 4096; b < (first + n + 4095) / 4096; ++b) {
-                const size_t lo = std::max<size_t>(first, b * 4096), hi = std::min<size_t>(first + n, (b + 1) * 4096);
-                for (size_t i = lo; i < hi; ++i) {
-                    for (int l = 0; l < NW; ++l) raw[i * (NW + 1) + l] = words[i * NW + l];
-                    raw[i * (NW + 1) + NW] = cnt[i];
-                }
-            }
-#endif
-            filled = first + n;
+            fill(v, first, n, first_occ + n_occ);
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_in).count();
+            std::lock_guard<std::mutex> l(mu);
+            fill_seconds += dt;
             return 0;
         } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> l(mu);
             error = e.what();
             return 1;
         }
@@ -142,20 +154,38 @@ struct ListBuilder {
     {
         return static_cast<ListBuilder *>(user)->take(v, first, n, first_occ, n_occ, hint);
     }
+    /* after the call: `res` is the complete result.  Nothing to do when the parts covered it; otherwise (the estimate
+     * fell short, or the engine delivered nothing) the list is built from `res` by the caller's threads. */
+    void complete(const hsk_result& res)
+    {
+        uint64_t covered = 0;
+        for (auto& r : done) covered += r.second;
+        if (!overflow && covered == res.n_kept) return;
+        release();
+        overflow = false;
+        if (res.n_kept == 0) return;
+        allocate(res.n_kept);
+        const uint64_t n = res.n_kept, block = 16384;
+        #pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+        for (uint64_t b = 0; b < (n + block - 1) / block; ++b)
+            fill(&res, b * block, std::min(block, n - b * block), res.n_occ);
+        done.emplace_back(0, n);
+    }
     /* the finished array becomes the storage of a std::vector */
-    std::unique_ptr<KmerListS> finish()
+    std::unique_ptr<KmerListS> finish(uint64_t n)
     {
         auto list = std::make_unique<KmerListS>();
-        if (!base || filled == 0) return list;
+        if (!base || n == 0) return list;
 #if defined(__GLIBCXX__) || defined(_LIBCPP_VERSION)
         /* libstdc++ / libc++: a vector with the default allocator is three pointers (begin, end, end of storage) */
         static_assert(sizeof(KmerListS) == 3 * sizeof(void *), "std::vector layout");
-        KmerListEntryS *triple[3] = {base, base + filled, base + cap};
+        KmerListEntryS *triple[3] = {base, base + n, base + cap};
         std::memcpy(static_cast<void *>(list.get()), triple, sizeof(triple));
-        base = nullptr; cap = filled = 0;
+        base = nullptr; cap = 0;
+        done.clear();
 #else
-        list->reserve(filled);
-        for (size_t i = 0; i < filled; ++i) list->push_back(std::move(base[i]));
+        list->reserve(n);
+        for (uint64_t i = 0; i < n; ++i) list->push_back(std::move(base[i]));
         release();
 #endif
         return list;
@@ -359,8 +389,11 @@ std::unique_ptr<KmerListS> kmer_count(const DnaBuffer& mydna, MPI_Comm comm)
     builder.nthreads = std::max(1, omp_get_max_threads());
     if (hsk_count_stream(ctx, bytes, nbytes, lens.data(), n, readoffset, &ListBuilder::sink, &builder, &res))
         throw std::runtime_error(builder.error.empty() ? std::string(hsk_last_error()) : "kmer_count: " + builder.error);
-    if (builder.filled != res.n_kept) throw std::runtime_error("kmer_count: internal: result parts do not add up");
-    auto list = builder.finish();
+    builder.complete(res);
+    if (const char *tr = std::getenv("HSK_TRACE"); tr && *tr == '1')
+        std::cerr << "[hsk trace] KmerListS: " << res.n_kept << " entries in " << builder.done.size() << " parts, "
+                  << builder.fill_seconds * 1e3 << " ms (summed over the threads) in the sink" << std::endl;
+    auto list = builder.finish(res.n_kept);
 
 #if LOG_LEVEL >= 1
     MPI_Barrier(comm);

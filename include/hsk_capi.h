@@ -131,12 +131,14 @@ int hsk_count(hsk_ctx *ctx, const uint8_t *packed, uint64_t nbytes, const uint64
 
 /* kmer_count on host buffers with the result handed over while it is being produced — what the C++ shim uses to build the
  * reference's KmerListS (std::vector<KmerListEntryS>, include/kmer.hpp:368-410; reference kmerops.cpp:883-904 copies the
- * task results into it at the end) while the GPU is still counting.  `sink` is called from one thread of the context, in
- * entry order, with parts [first_entry, first_entry + n_entries) of the result that have reached the host: `view` has
- * the hsk_result layout and is indexed with absolute entry / occurrence numbers (pointers valid during the call only);
- * `total_hint` estimates the final number of entries (exact in the last call).  A non-zero return of the sink stops the
- * deliveries and makes hsk_count_stream fail.  All calls of the sink have returned when hsk_count_stream returns; *out is
- * filled as by hsk_count.  `packed` may be pageable memory (a DnaBuffer is a plain heap array, reference
+ * task results into it at the end) while the GPU is still counting.  `sink` is called from the host threads of the
+ * context — several calls may run at the same time, in any order — with disjoint parts [first_entry, first_entry +
+ * n_entries) of the result that have reached the host; together they cover [0, n_kept) exactly.  `view` has the
+ * hsk_result layout and is indexed with absolute entry / occurrence numbers (pointers valid during the call only; the
+ * occurrences of the part are [first_occ, first_occ + n_occ)); `total_hint` is an estimate of the final number of entries
+ * that does not fall short by more than a few percent (exact in the part that is produced last).  A non-zero return of
+ * the sink stops the deliveries and makes hsk_count_stream fail.  All calls of the sink have returned when
+ * hsk_count_stream returns; *out is filled as by hsk_count, so a sink may also leave parts to its caller.  `packed` may be pageable memory (a DnaBuffer is a plain heap array, reference
  * include/dnabuffer.hpp:40): it is then copied through a page-locked staging ring by the context's host threads
  * (HSK_HOST_THREADS, default: the hardware threads divided by the ranks, at most 8), chunk by chunk under the extraction. */
 typedef int (*hsk_sink_fn)(void *user, const hsk_result *view, uint64_t first_entry, uint64_t n_entries, uint64_t first_occ,

@@ -20,7 +20,8 @@ def make(k, m, l, u, ext, target="standalone", log=0):
     obj = os.path.join(BUILD, "obj_" + tag)
     binp = os.path.join(BUILD, "hysortk_" + tag)
     subprocess.check_call(["make", "-s", "-j8", target, f"K={k}", f"M={m}", f"L={l}", f"U={u}", f"EXT={ext}", f"LOG={log}",
-                           f"OBJ={obj}", f"BIN={binp}"], cwd=ROOT, stdout=subprocess.DEVNULL)
+                           f"OBJ={obj}", f"BIN={binp}", "CUOBJ=" + os.path.join(BUILD, "cuda_obj")], cwd=ROOT,
+                          stdout=subprocess.DEVNULL)
     return obj, binp
 
 

@@ -281,21 +281,21 @@ def test_count_stream_parts_and_input_memory(k, m, ext, monkeypatch):
     order, their concatenation equals hsk_count's result and the oracle's; page-locked and pageable input (staged
     through the ring of page-locked buffers by the context's host threads) give the same result."""
     import torch
-    rs = synth.sample_fixed(800_000, 10.0, 3000, 0.01, seed=31 + k + ext)
+    rs = synth.sample_fixed(400_000, 25.0, 3000, 0.01, seed=31 + k + ext)
     exp = po.kmer_count(rs.packed, rs.readlens, k, m, 2, 50, ext, via_supermers=False)
     monkeypatch.setenv("HSK_GROUPS", "9")
     with capi.Context(k, m, 2, 50, ext) as ctx:
         base = ctx.count(rs.packed, rs.readlens)                      # pageable numpy memory
         s = ctx.count_stream(rs.packed, rs.readlens)
-        firsts = [p[0] for p in s["parts"]]
-        ns = [p[1] for p in s["parts"]]
-        assert firsts == list(np.cumsum([0] + ns[:-1])) and sum(ns) == base["n_kept"] and len(ns) >= 2
-        assert s["parts"][-1][2] == base["n_kept"]                   # the last hint is exact
+        parts = sorted(s["parts"])                                   # delivered by several threads, in any order
+        firsts, ns = [p[0] for p in parts], [p[1] for p in parts]
+        assert firsts == [int(x) for x in np.cumsum([0] + ns[:-1])] and sum(ns) == base["n_kept"] and len(ns) >= 2
+        assert max(p[2] for p in parts) >= base["n_kept"] and min(p[2] for p in parts) >= 0.9 * base["n_kept"]   # the hints
         assert np.array_equal(s["words"], base["words"]) and np.array_equal(s["cnt"], base["cnt"])
+        got = po.canonicalize(k, s["words"], s["cnt"], s.get("occ_off"), s.get("pos"), s.get("rid"))
+        po.assert_equal(got, exp, "stream vs oracle")               # (the order inside an occurrence list is not fixed)
         if ext:
             assert np.array_equal(s["occ_off"], base["occ_off"])
-            assert np.array_equal(s["pos"], base["pos"]) and np.array_equal(s["rid"], base["rid"])
-        po.assert_equal(po.canonicalize(k, s["words"], s["cnt"], s.get("occ_off"), s.get("pos"), s.get("rid")), exp, "stream vs oracle")
         # page-locked input goes up from where it is
         hp = torch.from_numpy(rs.packed).pin_memory()
         hl = torch.from_numpy(rs.readlens.view(np.int64)).pin_memory()
