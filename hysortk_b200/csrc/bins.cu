@@ -59,19 +59,19 @@ struct BinCfg {
     static constexpr int SW = (NW == 1 ? 4 : 8) + (EXT ? 4 : 0);
     static constexpr int PW = SW - (EXT ? 2 : 0);
     // table slots: K <= 32: 8192 (two CTAs per SM), with EXTENSION 4096 (three CTAs); K > 32: one CTA per SM
-    static constexpr int TS_BITS = NW == 1 ? (EXT || TH < 512 ? 12 : 13) : (NW == 2 && !EXT ? 13 : 12);
+    static constexpr int TS_BITS = NW == 1 ? (EXT ? 12 : 13) : (NW == 2 && !EXT ? 13 : 12);
     static constexpr int TS = 1 << TS_BITS;
     static constexpr int SLOTS_PT = TS / TH;
-    static constexpr int CTAS = NW == 1 ? (EXT ? 3 : (TH < 512 ? 4 : 2)) : 1;
+    static constexpr int CTAS = NW == 1 ? (EXT ? 3 : 2) : 1;
     // most k-mers one slot can hold (smallest K of the word count) = rounds of 32 k-mers a batch of 32 slots can need
     static constexpr int NMAX = 16 * (PW - 1) + 12 - (NW == 1 ? 3 : (NW == 2 ? 33 : 65)) + 1;
     // slots per walk batch (a warp stages them) and kept k-mers a CTA sorts itself; a bin that keeps more goes through
     // the staging area + big gather
     static constexpr int BATCH = TH != 512 ? 16 : 32;
-    static constexpr int SORTCAP = TH < 512 ? BN_SORTCAP / 2 : BN_SORTCAP;
+    static constexpr int SORTCAP = BN_SORTCAP;
     static constexpr int EPT = SORTCAP / TH;   // kept k-mers per thread in the sort
     static constexpr int HEADW = ((BATCH * NMAX + 31) / 32 + 3) / 4 * 4;   // rounds of 32 k-mers a batch can need
-    static constexpr int TARGET = NW == 1 ? (EXT || TH < 512 ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
+    static constexpr int TARGET = NW == 1 ? (EXT ? 4096 : 8192) : (NW == 2 && !EXT ? 6144 : 3072);
     // de-duplication of the supermers of a bin (K <= 64 without EXTENSION): cells of the supermer table, most slots of
     // a bin that goes through it (a multiple of TH, below the number of cells)
     static constexpr int DDTS = TH > 512 ? 4096 : 2048;
@@ -84,8 +84,8 @@ struct BinCfg {
 size_t bin_pending_scratch_bytes(int sm_count, int nwords) { return (size_t)sm_count * BN_MAX_CTAS * BN_SORTCAP * ((size_t)nwords * 8 + 4); }
 size_t bin_dedup_scratch_bytes(int sm_count, int slot_words) { return (size_t)sm_count * BN_MAX_CTAS * BN_DDLIMIT_MAX * ((size_t)slot_words * 4 + sizeof(u32)); }
 
-// threads per CTA of the kernels that come in two shapes (HSK_BIN_THREADS): K <= 32 without EXTENSION: 512 (two CTAs per SM,
-// 8192-slot tables) or 256 (four CTAs, 4096-slot tables, bins half as large); K in 33..64: 1024 or 512 (one CTA per SM)
+// threads per CTA of the kernel that comes in two shapes (HSK_BIN_THREADS): K in 33..64: 1024 or 512, one CTA per SM either
+// way.  (For K <= 32 four CTAs of 256 threads with 4096-slot tables and bins half as large were measured: no gain.)
 static int bin_threads_env(int dflt, int other)
 {
     const char *e = getenv("HSK_BIN_THREADS");
@@ -95,7 +95,6 @@ static int bin_threads_env(int dflt, int other)
 
 int bin_target_kmers(int nwords, bool ext)
 {
-    if (nwords == 1 && !ext && bin_threads_env(512, 256) == 256) return BinCfg<1, false, 256>::TARGET;
     if (nwords == 1) return ext ? BinCfg<1, true, 512>::TARGET : BinCfg<1, false, 512>::TARGET;
     if (nwords == 2) return ext ? BinCfg<2, true, 512>::TARGET : BinCfg<2, false, 512>::TARGET;
     return BinCfg<3, false, 512>::TARGET;
@@ -131,6 +130,7 @@ struct BinSmem {
     u32 bin, nk, S, bail, next_batch, seen, ncand, skip_out;
     u32 pend_valid, pend_lb, pend_tk;                       // a sorted bin waiting in the CTA's global scratch for its place in the arena
     u32 xor_hi, xor_lo;                                     // bits in which the kept k-mers' first words differ
+    u16 wlo[Cfg::WARPS + 1], wo0[Cfg::WARPS + 1];           // de-duplicated bin: first (slot, k-mer in it) of every warp's share of the walk
     u32 batch_slots;                                        // slots per walk batch: 32, fewer when the bin has few slots
     int nsrc;                                               // sources of the walk: P.nsrc, or 1 when the bin was de-duplicated
     const u32 *mult;                                        // weight per slot (de-duplicated bins) or null
@@ -298,7 +298,7 @@ __device__ __forceinline__ void dedup_fetch(const BinSmem<NW, EXT, TH> &sm, u32 
 }
 
 template <int NW, bool EXT, int TH>
-__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 S,
+__device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT, TH> &sm, const BinParams &P, u32 S, int k,
                                          const uint4 (&vs)[BinCfg<NW, EXT, TH>::DDPT][BinCfg<NW, EXT, TH>::SW / 4])
 {
     using Cfg = BinCfg<NW, EXT, TH>;
@@ -350,15 +350,22 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT, TH> &sm, const BinPara
         atomicAdd(&wgt[idx], 1u);
     }
     __syncthreads();
-    // compact the used cells into the CTA's list
-    constexpr int PER = DDTS / TH;
-    u32 used = 0, mask = 0;
+    // compact the used cells into the CTA's list; the k-mers of the distinct slots are dealt out evenly to the warps
+    // of the walk: warp w starts with k-mer floor(w * total / WARPS) of the list, wherever in a slot that falls
+    constexpr int PER = DDTS / TH, PW = Cfg::PW, W = Cfg::WARPS;
+    u32 used = 0, mask = 0, ksum = 0, nk[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        if (cell[tid * PER + i] != BN_EMPTY32) { mask |= 1u << i; ++used; }
+        nk[i] = 0;
+        if (cell[tid * PER + i] != BN_EMPTY32) {
+            mask |= 1u << i; ++used;
+            const u32 lw = reinterpret_cast<const u32 *>(&dk[(tid * PER + i) * Q])[PW - 1];
+            nk[i] = (lw & 0xFFu) - (u32)k + 1;
+            ksum += nk[i];
+        }
     }
-    u32 ex, d0, total, d1;
-    block_scan2<TH>(used, 0u, sm.wa, sm.wb, ex, d0, total, d1);
+    u32 ex, kp, total, ktot;
+    block_scan2<TH>(used, ksum, sm.wa, sm.wb, ex, kp, total, ktot);
     uint4 *outs = P.dd_slots + (size_t)blockIdx.x * BN_DDLIMIT_MAX * Q;
     u32 *outm = P.dd_mult + (size_t)blockIdx.x * BN_DDLIMIT_MAX;
 #pragma unroll
@@ -367,9 +374,17 @@ __device__ __forceinline__ u32 dedup_bin(BinSmem<NW, EXT, TH> &sm, const BinPara
 #pragma unroll
             for (int x = 0; x < Q; ++x) __stcg(&outs[(size_t)ex * Q + x], dk[(tid * PER + i) * Q + x]);
             __stcg(&outm[ex], wgt[tid * PER + i]);
+            // warps whose first k-mer lies in this slot: floor(w * ktot / W) in [kp, kp + n)
+            for (u32 w = (kp * W + ktot - 1) / ktot; w < (u32)W; ++w) {
+                const u32 b = (u32)(((u64)w * ktot) / W);
+                if (b >= kp + nk[i]) break;
+                sm.wlo[w] = (u16)ex; sm.wo0[w] = (u16)(b - kp);
+            }
+            kp += nk[i];
             ++ex;
         }
     }
+    if (tid == 0) { sm.wlo[W] = (u16)total; sm.wo0[W] = 0; }
     return total;
 }
 
@@ -395,12 +410,24 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT, TH> &sm, const BinPara
     u32 pre_m = 1;
     const u32 *const mult = sm.mult;   // de-duplicated bin: slots come from the CTA's own list (written by this kernel:
                                        // coherent loads), each with the number of copies it stands for
-    const u32 BS = sm.batch_slots;
+    // de-duplicated bin: the warp walks its own share of the k-mers of the list (it may begin and end inside a slot);
+    // otherwise the warps take batches of slots by ticket
+    const bool ranged = !PASS2 && mult != nullptr;
+    u32 r_lo = 0, r_hi = 0, r_o0 = 0, r_o1 = 0, lim = S, next_j = 0;
+    if (ranged) {
+        r_lo = sm.wlo[warp]; r_o0 = sm.wo0[warp]; r_hi = sm.wlo[warp + 1]; r_o1 = sm.wo0[warp + 1];
+        lim = r_hi + (r_o1 ? 1u : 0u);
+        next_j = r_lo;
+    }
+    const u32 BS = ranged ? min((u32)Cfg::BATCH, max(1u, lim - r_lo)) : sm.batch_slots;   // slots per batch
     auto claim = [&](u32 &j0) {
-        u32 bt = 0;
-        if (lane == 0) bt = atomicAdd(&sm.next_batch, 1u);
-        j0 = __shfl_sync(0xFFFFFFFFu, bt, 0) * BS;
-        if ((u32)lane < BS && j0 + lane < S) {
+        if (ranged) { j0 = next_j; next_j += BS; }
+        else {
+            u32 bt = 0;
+            if (lane == 0) bt = atomicAdd(&sm.next_batch, 1u);
+            j0 = __shfl_sync(0xFFFFFFFFu, bt, 0) * BS;
+        }
+        if ((u32)lane < BS && j0 + lane < lim) {
             const uint4 *sp = reinterpret_cast<const uint4 *>(slot_ptr(sm, j0 + lane, SW));
             if (mult) {
 #pragma unroll
@@ -414,14 +441,20 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT, TH> &sm, const BinPara
     };
     u32 j0;
     claim(j0);
-    while (j0 < S) {
-        u32 n = 0, my_m = 1;
-        if ((u32)lane < BS && j0 + lane < S) {
+    while (j0 < lim) {
+        u32 n = 0, my_m = 1, start = 0;
+        if ((u32)lane < BS && j0 + lane < lim) {
 #pragma unroll
             for (int x = 0; x < SW / 4; ++x) stg4[lane * (SW / 4) + x] = pre[x];
             const uint4 v = pre[(PW - 1) / 4];
             const u32 lw = ((PW - 1) % 4 == 3) ? v.w : ((PW - 1) % 4 == 1 ? v.y : ((PW - 1) % 4 == 2 ? v.z : v.x));
             n = (lw & 0xFFu) - (u32)k + 1;
+            if (ranged) {   // the first / last slot of the warp's share may be cut
+                const u32 j = j0 + lane;
+                const u32 end = (j == r_hi) ? r_o1 : n;
+                start = (j == r_lo) ? r_o0 : 0u;
+                n = end - start;
+            }
             my_m = pre_m;
         }
         claim(j0);
@@ -434,7 +467,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT, TH> &sm, const BinPara
         const u32 T = __shfl_sync(0xFFFFFFFFu, inc, 31);
         const u32 ex = inc - n;
         const u32 rounds = (T + 31) >> 5;
-        scan[lane] = (u16)ex;
+        scan[lane] = (u16)(ex - start);   // k-mer g of the batch is k-mer g - scan (mod 2^16) of its slot
         for (u32 r = lane; r < rounds && r < (u32)Cfg::HEADW; r += 32) heads[r] = 0;
         __syncwarp();
         if (n) atomicOr(&heads[ex >> 5], 1u << (ex & 31));
@@ -446,7 +479,7 @@ __device__ __forceinline__ void walk_bin(BinSmem<NW, EXT, TH> &sm, const BinPara
             const u32 s = base + __popc(word & (0xFFFFFFFFu >> (31 - lane))) - 1;
             base += __popc(word);
             const bool act = g < T;
-            const u32 o = act ? g - scan[s] : 0u;
+            const u32 o = act ? ((g - scan[s]) & 0xFFFFu) : 0u;
             const u32 *w = stg + s * SW;
             const u32 wi = o >> 4, sh = 2 * (o & 15);
             u64 key[NW];
@@ -812,7 +845,7 @@ __global__ void __launch_bounds__(TH, BinCfg<NW, EXT, TH>::CTAS) k_bin_count(Bin
         __syncthreads();
         if constexpr (DEDUP) {
             if (dd) {
-                const u32 Sd = dedup_bin<NW, EXT, TH>(sm, P, S, ddv);
+                const u32 Sd = dedup_bin<NW, EXT, TH>(sm, P, S, k, ddv);
                 __syncthreads();   // the list is complete; the table memory goes back to the k-mers
                 {
                     const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
@@ -1195,7 +1228,6 @@ static_assert(sizeof(BinSmem<1, false, 512>) <= (233472 - 2 * 1024) / 2, "K <= 3
 static_assert(sizeof(BinSmem<1, true, 512>) <= (233472 - 3 * 1024) / 3, "K <= 32 with EXTENSION: three CTAs per SM");
 static_assert(sizeof(BinSmem<2, false, 512>) <= 232448 && sizeof(BinSmem<2, true, 512>) <= 232448 && sizeof(BinSmem<3, true, 512>) <= 232448, "K > 32: one CTA per SM");
 static_assert(sizeof(BinSmem<2, false, 1024>) <= 232448, "K in 33..64: one CTA of 1024 threads per SM");
-static_assert(sizeof(BinSmem<1, false, 256>) <= (233472 - 4 * 1024) / 4, "K <= 32: four CTAs of 256 threads per SM");
 constexpr int GL_THREADS = 512;                    // gather: listed bins with more kept k-mers than a CTA sorts itself
 
 template <int NW, bool EXT, int TH>
@@ -1230,7 +1262,7 @@ cudaError_t launch_bin_count(const BinParams &P, int nwords, bool ext, int sm_co
     if (P.nbins == 0) return cudaSuccess;
     if (nwords == 1) {
         if (ext) return launch_bins_t<1, true, 512>(P, sm_count, s);
-        return bin_threads_env(512, 256) == 256 ? launch_bins_t<1, false, 256>(P, sm_count, s) : launch_bins_t<1, false, 512>(P, sm_count, s);
+        return launch_bins_t<1, false, 512>(P, sm_count, s);
     }
     if (nwords == 2) {
         if (ext) return launch_bins_t<2, true, 512>(P, sm_count, s);

@@ -173,58 +173,72 @@ class HostPool {
 public:
     explicit HostPool(unsigned nthreads) : n_(std::max(1u, nthreads))
     {
-        for (unsigned t = 1; t < n_; ++t) workers_.emplace_back([this, t] { run(t); });
+        for (unsigned t = 0; t < n_; ++t) workers_.emplace_back([this] { run(); });
     }
     ~HostPool()
     {
+        wait();
         { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
         cv_.notify_all();
         for (auto &w : workers_) w.join();
     }
-    void parallel_for(u64 n, const std::function<void(u64, u64)> &fn)
+    unsigned size() const { return n_; }
+    // one job at a time: items 0 .. nitems-1 are handed to the threads in order; returns at once
+    void start(u64 nitems, std::function<void(u64)> fn)
     {
-        if (n_ == 1 || n < 2) { if (n) fn(0, n); return; }
+        wait();
+        if (nitems == 0) return;
         {
             std::lock_guard<std::mutex> l(m_);
-            fn_ = &fn; total_ = n; left_ = n_ - 1; ++gen_;
+            fn_ = std::move(fn); total_ = nitems; next_.store(0); active_ = n_; running_ = true; ++gen_;
         }
         cv_.notify_all();
-        fn(0, n / n_);
+    }
+    void wait()
+    {
         std::unique_lock<std::mutex> l(m_);
-        done_.wait(l, [this] { return left_ == 0; });
-        fn_ = nullptr;
+        done_.wait(l, [this] { return !running_; });
+    }
+    // [0, n) in contiguous pieces, a few per thread; returns when all are done
+    void parallel_for(u64 n, const std::function<void(u64, u64)> &fn)
+    {
+        if (n == 0) return;
+        if (n_ == 1 || n < 2) { fn(0, n); return; }
+        const u64 pieces = std::min<u64>(n, (u64)n_ * 2);
+        start(pieces, [&fn, n, pieces](u64 i) { fn(n * i / pieces, n * (i + 1) / pieces); });
+        wait();
     }
 private:
-    void run(unsigned t)
+    void run()
     {
         u64 seen = 0;
         while (true) {
-            const std::function<void(u64, u64)> *fn;
-            u64 n;
             {
                 std::unique_lock<std::mutex> l(m_);
                 cv_.wait(l, [&] { return gen_ != seen; });
                 seen = gen_;
                 if (stop_) return;
-                fn = fn_; n = total_;
             }
-            (*fn)(n * t / n_, n * (t + 1) / n_);
-            { std::lock_guard<std::mutex> l(m_); if (--left_ == 0) done_.notify_one(); }
+            for (u64 i = next_.fetch_add(1); i < total_; i = next_.fetch_add(1)) fn_(i);
+            { std::lock_guard<std::mutex> l(m_); if (--active_ == 0) { running_ = false; done_.notify_all(); } }
         }
     }
     unsigned n_;
     std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_, done_;
-    const std::function<void(u64, u64)> *fn_ = nullptr;
+    std::function<void(u64)> fn_;
+    std::atomic<u64> next_{0};
     u64 total_ = 0, gen_ = 0;
-    unsigned left_ = 0;
-    bool stop_ = false;
+    unsigned active_ = 0;
+    bool running_ = false, stop_ = false;
 };
 
 // hsk_count_stream: parts of the result that have reached the page-locked host arrays are handed to the caller's sink by
 // a few threads of the context (one part per thread at a time) while the GPU works on the rest.
-struct SinkPart { u64 first, n, first_occ, n_occ, hint; cudaEvent_t ready; };
+// occurrences of a part: [occ0, occ1); ~0 = read it from the occurrence offsets of the entries once they have arrived
+struct SinkPart { u64 first, n, occ0, occ1, hint; cudaEvent_t ready; };
+constexpr u64 SINK_SUBPART = 1ull << 16;   // entries per delivery: small enough for the last ones to be short
 class SinkPool {
 public:
     explicit SinkPool(unsigned nthreads)
@@ -271,7 +285,11 @@ private:
             if (dev_set != device) { cudaSetDevice(device); dev_set = device; }
             int rc = 0;
             if (p.ready && cudaEventSynchronize(p.ready) != cudaSuccess) rc = 2;
-            if (!rc && !skip && fn) rc = fn(user, view, p.first, p.n, p.first_occ, p.n_occ, p.hint);
+            if (!rc && !skip && fn) {
+                const u64 o0 = p.occ0 != ~0ull ? p.occ0 : view->occ_off[p.first];
+                const u64 o1 = p.occ1 != ~0ull ? p.occ1 : view->occ_off[p.first + p.n];
+                rc = fn(user, view, p.first, p.n, o0, o1 - o0, p.hint);
+            }
             {
                 std::lock_guard<std::mutex> l(m_);
                 if (rc && !rc_) rc_ = rc;
@@ -306,7 +324,7 @@ struct hsk_ctx {
     // input staging (hsk_count)
     DevBuf d_packed, d_read_off, d_read_len, d_len64, d_rtscratch;
     // host pipeline of hsk_count: chunks of the packed reads in flight (tile bound + event), result streaming
-    struct InChunk { u64 tile_end; cudaEvent_t ready; u64 off, n; };
+    struct InChunk { u64 tile_end; cudaEvent_t ready; u64 off, n; u32 pieces; };
     std::vector<InChunk> in_chunks;
     bool stream_result = false;          // hsk_count: results go to the host buffers group by group
     u32 *d_in_flags = nullptr;           // hsk_count: read table checks (reads.cu), looked at after the first sync
@@ -334,13 +352,18 @@ struct hsk_ctx {
     hsk_sink_fn sink_fn = nullptr;
     void *sink_user = nullptr;
     hsk_result sink_view;
-    // pageable input: chunks are copied into a ring of page-locked buffers by the pool, then sent
-    static constexpr int RING = 3;
-    HostBuf h_ring[RING], h_len;
-    cudaEvent_t ring_free[RING] = {nullptr, nullptr, nullptr};
+    // pageable input: pieces of the buffer are copied into a ring of page-locked buffers by the pool's threads, each of
+    // which then sends its piece itself (stage_input / stage_chunk)
+    static constexpr u64 PIECE = 1ull << 20;
+    HostBuf h_ring, h_len;
+    std::vector<cudaEvent_t> ring_free;              // per ring slot: its last piece has left
+    std::unique_ptr<std::atomic<u32>[]> piece_enq;   // per piece: copy + event enqueued
+    std::unique_ptr<std::atomic<u32>[]> chunk_done;  // per extraction chunk: pieces enqueued
+    size_t flags_cap = 0;
     const u8 *in_host = nullptr;
     bool in_pageable = false;
-    size_t in_staged = 0;
+    std::atomic<int> stage_err{0};
+    std::atomic<long long> stage_ns[3];              // HSK_TRACE: time of the staging threads in memcpy / CUDA calls / waiting
     // extraction state between the count pass and the scatter pass
     ExtractParams xp;
     u32 x_nctas = 0;
@@ -488,7 +511,8 @@ void hsk_destroy(hsk_ctx *c)
     barrier();
     if (c->comm) g_nccl.CommDestroy(c->comm);
     for (auto &r : c->retired) r.release();
-    for (int r = 0; r < hsk_ctx::RING; ++r) { c->h_ring[r].release(); if (c->ring_free[r]) cudaEventDestroy(c->ring_free[r]); }
+    c->h_ring.release();
+    for (auto e : c->ring_free) cudaEventDestroy(e);
     c->h_len.release();
     DevBuf *db[] = {&c->d_packed, &c->d_read_off, &c->d_read_len, &c->d_len64, &c->d_rtscratch, &c->d_run_list, &c->d_tile_hdr, &c->d_tile_read, &c->d_bscratch, &c->d_bucket, &c->d_slots,
                     &c->d_alltot, &c->d_rslots, &c->d_seg, &c->d_lb, &c->d_peerinfo, &c->d_dd, &c->d_pend, &c->d_grp, &c->d_val[0], &c->d_val[1], &c->d_rscratch,
@@ -1111,7 +1135,14 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
         if (sinking && (nk || last)) {
             cudaEvent_t arrived = c->ev();
             CK(cudaEventRecord(arrived, cs));
-            c->sink->push({sent_kept, nk, sent_occ, no, last ? kept_end : std::max<u64>(kept_end, kept_total_hint), arrived});
+            const u64 hint = last ? kept_end : std::max<u64>(kept_end, kept_total_hint);
+            u64 f = sent_kept;
+            do {   // pieces of SINK_SUBPART entries, each to whichever delivery thread is free
+                const u64 n = std::min<u64>(SINK_SUBPART, kept_end - f);
+                const bool head = f == sent_kept, tail = f + n == kept_end;
+                c->sink->push({f, n, !ext ? 0 : (head ? sent_occ : ~0ull), !ext ? 0 : (tail ? occ_end : ~0ull), hint, arrived});
+                f += n;
+            } while (f < kept_end);
         }
         sent_kept = kept_end; sent_occ = occ_end;
         return 0;
@@ -1303,24 +1334,25 @@ static bool is_pageable(const void *p)
     return at.type == cudaMemoryTypeUnregistered;
 }
 
+// pageable input: waits until the pool's threads have copied extraction chunk ci into its ring slot and sent it (the
+// thread that finishes the last piece of a chunk enqueues the chunk's one H2D copy and records its event)
 static int stage_chunk(hsk_ctx *c, size_t ci)
 {
-    if (!c->in_pageable || ci < c->in_staged) return 0;
-    for (; c->in_staged <= ci; ++c->in_staged) {
-        const hsk_ctx::InChunk &ch = c->in_chunks[c->in_staged];
-        const int slot = (int)(c->in_staged % hsk_ctx::RING);
-        if (c->in_staged >= (size_t)hsk_ctx::RING) CK(cudaEventSynchronize(c->ring_free[slot]));   // its previous chunk has left
-        u8 *dst = c->h_ring[slot].as<u8>();
-        const u8 *src = c->in_host + ch.off;
-        c->pool->parallel_for((ch.n + 4095) / 4096, [=](u64 lo, u64 hi) {
-            const u64 b0 = lo * 4096, b1 = std::min<u64>(hi * 4096, ch.n);
-            if (b1 > b0) memcpy(dst + b0, src + b0, b1 - b0);
-        });
-        CK(cudaMemcpyAsync(c->d_packed.as<u8>() + ch.off, dst, ch.n, cudaMemcpyHostToDevice, c->copy_stream));
-        CK(cudaEventRecord(ch.ready, c->copy_stream));
-        CK(cudaEventRecord(c->ring_free[slot], c->copy_stream));
-        if (c->in_staged + 1 == c->in_chunks.size()) CK(cudaEventRecord(c->ev_h2d[1], c->copy_stream));
+    if (!c->in_pageable) return 0;
+    while (!c->piece_enq[ci].load(std::memory_order_acquire)) {
+        if (c->stage_err.load()) return fail("staging the input failed: %s", cudaGetErrorString((cudaError_t)c->stage_err.load()));
+        std::this_thread::yield();
     }
+    if (c->stage_err.load()) return fail("staging the input failed: %s", cudaGetErrorString((cudaError_t)c->stage_err.load()));
+    if (ci + 1 == c->in_chunks.size()) {
+        CK(cudaEventRecord(c->ev_h2d[1], c->copy_stream));
+        if (g_trace.on) {
+            char msg[200];
+            snprintf(msg, sizeof(msg), "all input chunks staged + enqueued (threads: %.3f ms in memcpy, %.3f ms in CUDA calls, %.3f ms waiting for ring slots)",
+                     c->stage_ns[0].load() * 1e-6, c->stage_ns[1].load() * 1e-6, c->stage_ns[2].load() * 1e-6);
+            g_trace.mark(msg);
+        }
+    } else if (ci == 0) g_trace.mark("first input chunk staged");
     return 0;
 }
 
@@ -1338,7 +1370,6 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
     c->d_in_flags = reinterpret_cast<u32 *>(c->d_rtscratch.as<u8>() + rts);
     c->in_pageable = nbytes > 0 && is_pageable(packed);
     c->in_host = packed;
-    c->in_staged = 0;
     CK(cudaMemsetAsync(c->d_in_flags, 0, 16, s));
     if (nreads) {
         const uint64_t *lens = read_len;
@@ -1363,13 +1394,9 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
     c->ev_h2d[0] = e0; c->ev_h2d[1] = e1;   // ms_h2d is read after the call has synchronised
     CK(cudaEventRecord(e0, cs));
     CK(cudaMemsetAsync(c->d_packed.as<u8>() + (nbytes & ~15ull), 0, padded - (nbytes & ~15ull), cs));
-    u64 chunk = std::min<u64>(std::max<u64>((nbytes / 8 + 4095) & ~4095ull, 2ull << 20), c->in_pageable ? (16ull << 20) : (256ull << 20));
-    if (c->in_pageable) {
-        for (int r = 0; r < hsk_ctx::RING; ++r) {
-            CK(c->h_ring[r].ensure(std::min<u64>(chunk, nbytes)));
-            if (!c->ring_free[r]) CK(cudaEventCreateWithFlags(&c->ring_free[r], cudaEventDisableTiming));
-        }
-    }
+    const u64 PIECE = hsk_ctx::PIECE;
+    u64 chunk = std::min<u64>(std::max<u64>((nbytes / 8 + 4095) & ~4095ull, 2ull << 20), 256ull << 20);
+    if (c->in_pageable) chunk = (std::min<u64>(chunk, 32ull << 20) + PIECE - 1) / PIECE * PIECE;   // ring slots of whole pieces
     for (u64 o = 0; o < nbytes; o += chunk) {
         const u64 n = std::min<u64>(chunk, nbytes - o);
         cudaEvent_t ev = c->ev();
@@ -1378,14 +1405,71 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
             CK(cudaEventRecord(ev, cs));
         }
         const u64 words = (o + n) / 4;   // a tile reads 34 words from its first one
-        c->in_chunks.push_back({words >= 34 ? (words - 34) / OL + 1 : 0, ev, o, n});
+        c->in_chunks.push_back({words >= 34 ? (words - 34) / OL + 1 : 0, ev, o, n, (u32)((n + PIECE - 1) / PIECE)});
     }
-    if (!c->in_pageable || nbytes == 0) CK(cudaEventRecord(e1, cs));
+    if (!c->in_pageable || nbytes == 0) { CK(cudaEventRecord(e1, cs)); return 0; }
+
+    // pageable: the pool's threads take 1 MiB pieces in order and copy them into the ring slot of their extraction chunk;
+    // whoever completes a chunk sends it with ONE cudaMemcpyAsync (a copy per piece costs ~50 us of fixed latency each on
+    // this platform) and records the chunk's event.  A slot is reused once the chunk that used it before has left.
+    const u64 npieces = (nbytes + PIECE - 1) / PIECE;
+    const u64 nchunks = c->in_chunks.size();
+    const u64 nring = std::min<u64>(nchunks, 4);
+    CK(c->h_ring.ensure(nring * chunk));
+    while (c->ring_free.size() < nring) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ring_free.push_back(e);
+    }
+    if (c->flags_cap < nchunks) {
+        c->flags_cap = nchunks * 2;
+        c->piece_enq.reset(new std::atomic<u32>[c->flags_cap]);    // per chunk: its copy + event are enqueued
+        c->chunk_done.reset(new std::atomic<u32>[c->flags_cap]);   // per chunk: pieces copied into the slot
+    }
+    for (u64 i = 0; i < nchunks; ++i) { c->piece_enq[i].store(0, std::memory_order_relaxed); c->chunk_done[i].store(0, std::memory_order_relaxed); }
+    c->stage_err.store(0);
+    for (auto &x : c->stage_ns) x.store(0);
+    const bool timing = g_trace.on;
+    const u64 ppc = chunk / PIECE;
+    const int device = c->cfg.device;
+    c->pool->start(npieces, [c, nring, nbytes, PIECE, ppc, chunk, device, timing](u64 j) {
+        auto tick = [] { return std::chrono::steady_clock::now(); };
+        auto ns = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count();
+        };
+        const auto t0 = tick();
+        static thread_local int dev_set = -1;
+        if (dev_set != device) { cudaSetDevice(device); dev_set = device; }
+        const u64 ci = j / ppc, slot = ci % nring, off = j * PIECE, n = std::min<u64>(PIECE, nbytes - off);
+        const hsk_ctx::InChunk &ch = c->in_chunks[ci];
+        cudaError_t e = cudaSuccess;
+        if (ci >= nring && !c->stage_err.load(std::memory_order_relaxed)) {
+            // the chunk that used the slot before must have left (pieces are taken in order: all of its pieces were taken earlier)
+            while (!c->piece_enq[ci - nring].load(std::memory_order_acquire)) std::this_thread::yield();
+            e = cudaEventSynchronize(c->ring_free[slot]);
+        }
+        u8 *dst = c->h_ring.as<u8>() + slot * chunk;
+        const auto t1 = tick();
+        if (e == cudaSuccess && !c->stage_err.load(std::memory_order_relaxed)) memcpy(dst + (off - ch.off), c->in_host + off, n);
+        const auto t2 = tick();
+        if (e != cudaSuccess) c->stage_err.store((int)e);
+        if (c->chunk_done[ci].fetch_add(1, std::memory_order_acq_rel) + 1 == ch.pieces) {   // the chunk is complete: send it
+            if (!c->stage_err.load()) {
+                e = cudaMemcpyAsync(c->d_packed.as<u8>() + ch.off, dst, ch.n, cudaMemcpyHostToDevice, c->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ch.ready, c->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(c->ring_free[slot], c->copy_stream);
+                if (e != cudaSuccess) c->stage_err.store((int)e);
+            }
+            c->piece_enq[ci].store(1, std::memory_order_release);
+        }
+        if (timing) { const auto t3 = tick(); c->stage_ns[0] += ns(t1, t2); c->stage_ns[1] += ns(t2, t3); c->stage_ns[2] += ns(t0, t1); }
+    });
     return 0;
 }
 
 static void end_input(hsk_ctx *c)
 {
+    if (c->pool) c->pool->wait();   // (an error may have left the staging job running)
     c->in_chunks.clear();
     c->d_in_flags = nullptr;
     c->in_host = nullptr;
@@ -1427,6 +1511,12 @@ int hsk_count_stream(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const u
     g_trace.mark("hsk_count end");
     c->stats.n_launches += staged_launches;
     CK(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_h2d[0], c->ev_h2d[1]));
+    if (g_trace.on) {
+        char msg[200];
+        snprintf(msg, sizeof(msg), "device: h2d %.3f ms, extract %.3f ms, bins %.3f ms, d2h %.3f ms, first kernel to last %.3f ms", c->stats.ms_h2d,
+                 c->stats.ms_extract, c->stats.ms_bins, c->stats.ms_d2h, c->stats.ms_total);
+        g_trace.mark(msg);
+    }
     const bool ext = c->cfg.ext != 0;
     out->nwords = c->nwords;
     out->n_kept = c->n_kept;

@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+TAG=${1:-r2g}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+b() { name=$1; shift; timeout 900 python bench.py "$@" > $OUT/bench_$name.json 2> $OUT/bench_$name.err; echo -n "$name: "; python tools/bench_brief.py $OUT/bench_$name.json || tail -5 $OUT/bench_$name.err; }
+for ht in 16 4; do
+HSK_HOST_THREADS=$ht HSK_TRACE=1 b c2_trace_h$ht --steps 3 --warmup 2 --no-cpu-baseline --no-parity; grep "hsk trace" $OUT/bench_c2_trace_h$ht.err | grep -v "bin group" | tail -12 > $OUT/trace_c2_h$ht.txt; cat $OUT/trace_c2_h$ht.txt
+done
+grep "hsk trace" $OUT/bench_c2_trace_h16.err | grep -B3 -A12 "hsk_count begin" | head -120 > $OUT/trace_full_h16.txt
