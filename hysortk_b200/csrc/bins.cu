@@ -7,28 +7,34 @@
 //   count_sorted_kmers                        (src/kmerops.cpp:1410-1445), histogram (hysortk.cpp:106-113)
 //
 // The reference sorts every k-mer occurrence and then run-length counts.  At 30x coverage a bin of
-// ~3000 occurrences holds only ~100 genomic k-mers x 30 copies plus error singletons, and all of
-// them are overlapping windows of a few loci (they share minimizers), so their leading bases take
-// few values: sorting the occurrences is both unbalanced (30-copy lumps) and wasted work.  Here:
-//
-//   k_bin_count   (one CTA per bin, bins taken in index order through a ticket)
-//     1. warps take batches of 32 consecutive supermer slots of the bin; a warp scan of the k-mers per slot and
-//        a bitmap of the slot starts map k-mer g of the batch to (slot, offset), so that in every round each
-//        lane extracts ONE k-mer directly from the staged slot words (funnel shift, reverse complement by bit
-//        reversal, canonical choice) — no per-thread walk, no divergence on supermer boundaries
-//     2. the k-mer is inserted into an open-addressing table in shared memory: for K <= 32 the cell is the
-//        k-mer itself (one 64-bit CAS, and only when a plain load did not already find it); for K > 32 a
-//        32-bit fingerprint cell guards the full key words (claim = EMPTY -> LOCK -> words -> fingerprint), and
-//        every fingerprint match is confirmed on the full words, so the table is exact.  A 32-bit counter per
-//        slot counts the occurrences
-//     3. every thread filters its slots with LOWER <= count <= UPPER, a block scan compacts the kept
-//        (k-mer, count) pairs and they are written to a staging area at an atomically claimed offset
-//     4. EXTENSION: the counters of the kept slots become cursors into the bin's occurrence area and a second
-//        walk over the bin places (pos, rid) of every occurrence of a kept k-mer
-//   k_bin_offsets  exclusive scan of the per-bin kept / occurrence totals -> final positions
-//   k_bin_gather   (one CTA per bin) sorts the bin's kept k-mers by key (bitonic sort in shared
-//                  memory over the few distinct kept keys) and writes them, with their occurrence
-//                  lists, to the final arena.
+// ~8000 occurrences holds only ~270 genomic k-mers x 30 copies plus error singletons, and all of
+// them are overlapping windows of a few loci (they share minimizers): sorting the occurrences is both
+// unbalanced (30-copy lumps) and wasted work.  Here, k_bin_count (one CTA per bin, bins taken in index
+// order through a ticket, every CTA resident):
+//   0. (K <= 64 without EXTENSION) identical supermer slots of the bin are merged first (dedup_bin): a supermer
+//      that was read 20 times is expanded once, with weight 20; the k-mers of the distinct slots are then dealt
+//      out to the warps in equal shares (a share may begin and end inside a slot)
+//   1. walk: a warp stages batches of up to 32 supermer slots; a warp scan of the k-mers per slot and a bitmap of
+//      the slot starts map k-mer g of the batch to (slot, offset), so that in every round each lane extracts ONE
+//      k-mer directly from the staged slot words (funnel shift, reverse complement by bit reversal, canonical
+//      choice) — no per-thread walk, no divergence on supermer boundaries
+//   2. count: the k-mer is inserted into an open-addressing table in shared memory: for K <= 32 the cell is the
+//      k-mer itself (one 64-bit CAS, and only when a plain load did not already find it); for K > 32 a
+//      32-bit fingerprint cell guards the full key words (claim = EMPTY -> LOCK -> words -> fingerprint), and
+//      every fingerprint match is confirmed on the full words, so the table is exact.  A 32-bit counter per
+//      slot counts the occurrences; the occurrence that lifts a counter to LOWER lists the slot as a candidate
+//   3. filter: candidates with LOWER <= count <= UPPER are kept; the bin publishes how many (look-back cell)
+//   4. sort: the kept k-mers of the bin in ascending order (sort_bin: one counting pass over the most
+//      significant differing byte + rank inside the bucket; only slot numbers move)
+//   5. emit: without EXTENSION the sorted (k-mer, count) entries are parked in the CTA's scratch (stash_bin) and
+//      move to their place in the arena — known from a decoupled look-back over the bins before — while the
+//      CTA already works on its next bin (flush_pending), so that nobody waits for the slowest bin in flight.
+//      With EXTENSION the place is resolved at once (emit_now), the counters of the kept slots become cursors
+//      into the bin's occurrence area and a second walk places (pos, rid) of every occurrence of a kept k-mer
+//   6. the CTA that completes a group of bins reports the arena cursor to page-locked host memory: the host
+//      streams that part of the result out while the kernel keeps counting (engine.cu)
+// A bin that keeps more than BN_SORTCAP k-mers goes unsorted to a staging area and is sorted + moved by
+// k_bin_gather afterwards (or takes the HBM path when the staging area is full).
 //
 // So the SORT is still there, but it runs over the distinct kept k-mers (D) instead of over every
 // occurrence (N): D/N is ~4 % at 30x coverage with 1 % errors.  The arena holds the bins in index order
