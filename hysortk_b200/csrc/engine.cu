@@ -126,9 +126,11 @@ Trace g_trace;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool view = false;   // p points into another allocation (set_view): never freed, never grown
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        if (view) return cudaErrorMemoryAllocation;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 16 + 256;
@@ -136,7 +138,17 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    // exactly `bytes` (no slack): for the one block that takes most of the free memory
+    cudaError_t ensure_exact(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void set_view(void *q, size_t bytes) { if (p && !view) cudaFree(p); p = q; cap = bytes; view = true; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; cap = 0; view = false; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -407,7 +419,11 @@ struct hsk_ctx {
     HostBuf h_cursor, h_owords, h_ocnt, h_oocc_off, h_opos, h_orid, h_hist;
     u64 n_kept = 0, n_occ = 0;
     bool have_result = false;
-    bool arena_capped = false;           // the last call gave the run list's memory to the arena (memory was short)
+    // memory-short mode: ONE block holds the run list during the extraction and the arena + staging area afterwards
+    DevBuf d_big;
+    bool big_mode = false;
+    u64 big_budget = 0;                  // HSK_ARENA_BUDGET_MB (tests) that sized the block, 0: the free memory did
+    u64 *run_list = nullptr;             // the run list of this call: d_run_list, or the start of d_big
     hsk_stats stats;
 
     std::vector<u64> h_dbg;
@@ -543,6 +559,7 @@ void hsk_destroy(hsk_ctx *c)
     barrier();
     if (c->comm) g_nccl.CommDestroy(c->comm);
     for (auto &r : c->retired) r.release();
+    c->d_big.release();
     c->h_ring.release();
     for (auto e : c->ring_free) cudaEventDestroy(e);
     c->h_len.release();
@@ -643,7 +660,8 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
     CK(launch_tile_reads(P, c->d_tile_read.as<u32>(), s));
     c->stats.n_launches += 1;
     for (int attempt = 0;; ++attempt) {
-        CK(c->d_run_list.ensure(run_cap * 8));
+        if (c->big_mode && run_cap * 8 <= c->d_big.cap) c->run_list = c->d_big.as<u64>();   // (the arena of the last call is over)
+        else { CK(c->d_run_list.ensure(run_cap * 8)); c->run_list = c->d_run_list.as<u64>(); }
         CK(cudaMemsetAsync(d_tot, 0, (host_u64 + XT_META) * 8, s));
         // pass A over the tiles whose bytes have arrived (hsk_count uploads the reads in chunks); a retry and
         // hsk_count_device see the whole buffer at once
@@ -660,7 +678,7 @@ static int extract_count(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_
             if (te <= tb) continue;
             P.tile_begin = tb; P.tile_end = te;
             P.tiles_per_warp = (u32)((te - tb + nwarps - 1) / nwarps);
-            CK(launch_supermer_count(P, nctas, d_tot, c->d_run_list.as<u64>(), c->d_tile_hdr.as<ulonglong2>(), d_runcur, run_cap, s));
+            CK(launch_supermer_count(P, nctas, d_tot, c->run_list, c->d_tile_hdr.as<ulonglong2>(), d_runcur, run_cap, s));
             c->stats.n_launches += 1;
             tb = te;
         }
@@ -707,7 +725,7 @@ static int extract_scatter(hsk_ctx *c, u64 *d_cur)
     const u64 nwarps = (u64)nctas * XT_WARPS;
     P.tiles_per_warp = (u32)((P.ntiles + nwarps - 1) / nwarps);
     c->begin(c->ev_extract);
-    if (P.ntiles) CK(launch_supermer_scatter(P, nctas, c->nwords, c->cfg.ext != 0, c->d_run_list.as<u64>(),
+    if (P.ntiles) CK(launch_supermer_scatter(P, nctas, c->nwords, c->cfg.ext != 0, c->run_list,
                                              c->d_tile_hdr.as<ulonglong2>(), d_cur, s));
     c->end(c->ev_extract);
     g_trace.mark("scatter enqueued");
@@ -837,12 +855,6 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.ms_h2d = keep.ms_h2d;
     c->have_result = false;
-    if (c->arena_capped) {
-        // memory was short in the last call: the arena took what the run list had given back; the run list comes first again
-        DevBuf *rel[] = {&c->d_owords, &c->d_ocnt, &c->d_swords, &c->d_scnt, &c->d_oocc_off, &c->d_opos, &c->d_orid, &c->d_spos, &c->d_srid};
-        for (auto *r : rel) r->release();
-        c->arena_capped = false;
-    }
     cudaEvent_t ev_t0 = c->ev(), ev_t1 = c->ev();
     CK(cudaEventRecord(ev_t0, s));
 
@@ -1032,33 +1044,62 @@ static int count_device(hsk_ctx *c, const u8 *d_packed, u64 nbytes, u64 nbytes_p
     {
         const size_t ent_b = (size_t)NW * 8 + 4 + (ext ? 8 : 0);
         const size_t need = 2 * (size_t)bound * ent_b + (ext ? 2 * (size_t)(owned + 8) * 8 : 0);
-        const size_t have = c->d_owords.cap + c->d_ocnt.cap + c->d_swords.cap + c->d_scnt.cap + c->d_oocc_off.cap + c->d_opos.cap +
-                            c->d_orid.cap + c->d_spos.cap + c->d_srid.cap;
-        size_t free_b = 0, total_b = 0;
         u64 budget = 0;
         if (const char *ev = getenv("HSK_ARENA_BUDGET_MB")) budget = strtoull(ev, nullptr, 10) << 20;   // tests
-        if (need > have && !budget) CK(cudaMemGetInfo(&free_b, &total_b));   // (a slow driver call: only when something has to grow)
-        if (budget || (need > have && (double)(need + need / 16) > 0.92 * (double)(free_b + have))) {
+        DevBuf *ar[] = {&c->d_owords, &c->d_ocnt, &c->d_swords, &c->d_scnt, &c->d_oocc_off, &c->d_opos, &c->d_orid, &c->d_spos, &c->d_srid};
+        if (c->big_mode && c->big_budget != budget) {
+            // (tests) the block was sized by HSK_ARENA_BUDGET_MB and the setting changed: start over.  The scatter pass, which
+            // may be reading the run list in the block, is complete after the synchronisation.
             CK(cudaStreamSynchronize(s));
-            DevBuf *rel[] = {&c->d_run_list, &c->d_tile_hdr, &c->d_owords, &c->d_ocnt, &c->d_swords, &c->d_scnt, &c->d_oocc_off,
-                             &c->d_opos, &c->d_orid, &c->d_spos, &c->d_srid};
-            for (auto *r : rel) r->release();
-            CK(cudaMemGetInfo(&free_b, &total_b));
-            if (!budget) budget = (u64)(0.85 * (double)free_b);
-            if (!ext) {
-                arena_cap = std::min<u64>(bound, budget / 9 * 8 / ent_b);
-                stage_cap = std::min<u64>(bound, budget / 9 / ent_b);
-            } else {
-                arena_cap = std::min<u64>(bound, budget / 100 * 40 / ent_b);
-                stage_cap = std::min<u64>(bound, budget / 100 * 10 / ent_b);
-                occ_cap = std::min<u64>(owned + 8, budget / 100 * 40 / 8);
-                stage_occ_cap = std::min<u64>(owned + 8, budget / 100 * 10 / 8);
+            for (auto *r : ar) r->release();
+            c->d_big.release();
+            c->big_mode = false;
+        }
+        if (!c->big_mode) {
+            size_t have = 0, free_b = 0, total_b = 0;
+            for (auto *r : ar) have += r->cap;
+            if (need > have && !budget) CK(cudaMemGetInfo(&free_b, &total_b));   // (a slow driver call: only when something has to grow)
+            if (budget || (need > have && (double)(need + need / 16) > 0.92 * (double)(free_b + have))) {
+                // enter the memory-short mode: from now on the run list and the arena share one block
+                CK(cudaStreamSynchronize(s));
+                c->d_run_list.release();
+                for (auto *r : ar) r->release();
+                CK(cudaMemGetInfo(&free_b, &total_b));
+                CK(c->d_big.ensure_exact(budget ? (size_t)budget : (size_t)(0.85 * (double)free_b)));
+                c->big_mode = true;
+                c->big_budget = budget;
+                g_trace.mark("memory is short: the run list and the arena share one block from now on");
             }
-            c->arena_capped = true;
-            g_trace.mark("memory is short: run list released, arena capped");
+        }
+        if (c->big_mode) {
+            // the arena is laid out in the block (the scatter pass, which reads the run list there, is ahead of the bin
+            // kernel on the stream); the kernels check the limits
+            const u64 B = c->d_big.cap > 8192 ? c->d_big.cap - 8192 : 0;
+            if (!ext) {
+                arena_cap = std::min<u64>(bound, B / 9 * 8 / ent_b);
+                stage_cap = std::min<u64>(bound, B / 9 / ent_b);
+            } else {
+                arena_cap = std::min<u64>(bound, B / 100 * 40 / ent_b);
+                stage_cap = std::min<u64>(bound, B / 100 * 10 / ent_b);
+                occ_cap = std::min<u64>(owned + 8, B / 100 * 40 / 8);
+                stage_occ_cap = std::min<u64>(owned + 8, B / 100 * 10 / 8);
+            }
+            u8 *at = c->d_big.as<u8>();
+            auto carve = [&](DevBuf &b, size_t bytes) { b.set_view(at, bytes); at += (bytes + 255) & ~(size_t)255; };
+            carve(c->d_owords, arena_cap * NW * 8);
+            carve(c->d_ocnt, arena_cap * 4);
+            carve(c->d_swords, stage_cap * NW * 8);
+            carve(c->d_scnt, stage_cap * 4);
+            if (ext) {
+                carve(c->d_oocc_off, (arena_cap + 1) * 8);
+                carve(c->d_opos, occ_cap * 4);
+                carve(c->d_orid, occ_cap * 4);
+                carve(c->d_spos, stage_occ_cap * 4);
+                carve(c->d_srid, stage_occ_cap * 4);
+            }
+            if ((size_t)(at - c->d_big.as<u8>()) > c->d_big.cap) return fail("internal: arena layout exceeds its block");
         }
     }
-    // exact sizes when capped (DevBuf::ensure adds slack)
     CK(c->d_owords.ensure(arena_cap * NW * 8));
     CK(c->d_ocnt.ensure(arena_cap * 4));
     CK(c->d_swords.ensure(stage_cap * NW * 8));
