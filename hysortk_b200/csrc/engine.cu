@@ -1349,7 +1349,14 @@ int hsk_count_device(hsk_ctx *c, const uint8_t *d_packed, uint64_t nbytes, const
     c->stats.ms_h2d = 0;
     c->ev_used = 0;
     end_input(c);
-    if (count_device(c, d_packed, nbytes, (nbytes + 15) & ~15ull, (const u64 *)d_read_off, d_read_len, nreads, readid_base)) return 1;
+    if (count_device(c, d_packed, nbytes, (nbytes + 15) & ~15ull, (const u64 *)d_read_off, d_read_len, nreads, readid_base)) {
+        const std::string msg = g_err;   // nothing of the failed call stays in flight; the first error is the one to report
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_stream);
+        (void)cudaGetLastError();
+        g_err = msg;
+        return 1;
+    }
     fill_device_result(c, out);
     return 0;
 }

@@ -375,9 +375,12 @@ std::unique_ptr<KmerListS> kmer_count(const DnaBuffer& mydna, MPI_Comm comm)
     MPI_Exscan(&numreads, &readoffset, 1, MPI_INT, MPI_SUM, comm);
     if (rank == 0) readoffset = 0;
 
+    /* read lengths as the C ABI takes them.  Kept between calls (a fresh 8 MB array per million reads would be first-touched
+     * every time) and filled by this thread alone: an OpenMP team here would keep spinning on the cores that the engine's
+     * host threads need a moment later */
     const size_t n = mydna.size();
-    std::vector<uint64_t> lens(n);
-    #pragma omp parallel for schedule(static) if (n > 65536)
+    static thread_local std::vector<uint64_t> lens;
+    lens.resize(n);
     for (size_t i = 0; i < n; ++i) lens[i] = mydna[i].size();
     const uint8_t *bytes = n ? mydna.getbufoffset(0) : nullptr;
     const size_t nbytes = n ? mydna.getrangebufsize(0, n) : 0;
