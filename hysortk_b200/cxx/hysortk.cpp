@@ -135,7 +135,11 @@ struct ListBuilder {
         try {
             {
                 std::lock_guard<std::mutex> l(mu);
-                if (!base) allocate(std::max<size_t>(first + n, hint));
+                if (!base) {
+                    size_t want = std::max<size_t>(first + n, hint);
+                    if (const char *t = std::getenv("HSK_TEST_LIST_HINT_DIV")) want = std::max<size_t>(first + n, want / std::max(1, std::atoi(t)));   /* tests: force the rebuild path */
+                    allocate(want);
+                }
                 if (first + n > cap) { overflow = true; return 0; }
                 if (n) done.emplace_back(first, n);
             }
@@ -167,8 +171,14 @@ struct ListBuilder {
         allocate(res.n_kept);
         const uint64_t n = res.n_kept, block = 16384;
         #pragma omp parallel for schedule(dynamic) num_threads(nthreads)
-        for (uint64_t b = 0; b < (n + block - 1) / block; ++b)
-            fill(&res, b * block, std::min(block, n - b * block), res.n_occ);
+        for (uint64_t b = 0; b < (n + block - 1) / block; ++b) {
+            const uint64_t first = b * block, cnt = std::min(block, n - first);
+#if EXTENSION == 1
+            fill(&res, first, cnt, res.occ_off[first + cnt]);   /* the complete result has the closing offset of every entry */
+#else
+            fill(&res, first, cnt, 0);
+#endif
+        }
         done.emplace_back(0, n);
     }
     /* the finished array becomes the storage of a std::vector */
