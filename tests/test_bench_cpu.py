@@ -34,3 +34,20 @@ def test_reference_arm_line():
 def test_reference_arm_other_ranks_are_silent():
     r = run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_config():
+    """`config` is what the workload IS: the reference arm prints the same dictionary our arm computes (the driver compares
+    them), whatever the number of ranks."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = run()
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    if "unavailable" in d:
+        return
+    assert d["config"] == bench.workload_config("tiny", 1)
+    c8 = bench.workload_config("c2_150Mbp_10kbp", 8)
+    assert c8["genome_len_total"] == 40_000_000 and c8["reads_per_gpu"] == 15_000 and c8["kmers_per_gpu"] == 149_550_000
+    assert bench.workload_config("c3_30Gbp", 8)["scaling"] == "strong" and bench.workload_config("c3_30Gbp", 8)["reads_per_gpu"] == 375_000
