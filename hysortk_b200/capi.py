@@ -17,7 +17,7 @@ SO_PATH = os.path.join(HERE, "libhysortk_b200.so")
 NCCL_ID_BYTES = 128
 
 EXPORTS = ["hsk_last_error", "hsk_version", "hsk_get_unique_id", "hsk_create", "hsk_destroy", "hsk_count",
-           "hsk_count_stream", "hsk_count_device", "hsk_fetch_result", "hsk_allreduce_histogram", "hsk_fill_entries", "hsk_debug_sort",
+           "hsk_count_stream", "hsk_count_device", "hsk_fetch_result", "hsk_host_register", "hsk_host_unregister", "hsk_allreduce_histogram", "hsk_fill_entries", "hsk_debug_sort",
            "hsk_debug_extract"]
 
 

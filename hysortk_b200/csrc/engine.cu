@@ -1624,6 +1624,25 @@ int hsk_count(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const uint64_t
     return hsk_count_stream(c, packed, nbytes, read_len, nreads, readid_base, nullptr, nullptr, out);
 }
 
+int hsk_host_register(void *p, size_t bytes, int32_t device)
+{
+    if (!p || !bytes) return fail("hsk_host_register: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { (void)cudaGetLastError(); return fail("hsk_host_register: no such device"); }
+    CK(cudaSetDevice(device));
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaHostRegister: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int hsk_host_unregister(void *p)
+{
+    if (!p) return fail("hsk_host_unregister: null argument");
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
 int hsk_allreduce_histogram(hsk_ctx *c, uint64_t *hist)
 {
     if (!c || !hist) return fail("hsk_allreduce_histogram: null argument");

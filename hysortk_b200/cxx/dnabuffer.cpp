@@ -31,7 +31,11 @@ DnaBuffer::DnaBuffer(const DnaBuffer& other) : store_(new uint8_t[other.capacity
     }
 }
 
-DnaBuffer::~DnaBuffer() { delete[] store_; }
+DnaBuffer::~DnaBuffer()
+{
+    if (on_release_) on_release_(store_);
+    delete[] store_;
+}
 
 size_t DnaBuffer::computebufsize(const std::vector<size_t>& seqlens)
 {

@@ -351,6 +351,15 @@ std::shared_ptr<DnaBuffer> read_dna_buffer(const std::string& fasta_fname, MPI_C
         if (map != MAP_FAILED) ::munmap(map, map_len);
     }
     auto dna = std::make_shared<DnaBuffer>(bufsize, lens.size(), buf, lens.data());   /* adopts buf */
+    /* page-lock the bytes: kmer_count then sends them to the GPU from where they are instead of staging
+     * them.  Failure is harmless (no GPU in this process, locked-memory limit): the buffer stays pageable. */
+    {
+        const char *pin = std::getenv("HSK_PIN_DNABUFFER");
+        if (bufsize >= (size_t(1) << 14) && !(pin && *pin == '0')) {
+            const int device = nranks > 1 ? local_device_for(rank) : (std::getenv("HSK_DEVICE") ? std::atoi(std::getenv("HSK_DEVICE")) : 0);
+            if (hsk_host_register(buf, bufsize, device) == 0) dna->set_release_hook([](uint8_t *p) { (void)hsk_host_unregister(p); });
+        }
+    }
     MPI_Barrier(comm);
 #if LOG_LEVEL >= 1
     if (rank == 0) {

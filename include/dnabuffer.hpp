@@ -29,6 +29,7 @@ class DnaBuffer
     const size_t capacity_;         // size of store_ in bytes
     size_t used_;                   // bytes taken by the reads appended so far
     std::vector<DnaSeq> reads_;     // views into store_, one per read
+    void (*on_release_)(uint8_t *) = nullptr;   // called with store_ before it is freed (see set_release_hook)
 
 public:
     // ---- construction ------------------------------------------------------------------------------
@@ -54,6 +55,11 @@ public:
     size_t getbufsize() const { return capacity_; }
     const uint8_t* getbufoffset(size_t i) const { return reads_[i].data(); }   /* first byte of read i */
     size_t getrangebufsize(size_t start, size_t count) const;                  /* bytes of reads [start, start+count) */
+
+    /* hysortk_b200 addition: `f(bytes)` is called right before the destructor frees the byte array.  read_dna_buffer
+     * page-locks the array of the buffer it returns (so that kmer_count sends it to the GPU from where it is) and uses
+     * the hook to undo that.  Not copied by the copy constructor. */
+    void set_release_hook(void (*f)(uint8_t *)) { on_release_ = f; }
 
     /* the reads as text, one per line */
     std::string getasciifilecontents() const;

@@ -155,6 +155,14 @@ int hsk_count_device(hsk_ctx *ctx, const uint8_t *d_packed, uint64_t nbytes, con
 /* Copies the last device result of the context to page-locked host arrays (hsk_result layout). */
 int hsk_fetch_result(hsk_ctx *ctx, hsk_result *out);
 
+/* Page-locks (cudaHostRegister, portable) / releases caller memory that will be handed to hsk_count repeatedly or is large:
+ * page-locked input goes to the GPU from where it is, pageable input is copied through the context's staging ring first.
+ * read_dna_buffer does this for the DnaBuffer it returns (the reference's FastaIndex::getmydna allocates it with new[],
+ * src/fastaindex.cpp:204-305).  `device`: the CUDA device of this rank.  Return 0 on success; failure (no GPU, no
+ * permission to lock that much memory) is harmless: the memory simply stays pageable. */
+int hsk_host_register(void *p, size_t bytes, int32_t device);
+int hsk_host_unregister(void *p);
+
 /* Sum of the per-rank histograms over all ranks (replaces the MPI_Allreduce of
  * hysortk.cpp:104,115); hist has upper+1 bins.  Collective. */
 int hsk_allreduce_histogram(hsk_ctx *ctx, uint64_t *hist);
