@@ -8,8 +8,11 @@
 //   filter_kmer       (kmerops.cpp:198-250)  -> bins.cu: one persistent kernel expands, counts, sorts and emits every
 //                                               bin; skewed bins go through expand.cu, radix.cu, count.cu (HBM path)
 // The reference's task system (TaskManager, classifier, dispatcher) has no equivalent here: bins are owned by rank in
-// contiguous ranges.  hsk_count additionally pipelines the host copies around the kernels (chunked H2D under the
-// extraction count pass, result groups streamed out while the bin kernel runs).
+// contiguous ranges.  hsk_count / hsk_count_stream additionally pipeline the host side around the kernels: the input goes
+// up in chunks under the extraction count pass (pageable memory through a ring of page-locked slots filled by the
+// context's host threads), the result leaves in groups of bins while the bin kernel runs and is handed to the caller's
+// sink by the context's delivery threads.  Memory: arena and staging area are limited by what is free; when that is short
+// the run list and the arena share one block (count_device).
 #include "../../include/hsk_capi.h"
 #include "kernels.cuh"
 
@@ -400,8 +403,8 @@ struct hsk_ctx {
     static constexpr u64 PIECE = 1ull << 20;
     HostBuf h_ring, h_len;
     std::vector<cudaEvent_t> ring_free;              // per ring slot: its last piece has left
-    std::unique_ptr<std::atomic<u32>[]> piece_enq;   // per piece: copy + event enqueued
-    std::unique_ptr<std::atomic<u32>[]> chunk_done;  // per extraction chunk: pieces enqueued
+    std::unique_ptr<std::atomic<u32>[]> chunk_sent;  // per extraction chunk: its H2D copy + event are enqueued
+    std::unique_ptr<std::atomic<u32>[]> chunk_done;  // per extraction chunk: pieces copied into its ring slot so far
     size_t flags_cap = 0;
     const u8 *in_host = nullptr;
     bool in_pageable = false;
@@ -1426,7 +1429,7 @@ static bool is_pageable(const void *p)
 static int stage_chunk(hsk_ctx *c, size_t ci)
 {
     if (!c->in_pageable) return 0;
-    while (!c->piece_enq[ci].load(std::memory_order_acquire)) {
+    while (!c->chunk_sent[ci].load(std::memory_order_acquire)) {
         if (c->stage_err.load()) return fail("staging the input failed: %s", cudaGetErrorString((cudaError_t)c->stage_err.load()));
         std::this_thread::yield();
     }
@@ -1510,10 +1513,10 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
     }
     if (c->flags_cap < nchunks) {
         c->flags_cap = nchunks * 2;
-        c->piece_enq.reset(new std::atomic<u32>[c->flags_cap]);    // per chunk: its copy + event are enqueued
+        c->chunk_sent.reset(new std::atomic<u32>[c->flags_cap]);    // per chunk: its copy + event are enqueued
         c->chunk_done.reset(new std::atomic<u32>[c->flags_cap]);   // per chunk: pieces copied into the slot
     }
-    for (u64 i = 0; i < nchunks; ++i) { c->piece_enq[i].store(0, std::memory_order_relaxed); c->chunk_done[i].store(0, std::memory_order_relaxed); }
+    for (u64 i = 0; i < nchunks; ++i) { c->chunk_sent[i].store(0, std::memory_order_relaxed); c->chunk_done[i].store(0, std::memory_order_relaxed); }
     c->stage_err.store(0);
     for (auto &x : c->stage_ns) x.store(0);
     const bool timing = g_trace.on;
@@ -1532,7 +1535,7 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
         cudaError_t e = cudaSuccess;
         if (ci >= nring && !c->stage_err.load(std::memory_order_relaxed)) {
             // the chunk that used the slot before must have left (pieces are taken in order: all of its pieces were taken earlier)
-            while (!c->piece_enq[ci - nring].load(std::memory_order_acquire)) std::this_thread::yield();
+            while (!c->chunk_sent[ci - nring].load(std::memory_order_acquire)) std::this_thread::yield();
             e = cudaEventSynchronize(c->ring_free[slot]);
         }
         u8 *dst = c->h_ring.as<u8>() + slot * chunk;
@@ -1547,7 +1550,7 @@ static int stage_input(hsk_ctx *c, const uint8_t *packed, uint64_t nbytes, const
                 if (e == cudaSuccess) e = cudaEventRecord(c->ring_free[slot], c->copy_stream);
                 if (e != cudaSuccess) c->stage_err.store((int)e);
             }
-            c->piece_enq[ci].store(1, std::memory_order_release);
+            c->chunk_sent[ci].store(1, std::memory_order_release);
         }
         if (timing) { const auto t3 = tick(); c->stage_ns[0] += ns(t1, t2); c->stage_ns[1] += ns(t2, t3); c->stage_ns[2] += ns(t0, t1); }
     });
