@@ -228,7 +228,6 @@ public:
         cv_.notify_all();
         for (auto &w : workers_) w.join();
     }
-    unsigned size() const { return n_; }
     // one job at a time: items 0 .. nitems-1 are handed to the threads in order; returns at once
     void start(u64 nitems, std::function<void(u64)> fn)
     {
