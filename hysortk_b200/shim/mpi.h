@@ -144,7 +144,12 @@ inline void wait_until(F cond, const char *what)
     unsigned spins = 0;
     double t0 = 0;
     while (!cond()) {
-        if (++spins < 200) { __builtin_ia32_pause(); continue; }
+        if (++spins < 200) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            continue;
+        }
         if (S.hdr && S.hdr->abort_code) _exit((int)S.hdr->abort_code);
         sched_yield();
         if ((spins & 0x3FF) == 0) {
