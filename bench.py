@@ -568,20 +568,31 @@ def main_ours(args):
     need_bytes = st["supermer_bytes"] + n_kept * (8 * nw + 4) + (n_occ * 8 if EXT else 0)
     ms_bins = st["ms_bins"]
     achieved = need_bytes / (ms_bins * 1e-3) / 1e9 if ms_bins > 0 else 0.0
-    traffic = issue_active = None
-    try:   # per-launch dram bytes / issue-slot utilisation of the kernel from the committed ncu --set full capture
+    traffic = issue_active = warp_inst = None
+    try:   # per-launch dram bytes / issue-slot utilisation / executed warp instructions of the kernel from the committed
+           # ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         traffic = tj.get(f"k_bin_count:{args.workload}:k{K}:ext{EXT}")
         issue_active = tj.get(f"k_bin_count:{args.workload}:k{K}:ext{EXT}:issue_active_pct")
+        warp_inst = tj.get(f"k_bin_count:{args.workload}:k{K}:ext{EXT}:warp_instructions")
     except (OSError, ValueError):
         pass
+    # the kernel's own ceiling: one warp instruction per scheduler and clock (4 schedulers per SM)
+    issue = None
+    if warp_inst and ms_bins > 0:
+        props = torch.cuda.get_device_properties(dev)
+        clock_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak_issue = props.multi_processor_count * 4 * clock_mhz * 1e6
+        issue = {"warp_instructions_per_launch": warp_inst, "achieved_warp_inst_per_s": warp_inst / (ms_bins * 1e-3),
+                 "peak_warp_inst_per_s": peak_issue, "frac": warp_inst / (ms_bins * 1e-3) / peak_issue,
+                 "note": "executed warp instructions of the ncu capture over this run's launch time, against SMs x 4 schedulers x SM clock"}
     roofline = {"bound": "issue+smem",
                 "kernel": "k_bin_count (expand + hash-count + sort one bin per CTA in shared memory; supermers read in place "
                           "from local HBM or from the peers over NVLink)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "algorithmic_bytes_per_launch": need_bytes, "ms_per_launch": ms_bins, "launches_per_step": 1,
-                "issue_active_pct_ncu": issue_active,
+                "issue_active_pct_ncu": issue_active, "issue": issue,
                 "note": "algorithmic bytes = what the kernel must move through HBM per launch: the supermer slots of the owned bins "
                         "in, the kept (k-mer, count[, occurrence]) entries out; the k-mer occurrences never leave the SM, so the "
                         "kernel is bound by instruction issue and shared-memory wavefronts, not by HBM (ncu: profiles/)",
