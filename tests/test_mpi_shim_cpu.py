@@ -38,3 +38,21 @@ def test_reference_as_mpi_job_matches_golden(name, nranks):
                                       threads_per_rank=2)
     po.assert_equal(c, g["expected"], f"reference, {nranks} MPI ranks")
     assert len(secs) == 1 and secs[0] > 0
+
+
+def test_reference_multi_round_exchange_matches_oracle():
+    """A read set large enough for many 80 KB exchange rounds per rank pair (the reference's MPI_Ialltoall / MPI_Wait loop
+    with a barrier in between, kmerops.cpp:814-968): the reference as a 4-rank job over the MPI stand-in equals the C
+    oracle, which has no notion of ranks."""
+    from hysortk_b200 import synth
+    if not po.ref_available(31, 17, 2, 50, 0):
+        pytest.skip("oracle/_ref not built")
+    rs = synth.sample_fixed(300_000, 15.0, 1000, 0.01, seed=12)
+    exp = po.kmer_count(rs.packed, rs.readlens, 31, 17, 2, 50, 0, via_supermers=False)
+    c, secs = po.ref_kmer_count_ranks(rs.packed, rs.readlens, 31, 17, 2, 50, 0, nranks=4, threads_per_rank=2)
+    po.assert_equal(c, exp, "reference, 4 MPI ranks, vs oracle")
+    # ... and the extension fields: global ReadIds come from the MPI_Exscan of the read counts (kmerops.cpp:65-70)
+    if po.ref_available(31, 17, 2, 50, 1):
+        exp1 = po.kmer_count(rs.packed, rs.readlens, 31, 17, 2, 50, 1, via_supermers=False)
+        c1, _ = po.ref_kmer_count_ranks(rs.packed, rs.readlens, 31, 17, 2, 50, 1, nranks=3, threads_per_rank=2)
+        po.assert_equal(c1, exp1, "reference EXT, 3 MPI ranks, vs oracle")
