@@ -439,8 +439,15 @@ void print_kmer_histogram(const KmerListS& kmerlist, MPI_Comm comm)
     /* counts never exceed UPPER_KMER_FREQ, so the histogram has a fixed size and the reference's
      * max-allreduce (hysortk.cpp:102-104) is not needed */
     std::vector<unsigned long long> histo(UPPER_KMER_FREQ + 1, 0);
-    for (const auto& e : kmerlist) {
-        if (e.cnt <= UPPER_KMER_FREQ) histo[e.cnt]++;
+    const size_t nent = kmerlist.size();
+    #pragma omp parallel if (nent > (size_t(1) << 16))
+    {
+        std::vector<unsigned long long> mine(UPPER_KMER_FREQ + 1, 0);   /* the list has millions of entries: one pass per thread */
+        #pragma omp for schedule(static) nowait
+        for (size_t i = 0; i < nent; ++i)
+            if (kmerlist[i].cnt <= UPPER_KMER_FREQ) mine[kmerlist[i].cnt]++;
+        #pragma omp critical
+        for (size_t c = 0; c < mine.size(); ++c) histo[c] += mine[c];
     }
     MPI_Allreduce(MPI_IN_PLACE, histo.data(), static_cast<int>(histo.size()), MPI_UNSIGNED_LONG_LONG, MPI_SUM, comm);
     int rank;
@@ -479,14 +486,14 @@ void write_output_file(const KmerListS& kmerlist, const std::string& output_dir,
         #pragma omp single
         nt = omp_get_num_threads();
     }
-    std::vector<std::string> part(static_cast<size_t>(nt));
-    for (size_t b0 = 0; b0 < n; b0 += BLOCK) {
+    /* two sets of per-thread strings: while block i is being written (by thread 0, inside the parallel region), the
+     * other threads already format block i + 1 */
+    std::vector<std::string> part[2] = {std::vector<std::string>(static_cast<size_t>(nt)), std::vector<std::string>(static_cast<size_t>(nt))};
+    auto format_block = [&](size_t b0, std::vector<std::string>& dst, size_t t, size_t nthr) {
         const size_t b1 = std::min(n, b0 + BLOCK);
-        #pragma omp parallel num_threads(nt)
         {
-            const size_t t = static_cast<size_t>(omp_get_thread_num());
-            const size_t lo = b0 + (b1 - b0) * t / nt, hi = b0 + (b1 - b0) * (t + 1) / nt;
-            std::string& out = part[t];
+            const size_t lo = b0 + (b1 - b0) * t / nthr, hi = b0 + (b1 - b0) * (t + 1) / nthr;
+            std::string& out = dst[t];
             out.clear();
             out.reserve((hi - lo) * (KMER_SIZE + 8));
             char line[KMER_SIZE + 24];
@@ -505,7 +512,20 @@ void write_output_file(const KmerListS& kmerlist, const std::string& output_dir,
                 out.append(line, static_cast<size_t>(len));
             }
         }
-        for (const std::string& sp : part) ofs.write(sp.data(), static_cast<std::streamsize>(sp.size()));
+    };
+    const size_t nblocks = (n + BLOCK - 1) / BLOCK;
+    #pragma omp parallel num_threads(nt)
+    {
+        const size_t t = static_cast<size_t>(omp_get_thread_num());
+        const size_t nthr = static_cast<size_t>(omp_get_num_threads());
+        if (nblocks) format_block(0, part[0], t, nthr);
+        #pragma omp barrier
+        for (size_t b = 0; b < nblocks; ++b) {
+            /* thread 0 writes block b; everybody (thread 0 afterwards) formats its share of block b + 1 into the other set */
+            if (t == 0) for (size_t u = 0; u < nthr; ++u) ofs.write(part[b & 1][u].data(), static_cast<std::streamsize>(part[b & 1][u].size()));
+            if (b + 1 < nblocks) format_block((b + 1) * BLOCK, part[(b + 1) & 1], t, nthr);
+            #pragma omp barrier
+        }
     }
 }
 
