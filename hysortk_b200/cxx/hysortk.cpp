@@ -191,6 +191,15 @@ struct ListBuilder {
         static_assert(sizeof(KmerListS) == 3 * sizeof(void *), "std::vector layout");
         KmerListEntryS *triple[3] = {base, base + n, base + cap};
         std::memcpy(static_cast<void *>(list.get()), triple, sizeof(triple));
+        if (list->data() != base || list->size() != n || list->capacity() != cap) {
+            /* not the layout we took it for: undo and take the portable way */
+            KmerListEntryS *none[3] = {nullptr, nullptr, nullptr};
+            std::memcpy(static_cast<void *>(list.get()), none, sizeof(none));
+            list->reserve(n);
+            for (uint64_t i = 0; i < n; ++i) list->push_back(std::move(base[i]));
+            release();
+            return list;
+        }
         base = nullptr; cap = 0;
         done.clear();
 #else
